@@ -1,0 +1,93 @@
+"""The checker itself: C restatement (oracle/jm_oracle.c) against (1) the committed golden vectors
+generated from the unmodified reference, and (2) the compiled reference oracle/_ref when present."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases as K
+import oracle
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat_sha256.json")))
+ALL = K.all_cases()
+
+
+def test_golden_covers_every_case():
+    assert set(GOLD) == {K.case_id(c) for c in ALL}
+    assert sum(1 for e in GOLD.values() if e["source"] == "reference") >= 100
+
+
+@pytest.mark.parametrize("c", ALL, ids=K.case_id)
+def test_port_matches_golden(c):
+    g = GOLD[K.case_id(c)]
+    r, n, out = K.run_case(oracle.port(), c)
+    assert (int(r), int(n), int(out.size)) == (g["ret"], g["out_len"], g["nbytes"])
+    assert K.sha(out) == g["sha256"]
+    if "hex" in g:
+        assert out.tobytes().hex() == g["hex"]
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref/libjmref.so not built")
+@pytest.mark.parametrize("c", [c for c in ALL if c["op"] in K.REF_OPS], ids=K.case_id)
+def test_port_matches_compiled_reference(c):
+    r1, n1, o1 = K.run_case(oracle.port(), c)
+    r2, n2, o2 = K.run_case(oracle.ref(), c)
+    assert (r1, n1) == (r2, n2)
+    assert np.array_equal(o1, o2)
+
+
+@pytest.mark.parametrize("chk", ["port", "ref"])
+def test_error_codes(chk):
+    if chk == "ref" and not oracle.have_ref():
+        pytest.skip("no compiled reference")
+    k = oracle.port() if chk == "port" else oracle.ref()
+    w, h, p = 16, 16, 32
+    s = np.zeros(p * h * 3 // 2, np.uint8)
+    out = np.full(w * h * 3 // 2, 0xA5, np.uint8)
+    need = w * h * 3 // 2
+    # nv_dec.cpp:757-758 no current frame; :768-771 NULL surface; :773-774 short buffer keeps *out_len
+    assert k.nvdec_output_frame(s, p, w, h, 1, out, need, have_frame=False) == (-1, need)
+    assert k.nvdec_output_frame(None, p, w, h, 1, out, need) == (-1, need)
+    assert k.nvdec_output_frame(s, p, w, h, 1, out, need - 1) == (-2, need - 1)
+    assert (out == 0xA5).all()
+    assert k.nvdec_output_frame(s, p, w, h, 1, out, need) == (need, need)      # :827 returns the byte count
+    # intel_dec.cpp:251-255 / :264-268 both zero *out_len
+    assert k.inteldec_output_frame(s, p * h, p, (0, 0, w, h), 1, out, need, have_surface=False) == (-1, 0)
+    assert k.inteldec_output_frame(s, p * h, p, (0, 0, w, h), 1, out, need - 1) == (-2, 0)
+    assert k.inteldec_output_frame(s, p * h, p, (0, 0, w, h), 1, out, need) == (0, need)
+    # intel_enc.cpp:254-259 no free surface
+    yuv = np.zeros(need, np.uint8)
+    surf = np.zeros(p * h * 3 // 2, np.uint8)
+    assert k.intelenc_input(yuv, 1, surf, p * h, p, (w, h), (0, 0, w, h), surface_free=False) == -1
+
+
+def test_i420_is_u_first():
+    """out_fmt 1 is really I420 -- even bytes of the UV row go to the FIRST plane."""
+    w, h, p = 8, 4, 16
+    s = np.zeros(p * h * 3 // 2, np.uint8)
+    uv = s[p * h:].reshape(-1, p)
+    uv[:, 0:w:2] = 10   # U
+    uv[:, 1:w:2] = 200  # V
+    out = np.zeros(w * h * 3 // 2, np.uint8)
+    oracle.port().nvdec_output_frame(s, p, w, h, 1, out, out.size)
+    assert (out[w * h: w * h + 8] == 10).all() and (out[w * h + 8:] == 200).all()
+
+
+def test_rgb_spec_known_points():
+    """Builder-defined BT.601 spec (parity unpinned): black, white, clamps."""
+    def px(y, u, v):
+        s = np.zeros(2 * 2 * 3 // 2 + 2, np.uint8)
+        s[0:4] = y
+        s[4], s[5] = u, v
+        o = np.zeros(12, np.uint8)
+        assert oracle.nv12_to_rgb24(s[:6].copy(), 2, 2, 2, o, 6) == 0
+        return tuple(int(x) for x in o[:3])
+    assert px(16, 128, 128) == (0, 0, 0)
+    assert px(235, 128, 128) == (255, 255, 255)
+    assert px(0, 128, 128) == (0, 0, 0)          # clamps below
+    assert px(255, 128, 128) == (255, 255, 255)  # clamps above
+    assert px(81, 90, 240) == (255, 0, 0)        # BT.601 red
+    assert px(145, 54, 34) == (0, 255, 1)        # BT.601 green: (386>>8)=1 by the integer formula
+    assert px(41, 240, 110) == (0, 0, 255)       # BT.601 blue
+    assert oracle.nv12_to_rgb24(np.zeros(4, np.uint8), 1, 1, 1, np.zeros(3, np.uint8), 3) == -1
