@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py -- NV12->I420 frames/s & HBM GB/s on 1..8 B200, next to the reference's CPU loop.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic decoded surfaces = ONE kernel
+launch (default workload: BASELINE.json configs[1], 300 pitched 1920x1080 NV12 surfaces, pitch
+2048 -> tight I420).  Per rank the batch is fixed (weak scaling: frames/streams are independent,
+ranks never exchange data; torch.distributed only carries the barrier and the max-over-ranks).
+
+  value     whole-job frames/s with the surfaces already resident in HBM (CUDA events on the
+            launching stream, max over ranks)
+  roofline  algorithmic bytes per launch / launch duration vs the measured HBM copy peak
+  e2e       same metric through the C-ABI pipeline with pinned HOST buffers: H2D of every surface,
+            convert, D2H of every tight frame inside the timed region
+  cpu_baseline / --impl reference
+            the UNMODIFIED reference function jm_nvdec_output_frame (nv_dec/nv_dec.cpp:750-828)
+            compiled into oracle/_ref, timed on this box's host cores on the same surfaces
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (op, w, h, pitch, frames per launch)
+    "nv12_to_i420_1080p_x300_pitch2048": ("i420", 1920, 1080, 2048, 300),
+    "nv12_to_i420_4k_x64_pitch4096": ("i420", 3840, 2160, 4096, 64),
+    "nv12_to_nv12_1080p_x300_pitch2048": ("nv12", 1920, 1080, 2048, 300),
+    "i420_to_nv12_1080p_x300_pitch2048": ("pack", 1920, 1080, 2048, 300),
+    "i420_to_nv12_4k_x64_pitch4096": ("pack", 3840, 2160, 4096, 64),
+    "nv12_to_rgb24_4k_x64_pitch4096": ("rgb", 3840, 2160, 4096, 64),
+    "nv12_to_i420_rgb24_4k_x64_pitch4096": ("fused", 3840, 2160, 4096, 64),
+}
+DEFAULT_WORKLOAD = "nv12_to_i420_1080p_x300_pitch2048"
+N_DISTINCT = 32          # distinct synthetic surfaces, tiled over the batch
+FALLBACK_HBM_GBS = 6650.0
+
+
+# ------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def recorded_traffic(workload):
+    """dram bytes per launch from the committed ncu --set full capture, or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    return rank, world, local
+
+
+def aggregate(units: int, ms: float, device):
+    """Whole-job units (sum over ranks) and the step time (MAX over ranks)."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return units, ms
+    t = torch.tensor([float(units)], dtype=torch.float64, device=device)
+    m = torch.tensor([float(ms)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    return int(round(t.item())), m.item()
+
+
+class ClockSampler:
+    """SM clock / throttle reasons sampled via NVML while the timed regions run."""
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz, self._run, self._on = [], set(), None, False, False
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                 "hw_thermal_slowdown": 0x40, "hw_power_brake_slowdown": 0x80}
+        while self._run:
+            if self._on:
+                try:
+                    self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                    except Exception:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                    for k, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(k)
+                except Exception:
+                    pass
+            time.sleep(0.002)
+
+    def start(self):
+        if self.nv:
+            self._run = True
+            self.t = threading.Thread(target=self._loop, daemon=True)
+            self.t.start()
+
+    def region(self, on):
+        self._on = on
+
+    def stop(self):
+        if self.nv and self._run:
+            self._run = False
+            self.t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+def make_inputs(op, w, h, pitch, rank):
+    from jmcodec_b200 import synth
+    if op == "pack":
+        return [synth.i420_frame(w, h, rank, f) for f in range(N_DISTINCT)]
+    return [synth.nv12_surface(w, h, pitch, rank, f) for f in range(N_DISTINCT)]
+
+
+def cpu_reference_fps(w, h, pitch, frames, threads, surfs=None):
+    """Time the reference's own CPU function (oracle/_ref, else the C port) on `frames` calls."""
+    import oracle
+    chk = oracle.best()
+    if surfs is None:
+        surfs = make_inputs("i420", w, h, pitch, 0)
+    S = np.stack(surfs)
+    out = np.zeros((max(N_DISTINCT, threads), w * h * 3 // 2), np.uint8)
+    chk.nvdec_run(S, out, pitch, w, h, 1, min(frames, 64), threads)          # warm-up: page in, spin up threads
+    t = chk.nvdec_run(S, out, pitch, w, h, 1, frames, threads)
+    return frames / t, chk.kind
+
+
+def run_reference_arm(args, name):
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return 0
+    op, w, h, pitch, n = WORKLOADS[name]
+    if op != "i420":
+        print(json.dumps({"impl": "reference", "unavailable": "the reference has CPU code only for NV12->I420/NV12 on this path"}))
+        return 0
+    threads = len(os.sched_getaffinity(0))
+    surfs = make_inputs("i420", w, h, pitch, 0)
+    # one step = one batch of n frames over all host threads (one reference handle per thread)
+    for _ in range(max(args.warmup, 1)):
+        cpu_reference_fps(w, h, pitch, n, threads, surfs)
+    import oracle
+    chk = oracle.best()
+    S = np.stack(surfs)
+    out = np.zeros((max(N_DISTINCT, threads), w * h * 3 // 2), np.uint8)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        chk.nvdec_run(S, out, pitch, w, h, 1, n, threads)
+    dt = time.perf_counter() - t0
+    fps = n * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "NV12->I420 frames/s", "value": fps, "unit": "frames/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": name, "width": w, "height": h, "pitch": pitch, "frames_per_step": n},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": chk.kind,
+                         "sample": f"{args.steps} steps x {n} frames, jm_nvdec_output_frame out_fmt=1, one handle per thread, "
+                                   f"{N_DISTINCT} distinct surfaces"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------
+def build_job(ctx, op, w, h, pitch, n, d_in, d_out, d_out2):
+    surf_bytes = pitch * h * 3 // 2
+    tight_bytes = w * h * 3 // 2
+    if op in ("i420", "nv12"):
+        j = ctx.job_nvdec(w, h, pitch, 1 if op == "i420" else 0)
+        j.surf.base, j.surf.stride, j.tight.base, j.tight.stride = d_in, surf_bytes, d_out, tight_bytes
+    elif op == "pack":
+        j = ctx.job_nvenc(w, h, pitch, 0x10)
+        j.tight.base, j.tight.stride, j.surf.base, j.surf.stride = d_in, tight_bytes, d_out, surf_bytes
+    else:
+        j = ctx.job_rgb(w, h, pitch, 3 * w, op == "fused")
+        j.surf.base, j.surf.stride = d_in, surf_bytes
+        if op == "fused":
+            j.tight.base, j.tight.stride, j.rgb.base, j.rgb.stride = d_out, tight_bytes, d_out2, 3 * w * h
+        else:
+            j.rgb.base, j.rgb.stride = d_out, 3 * w * h
+    j.n_frames = n
+    return j
+
+
+def io_bytes(op, w, h, pitch):
+    surf_bytes, tight_bytes, rgb = pitch * h * 3 // 2, w * h * 3 // 2, 3 * w * h
+    if op == "pack":
+        return tight_bytes, surf_bytes, 0
+    if op == "rgb":
+        return surf_bytes, rgb, 0
+    if op == "fused":
+        return surf_bytes, tight_bytes, rgb
+    return surf_bytes, tight_bytes, 0
+
+
+def device_only(ctx, name, rank, iters, warmup):
+    """Device-timed launches of one workload with inputs resident in HBM.  Returns a dict."""
+    op, w, h, pitch, n = WORKLOADS[name]
+    in_b, out_b, out2_b = io_bytes(op, w, h, pitch)
+    host = np.concatenate([make_inputs(op, w, h, pitch, rank)[f % N_DISTINCT] for f in range(min(n, N_DISTINCT))])
+    d_in = ctx.alloc(in_b * n)
+    reps = -(-n // N_DISTINCT)
+    for r in range(reps):                        # tile the distinct surfaces over the batch
+        cnt = min(N_DISTINCT, n - r * N_DISTINCT)
+        ctx.h2d(d_in + r * N_DISTINCT * in_b, host, cnt * in_b)
+    d_out = ctx.alloc(out_b * n)
+    d_out2 = ctx.alloc(out2_b * n) if out2_b else None
+    if op == "pack":
+        ctx.memset(d_out, 0, out_b * n)
+    j = build_job(ctx, op, w, h, pitch, n, d_in, d_out, d_out2)
+    for _ in range(warmup):
+        ctx.convert(j)
+    ctx.sync()
+    ms = ctx.convert_timed(j, iters)
+    alg = ctx.algorithmic_bytes(j) * n
+    res = {"ms_per_launch": ms, "frames_per_s": n / (ms * 1e-3), "algorithmic_bytes_per_launch": alg,
+           "gbs": alg / (ms * 1e-3) / 1e9}
+    for d in (d_in, d_out, d_out2):
+        if d:
+            ctx.free(d)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel table and the CPU baseline")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    name = args.workload
+    if args.impl == "reference":
+        return run_reference_arm(args, name)
+
+    rank, world, local = dist_env()
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- jmcodec_b200 has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import jmcodec_b200 as J
+
+    op, w, h, pitch, n = WORKLOADS[name]
+    in_b, out_b, out2_b = io_bytes(op, w, h, pitch)
+    ctx = J.Ctx(local)
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- inputs: pinned host copy of the whole batch (the e2e leg streams from here) ---------------
+    distinct = make_inputs(op, w, h, pitch, rank)
+    hin = ctx.alloc_host(in_b * n)
+    for f in range(n):
+        hin.array[f * in_b:(f + 1) * in_b] = distinct[f % N_DISTINCT]
+    hout = ctx.alloc_host(out_b * n)
+    hout2 = ctx.alloc_host(out2_b * n) if out2_b else None
+    d_in = ctx.alloc(in_b * n)
+    d_out = ctx.alloc(out_b * n)
+    d_out2 = ctx.alloc(out2_b * n) if out2_b else None
+    ctx.h2d(d_in, hin.array)
+    ctx.memset(d_out, 0, out_b * n)
+    job = build_job(ctx, op, w, h, pitch, n, d_in, d_out, d_out2)
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident: W warm-up steps, then exactly K timed steps ------------------------------
+    for _ in range(args.warmup):
+        ctx.convert(job)
+    barrier()
+    l0 = ctx.launches
+    sampler.region(True)
+    ms_total = ctx.convert_timed(job, args.steps) * args.steps
+    sampler.region(False)
+    launches = ctx.launches - l0
+    barrier()
+    units, ms_max = aggregate(n * args.steps, ms_total, dev)
+    value = units / (ms_max * 1e-3)
+    ms_per_step = ms_max / args.steps
+    alg_launch = ctx.algorithmic_bytes(job) * n
+    achieved = alg_launch / ((ms_total / args.steps) * 1e-3) / 1e9          # this rank's kernel, GB/s
+    peak, peak_src = peaks()
+
+    # ---- correctness spot-check on rank 0 (bit-exact vs the reference function) ---------------------
+    verified = None
+    if rank == 0 and op in ("i420", "nv12"):
+        import oracle
+        chk = oracle.best()
+        got = np.empty(out_b, np.uint8)
+        want = np.empty(out_b, np.uint8)
+        verified = True
+        for f in (0, n // 2, n - 1):
+            ctx.d2h(got, d_out + f * out_b)
+            chk.nvdec_output_frame(distinct[f % N_DISTINCT], pitch, w, h, 1 if op == "i420" else 0, want, out_b)
+            verified = verified and bool(np.array_equal(got, want))
+
+    # ---- e2e: pinned host surfaces -> H2D -> convert -> D2H tight frames, overlapped ----------------
+    sub = 30 if n % 30 == 0 else (16 if n % 16 == 0 else n)       # frames per pipeline batch
+    shape = build_job(ctx, op, w, h, pitch, sub, None, None, None)
+    pipe = J.Pipeline(ctx, shape, pitch * h * 3 // 2, depth=3)
+    ev0, ev1 = J.Event(ctx), J.Event(ctx)
+
+    def e2e_step():
+        for b in range(n // sub):
+            pipe.submit(hin.array[b * sub * in_b:], hout.array[b * sub * out_b:], sub,
+                        host_out2=hout2.array[b * sub * out2_b:] if hout2 else None)
+
+    for _ in range(args.warmup):
+        e2e_step()
+    pipe.drain()
+    barrier()
+    h0, d0 = pipe.h2d_bytes, pipe.d2h_bytes
+    sampler.region(True)
+    ev0.record(1)                                  # upload stream: first H2D of the timed region
+    for _ in range(args.steps):
+        e2e_step()
+    ev1.record(2)                                  # delivery stream: after the last D2H
+    e2e_ms = ev0.elapsed_ms(ev1)
+    pipe.drain()
+    sampler.region(False)
+    barrier()
+    e2e_units, e2e_ms_max = aggregate(n * args.steps, e2e_ms, dev)
+    e2e_value = e2e_units / (e2e_ms_max * 1e-3)
+    h2d_step = (pipe.h2d_bytes - h0) // args.steps
+    d2h_step = (pipe.d2h_bytes - d0) // args.steps
+    if rank == 0 and verified is not None:
+        import oracle
+        want = np.empty(out_b, np.uint8)
+        oracle.best().nvdec_output_frame(distinct[(n - 1) % N_DISTINCT], pitch, w, h, 1 if op == "i420" else 0, want, out_b)
+        verified = verified and bool(np.array_equal(hout.array[(n - 1) * out_b:n * out_b], want))
+    sampler.stop()
+    pipe.close()
+
+    # ---- extras on rank 0, N=1: per-kernel device table + CPU baseline ------------------------------
+    kernels, cpu = None, None
+    if rank == 0 and world == 1 and not args.no_extras:
+        for d in (d_in, d_out, d_out2):
+            if d:
+                ctx.free(d)
+        d_in = d_out = d_out2 = None
+        kernels = {}
+        for k in WORKLOADS:
+            r = device_only(ctx, k, rank, 10, 3)
+            kernels[k] = {"frames_per_s": round(r["frames_per_s"], 1), "gbs": round(r["gbs"], 1),
+                          "frac_of_peak": round(r["gbs"] / peak, 4), "ms_per_launch": round(r["ms_per_launch"], 4)}
+        threads = len(os.sched_getaffinity(0))
+        if op == "i420":
+            f1, kind = cpu_reference_fps(w, h, pitch, 1500, 1, distinct)
+            fN, _ = cpu_reference_fps(w, h, pitch, 300 * max(1, min(threads, 64)), threads, distinct)
+            cpu = {"value": fN, "unit": "frames/s", "cores": threads, "kind": kind,
+                   "value_1thread": f1,
+                   "sample": f"jm_nvdec_output_frame out_fmt=1 on {w}x{h} pitch {pitch}: 1500 frames on 1 thread, "
+                             f"{300 * max(1, min(threads, 64))} frames on {threads} threads (one handle per thread), "
+                             f"{N_DISTINCT} distinct surfaces"}
+
+    if rank == 0:
+        line = {
+            "metric": "NV12->I420 frames/s" if op == "i420" else f"{name} frames/s",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": name, "width": w, "height": h, "pitch": pitch, "frames_per_step_per_gpu": n,
+                       "launches_per_step": 1, "l2": f"batch {in_b * n / 1e6:.0f} MB in + {out_b * n / 1e6:.0f} MB out per step > 126 MB L2, no flush needed",
+                       "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": recorded_traffic(name), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": alg_launch},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
+                    "ms_per_step": e2e_ms_max / args.steps, "frames_per_pipeline_batch": sub, "pipeline_depth": 3,
+                    "pcie_gbs_each_way": [h2d_step / (e2e_ms_max / args.steps * 1e-3) / 1e9, d2h_step / (e2e_ms_max / args.steps * 1e-3) / 1e9]},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "verified_bit_exact": verified,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        if kernels:
+            line["kernels"] = kernels
+        print(json.dumps(line))
+    for b in (hin, hout, hout2):
+        if b:
+            b.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

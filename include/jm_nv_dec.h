@@ -1,0 +1,122 @@
+/*
+ * jm_nv_dec.h -- drop-in for the reference's nv_dec/jm_nv_dec.h (the jm_nvdec_* decoder API).
+ *
+ * Same eleven entry points, argument meaning and return conventions as the reference
+ * (nv_dec/jm_nv_dec.h:27-88, bodies nv_dec/nv_dec.cpp:695-870), so the call sequences of
+ * test_nv_dec/test_nv_dec.cpp:163-259 and test_player/test_player.cpp:204-258 compile and behave
+ * the same.  Differences, all additive:
+ *   - exports are extern "C" with default visibility (the reference's are MSVC C++-mangled
+ *     _declspec(dllexport), jm_nv_dec.h:14-17, so its binary ABI was never portable);
+ *   - the decoded-surface format path behind jm_nvdec_decode_frame / jm_nvdec_output_frame runs
+ *     as sm_100a CUDA kernels (NV12 -> tight NV12 / I420 on the device, only the tight frame
+ *     crosses PCIe) instead of cuMemcpyDtoH of the padded surface + a CPU loop
+ *     (nv_dec.cpp:452, :782-820);
+ *   - codec_type JM_NVDEC_CODEC_RAW_NV12 accepts already-decoded pitched NV12 surfaces as
+ *     "packets" (host bytes or a device pointer), which is how the path is exercised where no
+ *     NVDEC bitstream front-end is available;
+ *   - jm_nvdec_set_device() picks the GPU (the reference hard-codes device 0, nv_dec.cpp:209).
+ * There is no CPU fallback: without a CUDA device jm_nvdec_init fails.
+ */
+#ifndef _JM_NV_DECODER_H_
+#define _JM_NV_DECODER_H_
+
+#include <stdint.h>
+#ifndef __cplusplus
+#include <stdbool.h>
+#endif
+
+#ifndef JMDLL_FUNC
+#if defined(__GNUC__)
+#define JMDLL_FUNC __attribute__((visibility("default")))
+#else
+#define JMDLL_FUNC
+#endif
+#define JMDLL_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *handle_nvdec;
+
+/* codec_type values of jm_nvdec_init (enum NV_CODEC_TYPE, nv_dec/nv_dec.h:37-46) */
+#define JM_NVDEC_CODEC_AVC    0
+#define JM_NVDEC_CODEC_HEVC   1
+#define JM_NVDEC_CODEC_MJPEG  2
+#define JM_NVDEC_CODEC_MPEG4  3
+#define JM_NVDEC_CODEC_MPEG2  4
+#define JM_NVDEC_CODEC_VP8    5
+#define JM_NVDEC_CODEC_VP9    6
+#define JM_NVDEC_CODEC_VC1    7
+/* extension: every "packet" is one decoded surface (struct jm_nvdec_raw_packet) */
+#define JM_NVDEC_CODEC_RAW_NV12 100
+
+#define JM_NVDEC_RAW_MAGIC 0x53524D4Au      /* "JMRS" */
+#define JM_NVDEC_RAW_DEVICE_PTR 1u          /* flags: surface already in device memory at device_ptr */
+
+/* What cuvidMapVideoFrame hands the reference (a device pointer + pitch, nv_dec.cpp:439-442),
+ * as a packet.  Without JM_NVDEC_RAW_DEVICE_PTR the header is followed by pitch*height*3/2
+ * bytes of pitched NV12 (Y rows, then UV rows from row `height`, nv_dec.cpp:453,765). */
+typedef struct jm_nvdec_raw_packet {
+    uint32_t magic;
+    int32_t  width, height, pitch;
+    uint32_t flags;
+    uint32_t reserved;
+    uint64_t device_ptr;
+} jm_nvdec_raw_packet;
+
+/** create decode handle (new + zero, no CUDA; nv_dec.cpp:54-60) */
+JMDLL_FUNC handle_nvdec jm_nvdec_create_handle(void);
+
+/**
+ *   Init decode before use (nv_dec.cpp:62-80).
+ *   codec_type: 0 - H.264, 1 - H.265 ... 7 - VC1, or JM_NVDEC_CODEC_RAW_NV12
+ *   out_fmt:    0 - NV12, anything else - "YV12", which the reference writes U-plane-first,
+ *               i.e. I420 (nv_dec.cpp:814-815)
+ *   extra_data: sps/pps buffer, NULL is OK
+ *   return: 0 - successful, else failed (-2 no CUDA device, -3 bad device id as
+ *           nvdec_cuda_init nv_dec.cpp:219-231; -4 no NVDEC parser library for a bitstream codec)
+ */
+JMDLL_FUNC int jm_nvdec_init(int codec_type, int out_fmt, char *extra_data, int len, handle_nvdec handle);
+
+/** destroy decode handle (nv_dec.cpp:82-110); the handle is invalid afterwards */
+JMDLL_FUNC int jm_nvdec_deinit(handle_nvdec handle);
+
+/**
+ *   decode video frame (nv_dec.cpp:481-494): consumes in_buf before returning; in_data_len == 0
+ *   (or in_buf == NULL) flushes / signals end of stream; *got_frame = 1 if a frame is ready for
+ *   jm_nvdec_output_frame.  At most one frame per call.  Always returns 0, like the reference.
+ */
+JMDLL_FUNC int jm_nvdec_decode_frame(unsigned char *in_buf, int in_data_len, int *got_frame, handle_nvdec handle);
+
+/**
+ *   fetch the frame announced by got_frame (nv_dec.cpp:750-828).
+ *   out_len [in] capacity of out_buf, [out] frame size w*h*3/2.
+ *   return: w*h*3/2 (>0, NOT 0 -- nv_dec.cpp:827) on success; -1 no frame / NULL buffer;
+ *           -2 capacity too small (*out_len left untouched, :773-774).
+ *   out_buf may be pageable (as in the reference) or pinned (jm_nvdec_memory_alloc_host): a pinned
+ *   buffer receives the frame by direct DMA.
+ */
+JMDLL_FUNC int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec handle);
+
+/** display size of the stream, valid after the first decoded frame (nv_dec.cpp:839-846) */
+JMDLL_FUNC int jm_nvdec_stream_info(int *disp_width, int *disp_height, handle_nvdec handle);
+
+JMDLL_FUNC void jm_nvdec_set_eof(bool is_eof, handle_nvdec handle);
+JMDLL_FUNC bool jm_nvdec_is_exit(handle_nvdec handle);
+/** info block built when the stream is drained (nv_dec.cpp:663-683); owned by the handle */
+JMDLL_FUNC char *jm_nvdec_show_dec_info(handle_nvdec handle);
+JMDLL_FUNC bool jm_nvdec_is_hw_support(void);
+
+/* ---- extensions ---------------------------------------------------------------------------- */
+/** choose the CUDA device before jm_nvdec_init (default 0, or env JMC_DEVICE) */
+JMDLL_FUNC int jm_nvdec_set_device(int device, handle_nvdec handle);
+/** pinned host memory for out_buf (mirror of jm_nvenc_memory_alloc_host, jmnv_enc.h:65-66) */
+JMDLL_FUNC int jm_nvdec_memory_alloc_host(void **buf, int buf_len, handle_nvdec handle);
+JMDLL_FUNC int jm_nvdec_memory_release_host(void *buf, handle_nvdec handle);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* _JM_NV_DECODER_H_ */

@@ -1,0 +1,164 @@
+/*
+ * jmc_kernels.cu -- turns a jmc_job into ONE kernel launch (see jmc_kernels.cuh for the kernels).
+ */
+#include "jmc_internal.h"
+#include "jmc_kernels.cuh"
+
+using namespace jmc;
+
+typedef Cfg256x4 PlaneCfg;
+
+static FrameSet to_set(const jmc_frames &f)
+{
+    FrameSet s;
+    s.base = (uint8_t *)f.base;
+    s.stride = f.stride;
+    s.list = (uint8_t *const *)f.list;
+    return s;
+}
+
+static bool frames_ok(const jmc_frames &f) { return f.base != nullptr || f.list != nullptr; }
+
+static Part make_part(int kind, uint32_t rows, uint32_t row_elems, int64_t p_off, int32_t pitch, int64_t a_off, int64_t b_off)
+{
+    Part p;
+    p.kind = (rows && row_elems) ? kind : PART_NONE;
+    p.rows = rows;
+    p.row_elems = row_elems;
+    const uint64_t total = (uint64_t)rows * row_elems;
+    p.tiles = (uint32_t)((total + TileGeom<PlaneCfg>::TILE_ELEMS - 1) / TileGeom<PlaneCfg>::TILE_ELEMS);
+    p.p_off = p_off;
+    p.p_pitch = pitch;
+    p.pad_ = 0;
+    p.a_off = a_off;
+    p.b_off = b_off;
+    /* fast_div(): m = ceil(2^sh / d), sh = 31 + ceil(log2 d) */
+    const uint32_t d = row_elems ? row_elems : 1;
+    uint32_t s = 0;
+    while ((1ull << s) < d) s++;
+    p.rdiv.d = d;
+    p.rdiv.sh = 31 + s;
+    p.rdiv.m = (uint32_t)(((1ull << (31 + s)) + d - 1) / d);
+    p.rdiv.pad_ = 0;
+    return p;
+}
+
+/* Can the host prove that every access of this job is 16-byte aligned?  (1080p, 4K, 720p ... are.) */
+static bool all_wide(const jmc_job *j, const PlaneParams &p)
+{
+    uint64_t bits = 0;
+    const jmc_frames *sets[2] = { &j->surf, &j->tight };
+    for (int i = 0; i < 2; i++) {
+        if (sets[i]->list) { if (!(j->flags & JMC_JOB_ALIGNED16)) return false; }
+        else bits |= (uint64_t)(uintptr_t)sets[i]->base | (uint64_t)sets[i]->stride;
+    }
+    for (int i = 0; i < 2; i++) {
+        const Part &pt = p.part[i];
+        if (pt.kind == PART_NONE) continue;
+        bits |= (uint64_t)pt.p_off | (uint64_t)(uint32_t)pt.p_pitch | (uint64_t)pt.a_off | pt.row_elems;
+        if (pt.kind != PART_COPY) bits |= (uint64_t)pt.b_off;
+    }
+    return (bits & 15) == 0;
+}
+
+static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
+{
+    if (!frames_ok(j->surf) || !frames_ok(j->tight)) { jmc_set_error("jmc_convert: surf/tight frame set is empty"); return JMC_ERR_INVALID; }
+    const uint32_t w = (uint32_t)j->width, h = (uint32_t)j->height;
+    PlaneParams p;
+    p.pitched = to_set(j->surf);
+    p.tight = to_set(j->tight);
+    p.n_frames = (uint32_t)j->n_frames;
+    p.to_tight = (j->op == JMC_OP_NV12_TO_NV12 || j->op == JMC_OP_NV12_TO_I420) ? 1 : 0;
+    /* luma: h rows of w bytes (nv_dec.cpp:787-790,801-804; intel_enc.cpp:291-295; nv_enc.cpp:1043-1051) */
+    p.part[0] = make_part(PART_COPY, h, w, j->surf_y_off, j->pitch, 0, 0);
+    if (j->op == JMC_OP_NV12_TO_NV12 || j->op == JMC_OP_NV12_TO_SURF) {
+        /* chroma kept interleaved: h>>1 rows of w bytes at tight offset w*h (nv_dec.cpp:792-796) */
+        p.part[1] = make_part(PART_COPY, h >> 1, w, j->surf_uv_off, j->pitch, (int64_t)w * h, 0);
+    } else {
+        /* (h>>1) x (w>>1) chroma pairs (nv_dec.cpp:807-818; intel_enc.cpp:366-380) */
+        p.part[1] = make_part(j->op == JMC_OP_NV12_TO_I420 ? PART_SPLIT : PART_MERGE, h >> 1, w >> 1,
+                              j->surf_uv_off, j->pitch, j->tight_u_off, j->tight_v_off);
+    }
+    p.tiles_per_frame = p.part[0].tiles + p.part[1].tiles;
+    const uint64_t total = (uint64_t)p.tiles_per_frame * p.n_frames;
+    if (total == 0) return JMC_OK;
+    if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }
+    p.total_tiles = (uint32_t)total;
+    const uint32_t max_grid = (uint32_t)ctx->sm_count * PlaneCfg::BLOCKS_PER_SM;
+    const uint32_t grid = p.total_tiles < max_grid ? p.total_tiles : max_grid;
+    const bool wide = all_wide(j, p);
+    const int k1 = p.part[1].kind == PART_NONE ? PART_COPY : p.part[1].kind;
+#define JMC_LAUNCH(TT, K1)                                                                               \
+    do {                                                                                                 \
+        if (wide) planes_kernel<PlaneCfg, TT, K1, true><<<grid, PlaneCfg::THREADS, 0, stream>>>(p);      \
+        else planes_kernel<PlaneCfg, TT, K1, false><<<grid, PlaneCfg::THREADS, 0, stream>>>(p);          \
+    } while (0)
+    if (p.to_tight) {
+        if (k1 == PART_SPLIT) JMC_LAUNCH(true, PART_SPLIT); else JMC_LAUNCH(true, PART_COPY);
+    } else {
+        if (k1 == PART_MERGE) JMC_LAUNCH(false, PART_MERGE); else JMC_LAUNCH(false, PART_COPY);
+    }
+#undef JMC_LAUNCH
+    JMC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return JMC_OK;
+}
+
+static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
+{
+    const bool fused = j->op == JMC_OP_NV12_TO_I420_RGB24;
+    if (!frames_ok(j->surf) || !frames_ok(j->rgb) || (fused && !frames_ok(j->tight))) {
+        jmc_set_error("jmc_convert: surf/rgb/tight frame set is empty");
+        return JMC_ERR_INVALID;
+    }
+    if ((j->width >> 1) < 1 || (j->height >> 1) < 1) { jmc_set_error("jmc_convert: RGB needs width,height >= 2"); return JMC_ERR_INVALID; }
+    if (j->rgb_pitch < 3 * j->width) { jmc_set_error("jmc_convert: rgb_pitch < 3*width"); return JMC_ERR_INVALID; }
+    RgbParams p;
+    p.surf = to_set(j->surf);
+    p.tight = to_set(j->tight);
+    p.rgb = to_set(j->rgb);
+    p.n_frames = (uint32_t)j->n_frames;
+    p.width = j->width; p.height = j->height; p.pitch = j->pitch;
+    p.y_off = j->surf_y_off; p.uv_off = j->surf_uv_off;
+    p.u_off = j->tight_u_off; p.v_off = j->tight_v_off;
+    p.rgb_pitch = j->rgb_pitch;
+    p.fused = fused ? 1 : 0;
+    p.segs_per_row = ((uint32_t)j->width + 511) / 512;
+    p.row_pairs = ((uint32_t)j->height + 1) / 2;
+    p.tasks_per_frame = p.segs_per_row * p.row_pairs;
+    const uint64_t total = (uint64_t)p.tasks_per_frame * p.n_frames;
+    if (total == 0) return JMC_OK;
+    if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }
+    p.total_tasks = (uint32_t)total;
+    constexpr uint32_t WARPS = RgbCfg::THREADS / 32;
+    const uint32_t blocks_needed = (p.total_tasks + WARPS - 1) / WARPS;
+    const uint32_t max_grid = (uint32_t)ctx->sm_count * RgbCfg::BLOCKS_PER_SM;
+    const uint32_t grid = blocks_needed < max_grid ? blocks_needed : max_grid;
+    rgb_kernel<RgbCfg><<<grid, RgbCfg::THREADS, 0, stream>>>(p);
+    JMC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return JMC_OK;
+}
+
+int jmc_launch_job(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
+{
+    if (!ctx || !j) { jmc_set_error("jmc_convert: NULL ctx/job"); return JMC_ERR_INVALID; }
+    if (j->n_frames < 0 || j->width < 0 || j->height < 0 || j->pitch < 0) { jmc_set_error("jmc_convert: negative geometry"); return JMC_ERR_INVALID; }
+    if ((uint64_t)j->width * (uint64_t)j->height > 0x7fffffffull) { jmc_set_error("jmc_convert: frame too large"); return JMC_ERR_INVALID; }
+    if (j->n_frames == 0 || j->width == 0 || j->height == 0) return JMC_OK;
+    if (j->pitch < j->width) { jmc_set_error("jmc_convert: pitch %d < width %d", j->pitch, j->width); return JMC_ERR_INVALID; }
+    switch (j->op) {
+    case JMC_OP_NV12_TO_NV12:
+    case JMC_OP_NV12_TO_I420:
+    case JMC_OP_NV12_TO_SURF:
+    case JMC_OP_I420_TO_SURF:
+        return launch_planes(ctx, j, stream);
+    case JMC_OP_NV12_TO_RGB24:
+    case JMC_OP_NV12_TO_I420_RGB24:
+        return launch_rgb(ctx, j, stream);
+    default:
+        jmc_set_error("jmc_convert: unknown op %d", j->op);
+        return JMC_ERR_INVALID;
+    }
+}

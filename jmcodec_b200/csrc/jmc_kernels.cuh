@@ -1,0 +1,545 @@
+/*
+ * jmc_kernels.cuh -- sm_100a kernels for the decoded-surface format path.
+ *
+ * Everything here is HBM-bound byte movement (arithmetic intensity ~0; ~6 int-ops/B for RGB),
+ * so the design rules are: 16-byte coalesced vector accesses, several independent loads in
+ * flight per thread before the first store, a persistent grid sized in multiples of the SM
+ * count looping over fixed-size tiles, ONE launch per batch of frames, no tensor cores.
+ *
+ * Two kernels:
+ *   planes_kernel : 2-D copy (strip/add pitch), U/V de-interleave (prmt 0x6420/0x7531) and
+ *                   interleave (prmt 0x5140/0x7362).  Replaces the CPU loops of
+ *                   nv_dec/nv_dec.cpp:782-820, intel_dec/intel_dec.cpp:284-314,
+ *                   intel_enc/intel_enc.cpp:291-307,366-380 and the InterleaveUV launch of
+ *                   nv_enc/nv_enc.cpp:1041-1081.
+ *   rgb_kernel    : NV12 -> RGB24 (integer BT.601, dp2a + cvt.pack.sat) with optional fused I420
+ *                   output; RGB rows are staged through shared memory so that every global
+ *                   store instruction writes 512 contiguous bytes.
+ *
+ * The vector width of every (frame, plane) is chosen INSIDE the kernel from the actual
+ * addresses/pitches (block-uniform branch), so odd sizes, odd crops and arbitrary pointer lists
+ * are always correct and aligned geometries (1080p, 4K) always take the 16-byte path.
+ */
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace jmc {
+
+struct FrameSet {
+    uint8_t *base;
+    size_t stride;
+    uint8_t *const *list;
+};
+
+__device__ __forceinline__ uint8_t *frame_ptr(const FrameSet &s, uint32_t f)
+{
+    return s.list ? s.list[f] : s.base + (size_t)f * s.stride;
+}
+
+/* ---- division by a launch-invariant divisor ------------------------------------------------
+ * floor(n / d) for n < 2^31 as (n * m) >> sh with m = ceil(2^sh / d), sh = 31 + ceil(log2 d):
+ * the error term n*e/(d*2^sh), e < d <= 2^(sh-31), stays below 1/d.  Two instructions instead of
+ * the ~20 of a generic 32-bit divide, four times per thread per tile. */
+struct FastDiv {
+    uint32_t m, sh, d, pad_;
+};
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv &f)
+{
+    return (uint32_t)(((uint64_t)n * f.m) >> f.sh);
+}
+
+enum PartKind : int32_t { PART_NONE = 0, PART_COPY = 1, PART_SPLIT = 2, PART_MERGE = 3 };
+
+/* One plane-level piece of work per frame.  "Elements" are bytes of a row (COPY) or chroma
+ * sample pairs of a row (SPLIT / MERGE).  The tight side is always contiguous: element e of the
+ * part lives at tight_frame + a_off + e (COPY; SPLIT/MERGE first chroma plane) and b_off + e
+ * (second chroma plane). */
+struct Part {
+    int32_t kind;
+    uint32_t rows;
+    uint32_t row_elems;
+    uint32_t tiles;      /* ceil(rows*row_elems / TILE_ELEMS) */
+    int64_t p_off;       /* pitched side: offset of the part's first byte from the frame pointer */
+    int32_t p_pitch;
+    int32_t pad_;
+    int64_t a_off;
+    int64_t b_off;
+    FastDiv rdiv;        /* division by row_elems */
+};
+
+struct PlaneParams {
+    FrameSet pitched;
+    FrameSet tight;
+    uint32_t n_frames;
+    int32_t to_tight;    /* 1: pitched -> tight (decode side), 0: tight -> pitched (encode side) */
+    uint32_t tiles_per_frame;
+    uint32_t total_tiles;
+    Part part[2];
+};
+
+/* ------------------------------------------------------------------------------------------ */
+/* memory access helpers.  LD policy 0: ld.global.nc  1: + L1::no_allocate  2: ld.global.cs      */
+/*                         ST policy 0: st.global     1: st.global.cs       2: L1::no_allocate   */
+template <int POL> __device__ __forceinline__ uint4 ld16(const void *p)
+{
+    uint4 r;
+    if (POL == 1)
+        asm("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else if (POL == 2)
+        asm("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    else
+        asm("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+template <int POL> __device__ __forceinline__ uint2 ld8(const void *p)
+{
+    uint2 r;
+    if (POL == 1)
+        asm("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    else if (POL == 2)
+        asm("ld.global.cs.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    else
+        asm("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+template <int POL> __device__ __forceinline__ void st16(void *p, uint4 v)
+{
+    if (POL == 1)
+        asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else if (POL == 2)
+        asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+    else
+        asm volatile("st.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+template <int POL> __device__ __forceinline__ void st8(void *p, uint2 v)
+{
+    if (POL == 1)
+        asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+    else if (POL == 2)
+        asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+    else
+        asm volatile("st.global.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+/* A V-byte chunk held in registers (V = 16, 8, 4, 2, 1). */
+template <int V> struct Chunk {
+    uint32_t w[(V + 3) / 4];
+};
+
+template <int V, int LDP> __device__ __forceinline__ Chunk<V> load_chunk(const uint8_t *p)
+{
+    Chunk<V> c;
+    if (V == 16) { uint4 t = ld16<LDP>(p); c.w[0] = t.x; c.w[1] = t.y; c.w[2] = t.z; c.w[3] = t.w; }
+    else if (V == 8) { uint2 t = ld8<LDP>(p); c.w[0] = t.x; c.w[1] = t.y; }
+    else if (V == 4) c.w[0] = __ldg((const uint32_t *)p);
+    else if (V == 2) c.w[0] = __ldg((const uint16_t *)p);
+    else c.w[0] = __ldg(p);
+    return c;
+}
+template <int V, int STP> __device__ __forceinline__ void store_chunk(uint8_t *p, const Chunk<V> &c)
+{
+    if (V == 16) st16<STP>(p, make_uint4(c.w[0], c.w[1], c.w[2], c.w[3]));
+    else if (V == 8) st8<STP>(p, make_uint2(c.w[0], c.w[1]));
+    else if (V == 4) *(uint32_t *)p = c.w[0];
+    else if (V == 2) *(uint16_t *)p = (uint16_t)c.w[0];
+    else *p = (uint8_t)c.w[0];
+}
+
+/* largest power-of-two vector width (<=16) dividing every bit set in `bits` */
+__device__ __forceinline__ int vec_width(uint64_t bits)
+{
+    uint32_t low = (uint32_t)bits & 15u;
+    if (low == 0) return 16;
+    return (int)(low & (0u - low));
+}
+
+struct Cfg256x4 {
+    static constexpr int THREADS = 256;
+    static constexpr int UNROLL = 4;      /* 16-byte vectors per thread in flight */
+    static constexpr int LDP = 1;
+    static constexpr int STP = 0;
+    static constexpr int BLOCKS_PER_SM = 4;
+};
+
+template <class C> struct TileGeom {
+    static constexpr uint32_t TILE_ELEMS = (uint32_t)C::THREADS * C::UNROLL * 16u;
+};
+
+/* ---- COPY: rows x row_elems bytes between a pitched and a contiguous plane ----------------
+ * Element e (a byte of the contiguous side) sits at row e / row_elems, column e % row_elems of
+ * the pitched side.  Loads of a thread's UNROLL chunks are issued back to back (indices clamped
+ * into the tile so no load is conditional), then the stores, predicated on the real bound. */
+template <class C, int V, bool TO_TIGHT>
+__device__ __forceinline__ void copy_tile(uint8_t *pitched, uint32_t pitch, uint8_t *tight,
+                                          const FastDiv &rd, uint32_t e0, uint32_t e1)
+{
+    constexpr uint32_t STEP = (uint32_t)C::THREADS * V;
+#pragma unroll 1
+    for (uint32_t base = e0 + threadIdx.x * V; base < e1; base += STEP * C::UNROLL) {
+        Chunk<V> r[C::UNROLL];
+        uint32_t e[C::UNROLL];
+        size_t poff[C::UNROLL];
+#pragma unroll
+        for (int k = 0; k < C::UNROLL; k++) {
+            e[k] = base + k * STEP;
+            const uint32_t ec = min(e[k], e1 - V);
+            const uint32_t row = fast_div(ec, rd);
+            poff[k] = (size_t)row * pitch + (ec - row * rd.d);
+            r[k] = TO_TIGHT ? load_chunk<V, C::LDP>(pitched + poff[k]) : load_chunk<V, C::LDP>(tight + ec);
+        }
+#pragma unroll
+        for (int k = 0; k < C::UNROLL; k++) {
+            if (e[k] < e1) {
+                if (TO_TIGHT) store_chunk<V, C::STP>(tight + e[k], r[k]);
+                else store_chunk<V, C::STP>(pitched + poff[k], r[k]);
+            }
+        }
+    }
+}
+
+/* ---- SPLIT: interleaved UV rows -> two contiguous chroma planes (V bytes per plane per chunk) */
+template <int V> __device__ __forceinline__ void deinterleave(const Chunk<V> &lo, const Chunk<V> &hi, Chunk<V> &u, Chunk<V> &v)
+{
+    /* lo|hi hold 2V interleaved bytes U0 V0 U1 V1 ...; V >= 4 here */
+#pragma unroll
+    for (int i = 0; i < V / 4; i++) {
+        const uint32_t a = (2 * i < V / 4) ? lo.w[2 * i] : hi.w[2 * i - V / 4];
+        const uint32_t b = (2 * i + 1 < V / 4) ? lo.w[2 * i + 1] : hi.w[2 * i + 1 - V / 4];
+        u.w[i] = __byte_perm(a, b, 0x6420);
+        v.w[i] = __byte_perm(a, b, 0x7531);
+    }
+}
+template <int V> __device__ __forceinline__ void interleave(const Chunk<V> &u, const Chunk<V> &v, Chunk<V> &lo, Chunk<V> &hi)
+{
+#pragma unroll
+    for (int i = 0; i < V / 4; i++) {
+        const uint32_t a = __byte_perm(u.w[i], v.w[i], 0x5140);
+        const uint32_t b = __byte_perm(u.w[i], v.w[i], 0x7362);
+        if (2 * i < V / 4) lo.w[2 * i] = a; else hi.w[2 * i - V / 4] = a;
+        if (2 * i + 1 < V / 4) lo.w[2 * i + 1] = b; else hi.w[2 * i + 1 - V / 4] = b;
+    }
+}
+
+/* elements are chroma sample pairs: pair e is bytes 2*(e % row_elems), +1 of UV row e / row_elems */
+template <class C, int V>
+__device__ __forceinline__ void split_tile(const uint8_t *uv, uint32_t pitch, uint8_t *pu, uint8_t *pv,
+                                           const FastDiv &rd, uint32_t e0, uint32_t e1)
+{
+    constexpr uint32_t STEP = (uint32_t)C::THREADS * V;
+    constexpr int U2 = (V == 16) ? (C::UNROLL + 1) / 2 : C::UNROLL;   /* 2V bytes are loaded per chunk */
+#pragma unroll 1
+    for (uint32_t base = e0 + threadIdx.x * V; base < e1; base += STEP * U2) {
+        Chunk<V> lo[U2], hi[U2];
+        uint32_t e[U2];
+#pragma unroll
+        for (int k = 0; k < U2; k++) {
+            e[k] = base + k * STEP;
+            const uint32_t ec = min(e[k], e1 - V);
+            const uint32_t row = fast_div(ec, rd);
+            const uint8_t *s = uv + (size_t)row * pitch + 2 * (size_t)(ec - row * rd.d);
+            if (V >= 4) {
+                lo[k] = load_chunk<V, C::LDP>(s);
+                hi[k] = load_chunk<V, C::LDP>(s + V);
+            } else if (V == 2) {
+                lo[k].w[0] = __ldg((const uint32_t *)s);
+            } else {
+                lo[k].w[0] = __ldg(s);
+                hi[k].w[0] = __ldg(s + 1);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < U2; k++) {
+            if (e[k] < e1) {
+                Chunk<V> u, v;
+                if (V >= 4) deinterleave<V>(lo[k], hi[k], u, v);
+                else if (V == 2) { u.w[0] = __byte_perm(lo[k].w[0], 0, 0x4420); v.w[0] = __byte_perm(lo[k].w[0], 0, 0x4431); }
+                else { u.w[0] = lo[k].w[0]; v.w[0] = hi[k].w[0]; }
+                store_chunk<V, C::STP>(pu + e[k], u);
+                store_chunk<V, C::STP>(pv + e[k], v);
+            }
+        }
+    }
+}
+
+/* ---- MERGE: two contiguous chroma planes -> interleaved UV rows ----------------------------- */
+template <class C, int V>
+__device__ __forceinline__ void merge_tile(uint8_t *uv, uint32_t pitch, const uint8_t *pu, const uint8_t *pv,
+                                           const FastDiv &rd, uint32_t e0, uint32_t e1)
+{
+    constexpr uint32_t STEP = (uint32_t)C::THREADS * V;
+    constexpr int U2 = (V == 16) ? (C::UNROLL + 1) / 2 : C::UNROLL;
+#pragma unroll 1
+    for (uint32_t base = e0 + threadIdx.x * V; base < e1; base += STEP * U2) {
+        Chunk<V> u[U2], v[U2];
+        uint32_t e[U2];
+#pragma unroll
+        for (int k = 0; k < U2; k++) {
+            e[k] = base + k * STEP;
+            const uint32_t ec = min(e[k], e1 - V);
+            u[k] = load_chunk<V, C::LDP>(pu + ec);
+            v[k] = load_chunk<V, C::LDP>(pv + ec);
+        }
+#pragma unroll
+        for (int k = 0; k < U2; k++) {
+            if (e[k] < e1) {
+                const uint32_t row = fast_div(e[k], rd);
+                uint8_t *d = uv + (size_t)row * pitch + 2 * (size_t)(e[k] - row * rd.d);
+                if (V >= 4) {
+                    Chunk<V> lo, hi;
+                    interleave<V>(u[k], v[k], lo, hi);
+                    store_chunk<V, C::STP>(d, lo);
+                    store_chunk<V, C::STP>(d + V, hi);
+                } else if (V == 2) {
+                    *(uint32_t *)d = __byte_perm(u[k].w[0], v[k].w[0], 0x5140);
+                } else {
+                    d[0] = (uint8_t)u[k].w[0];
+                    d[1] = (uint8_t)v[k].w[0];
+                }
+            }
+        }
+    }
+}
+
+#define JMC_DISPATCH_V(vw, CALL)            \
+    switch (vw) {                           \
+    case 16: { constexpr int V = 16; CALL; } break; \
+    case 8:  { constexpr int V = 8;  CALL; } break; \
+    case 4:  { constexpr int V = 4;  CALL; } break; \
+    case 2:  { constexpr int V = 2;  CALL; } break; \
+    default: { constexpr int V = 1;  CALL; } break; \
+    }
+
+/* vector width usable for a SPLIT/MERGE part: chunks of V bytes on every side, except V == 2
+ * which moves one 4-byte word on the interleaved side */
+__device__ __forceinline__ int chroma_vec_width(uint64_t pbits, uint64_t tbits)
+{
+    int vw = vec_width(pbits | tbits);
+    if (vw == 2 && (pbits & 3)) vw = 1;
+    return vw;
+}
+
+/* TO_TIGHT: 1 = pitched -> tight (decode side), 0 = tight -> pitched (encode side).
+ * KIND1: what part[1] is (PART_COPY, PART_SPLIT or PART_MERGE); part[0] is always a COPY.
+ * WIDE_ONLY: the host has proved every address/pitch/size 16-byte aligned (the 1080p / 4K case):
+ * only the 16-byte path is compiled in, which keeps the register count low. */
+template <class C, bool TO_TIGHT, int KIND1, bool WIDE_ONLY>
+__global__ void __launch_bounds__(C::THREADS, WIDE_ONLY ? C::BLOCKS_PER_SM : 2) planes_kernel(const __grid_constant__ PlaneParams p)
+{
+    constexpr uint32_t TILE = TileGeom<C>::TILE_ELEMS;
+    for (uint32_t t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const uint32_t f = t / p.tiles_per_frame;
+        uint32_t r = t - f * p.tiles_per_frame;
+        const bool second = r >= p.part[0].tiles;
+        if (second) r -= p.part[0].tiles;
+        uint8_t *pf = frame_ptr(p.pitched, f);
+        uint8_t *tp = frame_ptr(p.tight, f);
+        const uint32_t e0 = r * TILE;
+        if (!second || KIND1 == PART_COPY) {
+            const Part &pt = second ? p.part[1] : p.part[0];
+            const uint32_t e1 = min(e0 + TILE, pt.rows * pt.row_elems);
+            const uint32_t pitch = (uint32_t)pt.p_pitch;
+            uint8_t *pp = pf + pt.p_off, *a = tp + pt.a_off;
+            if (WIDE_ONLY) {
+                copy_tile<C, 16, TO_TIGHT>(pp, pitch, a, pt.rdiv, e0, e1);
+            } else {
+                const int vw = vec_width((uint64_t)(uintptr_t)pp | (uint64_t)(uintptr_t)a | pitch | pt.row_elems);
+                JMC_DISPATCH_V(vw, (copy_tile<C, V, TO_TIGHT>(pp, pitch, a, pt.rdiv, e0, e1)))
+            }
+        } else {
+            const Part &pt = p.part[1];
+            const uint32_t e1 = min(e0 + TILE, pt.rows * pt.row_elems);
+            const uint32_t pitch = (uint32_t)pt.p_pitch;
+            uint8_t *pp = pf + pt.p_off, *a = tp + pt.a_off, *b = tp + pt.b_off;
+            if (WIDE_ONLY) {
+                if (KIND1 == PART_SPLIT) split_tile<C, 16>(pp, pitch, a, b, pt.rdiv, e0, e1);
+                else merge_tile<C, 16>(pp, pitch, a, b, pt.rdiv, e0, e1);
+            } else {
+                const int vw = chroma_vec_width((uint64_t)(uintptr_t)pp | pitch,
+                                                (uint64_t)(uintptr_t)a | (uint64_t)(uintptr_t)b | pt.row_elems);
+                if (KIND1 == PART_SPLIT) { JMC_DISPATCH_V(vw, (split_tile<C, V>(pp, pitch, a, b, pt.rdiv, e0, e1))) }
+                else                     { JMC_DISPATCH_V(vw, (merge_tile<C, V>(pp, pitch, a, b, pt.rdiv, e0, e1))) }
+            }
+        }
+    }
+}
+
+/* ========================================================================================== */
+/* NV12 -> RGB24 (+ optional I420)                                                            */
+/* ========================================================================================== */
+struct RgbParams {
+    FrameSet surf, tight, rgb;
+    uint32_t n_frames;
+    int32_t width, height, pitch;
+    int64_t y_off, uv_off;
+    int64_t u_off, v_off;      /* tight I420 plane offsets (fused only) */
+    int32_t rgb_pitch;
+    int32_t fused;
+    uint32_t segs_per_row;     /* ceil(width / 512): one warp covers 512 pixels of a row pair */
+    uint32_t row_pairs;        /* ceil(height / 2) */
+    uint32_t tasks_per_frame;  /* row_pairs * segs_per_row */
+    uint32_t total_tasks;
+};
+
+/* d = c + a.lo16 * b.byte[0|2] + a.hi16 * b.byte[1|3]   (signed 16-bit coefficients x unsigned bytes) */
+__device__ __forceinline__ int dp2a_lo(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ int dp2a_hi(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+/* (sat_u16(a) << 16) | sat_u16(b).  clip8(x >> 8) == sat_u16(x) >> 8, so the result bytes we want
+ * are byte 3 (from a) and byte 1 (from b). */
+__device__ __forceinline__ uint32_t pack_sat_u16(int a, int b)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u16.s32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+/* BT.601 limited range, integer:  x_r = 298(Y-16)+409(V-128)+128, etc. */
+constexpr int RGB_CR = -298 * 16 - 409 * 128 + 128;
+constexpr int RGB_CG = -298 * 16 + 100 * 128 + 208 * 128 + 128;
+constexpr int RGB_CB = -298 * 16 - 516 * 128 + 128;
+constexpr uint32_t COEF_RV = (409u << 16);                              /* 0*U + 409*V   */
+constexpr uint32_t COEF_GUV = ((uint32_t)(uint16_t)(-100)) | ((uint32_t)(uint16_t)(-208) << 16);
+constexpr uint32_t COEF_BU = 516u;                                      /* 516*U + 0*V   */
+constexpr uint32_t COEF_Y_EVEN = 298u;                                  /* picks byte 0 / 2 */
+constexpr uint32_t COEF_Y_ODD = (298u << 16);                           /* picks byte 1 / 3 */
+
+/* 4 pixels (one Y word) + their 2 chroma pairs (one UV word) -> 12 RGB bytes in 3 words */
+__device__ __forceinline__ void rgb4(uint32_t yw, int r0, int g0, int b0, int r1, int g1, int b1, uint32_t *out)
+{
+    const int R0 = dp2a_lo(COEF_Y_EVEN, yw, r0), G0 = dp2a_lo(COEF_Y_EVEN, yw, g0), B0 = dp2a_lo(COEF_Y_EVEN, yw, b0);
+    const int R1 = dp2a_lo(COEF_Y_ODD, yw, r0), G1 = dp2a_lo(COEF_Y_ODD, yw, g0), B1 = dp2a_lo(COEF_Y_ODD, yw, b0);
+    const int R2 = dp2a_hi(COEF_Y_EVEN, yw, r1), G2 = dp2a_hi(COEF_Y_EVEN, yw, g1), B2 = dp2a_hi(COEF_Y_EVEN, yw, b1);
+    const int R3 = dp2a_hi(COEF_Y_ODD, yw, r1), G3 = dp2a_hi(COEF_Y_ODD, yw, g1), B3 = dp2a_hi(COEF_Y_ODD, yw, b1);
+    out[0] = __byte_perm(pack_sat_u16(G0, R0), pack_sat_u16(R1, B0), 0x7531);   /* R0 G0 B0 R1 */
+    out[1] = __byte_perm(pack_sat_u16(B1, G1), pack_sat_u16(G2, R2), 0x7531);   /* G1 B1 R2 G2 */
+    out[2] = __byte_perm(pack_sat_u16(R3, B2), pack_sat_u16(B3, G3), 0x7531);   /* B2 R3 G3 B3 */
+}
+
+__device__ __forceinline__ uint8_t clip8_dev(int v) { return (uint8_t)min(max(v, 0), 255); }
+
+struct RgbCfg {
+    static constexpr int THREADS = 256;
+    static constexpr int BLOCKS_PER_SM = 4;
+    static constexpr int LDP = 1;
+    static constexpr int STP = 0;
+};
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const __grid_constant__ RgbParams p)
+{
+    constexpr int WARPS = C::THREADS / 32;
+    __shared__ __align__(16) uint8_t stage[WARPS][32 * 48];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t warps_total = gridDim.x * WARPS;
+    const int w = p.width, h = p.height, cw = w >> 1, ch = h >> 1;
+
+    for (uint32_t task = blockIdx.x * WARPS + wib; task < p.total_tasks; task += warps_total) {
+        const uint32_t f = task / p.tasks_per_frame;
+        const uint32_t r = task - f * p.tasks_per_frame;
+        const uint32_t rp = r / p.segs_per_row, seg = r - rp * p.segs_per_row;
+        const uint8_t *sp = frame_ptr(p.surf, f);
+        uint8_t *rgbp = frame_ptr(p.rgb, f);
+        uint8_t *tp = p.fused ? frame_ptr(p.tight, f) : nullptr;
+        const uint32_t y0 = rp * 2;
+        const bool two = (y0 + 1 < (uint32_t)h);
+        const uint32_t cy = min(rp, (uint32_t)(ch - 1));
+        const uint8_t *yrow = sp + p.y_off + (size_t)y0 * p.pitch;
+        const uint8_t *crow = sp + p.uv_off + (size_t)cy * p.pitch;
+        uint8_t *orow = rgbp + (size_t)y0 * p.rgb_pitch;
+
+        uint64_t bits = (uint64_t)(uintptr_t)(sp + p.y_off) | (uint64_t)(uintptr_t)(sp + p.uv_off) | (uint32_t)p.pitch |
+                        (uint64_t)(uintptr_t)rgbp | (uint32_t)p.rgb_pitch | (uint32_t)w;
+        bool fast = (bits & 15) == 0;
+        if (p.fused)
+            fast = fast && (((uint64_t)(uintptr_t)tp & 15) == 0) && (((uint64_t)(uintptr_t)(tp + p.u_off) | (uint64_t)(uintptr_t)(tp + p.v_off)) & 7) == 0;
+
+        if (fast) {
+            const uint32_t units_row = (uint32_t)w >> 4;
+            const uint32_t unit = seg * 32 + lane;
+            const uint32_t nvalid = min(32u, units_row - seg * 32);      /* lanes with work in this warp */
+            const bool act = lane < nvalid;
+            uint4 ya = make_uint4(0, 0, 0, 0), yb = ya, uv = ya;
+            if (act) {
+                ya = ld16<C::LDP>(yrow + unit * 16);
+                uv = ld16<C::LDP>(crow + unit * 16);
+                if (two) yb = ld16<C::LDP>(yrow + p.pitch + unit * 16);
+            }
+            if (p.fused && act) {
+                st16<C::STP>(tp + (size_t)y0 * w + unit * 16, ya);
+                if (two) st16<C::STP>(tp + (size_t)(y0 + 1) * w + unit * 16, yb);
+                if (rp < (uint32_t)ch) {
+                    uint2 u, v;
+                    u.x = __byte_perm(uv.x, uv.y, 0x6420); v.x = __byte_perm(uv.x, uv.y, 0x7531);
+                    u.y = __byte_perm(uv.z, uv.w, 0x6420); v.y = __byte_perm(uv.z, uv.w, 0x7531);
+                    st8<C::STP>(tp + p.u_off + (size_t)rp * cw + unit * 8, u);
+                    st8<C::STP>(tp + p.v_off + (size_t)rp * cw + unit * 8, v);
+                }
+            }
+            /* chroma terms of the 8 pairs this thread owns */
+            int cr[8], cg[8], cb[8];
+            const uint32_t uvw[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                cr[2 * j] = dp2a_lo(COEF_RV, uvw[j], RGB_CR);  cr[2 * j + 1] = dp2a_hi(COEF_RV, uvw[j], RGB_CR);
+                cg[2 * j] = dp2a_lo(COEF_GUV, uvw[j], RGB_CG); cg[2 * j + 1] = dp2a_hi(COEF_GUV, uvw[j], RGB_CG);
+                cb[2 * j] = dp2a_lo(COEF_BU, uvw[j], RGB_CB);  cb[2 * j + 1] = dp2a_hi(COEF_BU, uvw[j], RGB_CB);
+            }
+            uint8_t *st = stage[wib];
+#pragma unroll
+            for (int row = 0; row < 2; row++) {
+                if (row == 1 && !two) break;
+                const uint4 yy = row ? yb : ya;
+                const uint32_t yw[4] = {yy.x, yy.y, yy.z, yy.w};
+                uint32_t o[12];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    rgb4(yw[j], cr[2 * j], cg[2 * j], cb[2 * j], cr[2 * j + 1], cg[2 * j + 1], cb[2 * j + 1], o + 3 * j);
+                __syncwarp();
+                uint4 *s4 = (uint4 *)(st + lane * 48);
+                s4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                s4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                s4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+                __syncwarp();
+                uint8_t *g = orow + (size_t)row * p.rgb_pitch + (size_t)seg * (32 * 48);
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    const uint32_t c = k * 32 + lane;                 /* 16-byte chunk of the warp's 1536-byte span */
+                    if (c < nvalid * 3) st16<C::STP>(g + c * 16, *(const uint4 *)(st + c * 16));
+                }
+            }
+        } else {
+            /* any geometry: one pixel per lane per step, byte accesses */
+            const uint32_t x_begin = seg * 512, x_end = min((uint32_t)w, x_begin + 512);
+            for (uint32_t x = x_begin + lane; x < x_end; x += 32) {
+                const uint32_t cx = min(x >> 1, (uint32_t)(cw - 1));
+                const int U = crow[2 * cx], V = crow[2 * cx + 1];
+                const int d = U - 128, e = V - 128;
+                for (uint32_t row = 0; row < (two ? 2u : 1u); row++) {
+                    const int Y = yrow[(size_t)row * p.pitch + x];
+                    const int c = Y - 16;
+                    uint8_t *o = orow + (size_t)row * p.rgb_pitch + 3 * (size_t)x;
+                    o[0] = clip8_dev((298 * c + 409 * e + 128) >> 8);
+                    o[1] = clip8_dev((298 * c - 100 * d - 208 * e + 128) >> 8);
+                    o[2] = clip8_dev((298 * c + 516 * d + 128) >> 8);
+                    if (p.fused) tp[(size_t)(y0 + row) * w + x] = (uint8_t)Y;
+                }
+                if (p.fused && rp < (uint32_t)ch && (x & 1) == 0 && (x >> 1) < (uint32_t)cw) {
+                    tp[p.u_off + (size_t)rp * cw + (x >> 1)] = (uint8_t)U;
+                    tp[p.v_off + (size_t)rp * cw + (x >> 1)] = (uint8_t)V;
+                }
+            }
+        }
+    }
+}
+
+} /* namespace jmc */

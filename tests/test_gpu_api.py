@@ -1,0 +1,244 @@
+"""GPU tests of the drop-in API (jm_nvdec_*, jm_nvenc_*), the delivery pipeline, and full-size
+size-independent properties.  Written to read like a port of test_nv_dec.cpp's call sequence."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle
+from jmcodec_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def J():
+    import jmcodec_b200
+    return jmcodec_b200
+
+
+@pytest.fixture(scope="module")
+def ctx(J):
+    c = J.Ctx(0)
+    yield c
+    c.close()
+
+
+# --------------------------------------------------------------------------------------------
+# jm_nvdec_*: create / init / decode_frame / output_frame / deinit  (test_nv_dec.cpp:163-259)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("out_fmt", [0, 1])
+@pytest.mark.parametrize("geom", [(1920, 1080, 2048), (1919, 1079, 2048), (64, 48, 64), (2, 2, 256)])
+def test_nvdec_api_matches_reference_function(J, out_fmt, geom):
+    w, h, pitch = geom
+    chk = oracle.best()
+    assert J.load().jm_nvdec_is_hw_support()
+    dec = J.NvDec()
+    assert dec.init(J.NvDec.CODEC_RAW_NV12, out_fmt) == 0
+    need = w * h * 3 // 2
+    cap = need + 64
+    out = np.full(cap, synth.OUT_FILL, np.uint8)
+    # nothing decoded yet: the reference returns -1 (nv_dec.cpp:757-758)
+    assert dec.output_frame(out, cap) == (-1, cap)
+    frames = 0
+    for f in range(6):
+        s = synth.nv12_surface(w, h, pitch, 11, f)
+        pkt = J.NvDec.raw_packet(s, w, h, pitch)
+        r, got = dec.decode_frame(pkt)
+        assert (r, got) == (0, 1)
+        assert dec.stream_info() == (w, h)
+        # short buffer: -2 and *out_len untouched (nv_dec.cpp:773-774)
+        assert dec.output_frame(out, need - 1) == (-2, need - 1)
+        out[:] = synth.OUT_FILL
+        want = out.copy()
+        assert dec.output_frame(out, cap) == chk.nvdec_output_frame(s, pitch, w, h, out_fmt, want, cap) == (need, need)
+        assert np.array_equal(out, want)
+        frames += 1
+    # flush: len 0 => end of stream; no frame left => is_exit + info block (nv_dec.cpp:389-392,460-466)
+    assert not dec.is_exit()
+    assert dec.decode_frame(None, 0) == (0, 0)
+    assert dec.is_exit()
+    info = dec.show_dec_info()
+    assert f"Frame Count:\t{frames}" in info and f"Display:\t{w} x {h}" in info
+    assert ("NV12" if out_fmt == 0 else "YV12") in info
+    assert dec.deinit() == 0
+
+
+def test_nvdec_api_queue_and_pinned_and_device_packets(J, ctx):
+    """Several packets before fetching (display queue, one frame out per call), pinned out_buf (direct
+    DMA) and device-pointer packets (what cuvidMapVideoFrame yields)."""
+    w, h, pitch = 320, 180, 512
+    need = w * h * 3 // 2
+    chk = oracle.best()
+    dec = J.NvDec(0)
+    assert dec.init(J.NvDec.CODEC_RAW_NV12, 1) == 0
+    pinned = dec.alloc_host(need)
+    out = np.ctypeslib.as_array((C.c_uint8 * need).from_address(pinned))
+    surfs = [synth.nv12_surface(w, h, pitch, 12, f) for f in range(4)]
+    dptr = ctx.upload(surfs[3])
+    assert dec.decode_frame(J.NvDec.raw_packet(surfs[0], w, h, pitch)) == (0, 1)       # frame 0 ready
+    want = np.empty(need, np.uint8)
+    for nxt, cur in ((1, 0), (2, 1)):
+        # decode the next packet BEFORE fetching: the fetched frame is the newest announced one
+        assert dec.decode_frame(J.NvDec.raw_packet(surfs[nxt], w, h, pitch)) == (0, 1)
+        assert dec.output_frame(out, need) == (need, need)
+        chk.nvdec_output_frame(surfs[nxt], pitch, w, h, 1, want, need)
+        assert np.array_equal(out, want)
+    assert dec.decode_frame(J.NvDec.raw_packet(None, w, h, pitch, device_ptr=dptr)) == (0, 1)
+    assert dec.output_frame(out, need) == (need, need)
+    chk.nvdec_output_frame(surfs[3], pitch, w, h, 1, want, need)
+    assert np.array_equal(out, want)
+    # garbage packet: consumed, no frame, still returns 0 like the reference's swallowed errors
+    assert dec.decode_frame(np.zeros(64, np.uint8)) == (0, 0)
+    dec.free_host(pinned)
+    dec.deinit()
+    ctx.free(dptr)
+
+
+def test_nvdec_bitstream_codecs_fail_loudly(J):
+    dec = J.NvDec()
+    assert dec.init(0, 1) != 0           # H.264 needs the NVDEC parser front-end: no silent fallback
+    assert dec.decode_frame(np.zeros(16, np.uint8)) == (0, 0)
+    dec.deinit()
+
+
+# --------------------------------------------------------------------------------------------
+# jm_nvenc_*: encoder input path (surface-only on B200)
+# --------------------------------------------------------------------------------------------
+def test_nvenc_needs_surface_only_mode(J):
+    enc = J.NvEnc()
+    assert enc.init(64, 64, J.NvEnc.FMT_NV12, codec_id=0) == 1      # NV_ENC_ERR_NO_ENCODE_DEVICE
+    enc.deinit()
+
+
+@pytest.mark.parametrize("fmt", ["nv12", "yv12", "argb"])
+@pytest.mark.parametrize("geom", [(1920, 1080), (1280, 720), (354, 290), (64, 64)])
+def test_nvenc_api_upload(J, ctx, fmt, geom):
+    w, h = geom
+    code = {"nv12": J.NvEnc.FMT_NV12, "yv12": J.NvEnc.FMT_YV12, "argb": J.NvEnc.FMT_ARGB}[fmt]
+    enc = J.NvEnc(0)
+    assert enc.init(w, h, code) == 0
+    assert enc.peek_surface()[0] == -1
+    assert enc.enc_frame(None, 0) == (0, 0)                          # EOS before anything: fine
+    n_in = w * h * 4 if fmt == "argb" else w * h * 3 // 2
+    for f in range(3):
+        src = synth.random_bytes(n_in, synth.frame_key(13, f))
+        assert enc.enc_frame(src) == (0, 0)                          # uploaded + packed, no packet (no NVENC)
+        assert enc.get_bitstream() == (-1, 0)
+        r, dptr, pitch, rows = enc.peek_surface()
+        assert r == 0 and pitch >= (w * 4 if fmt == "argb" else w)
+        got = np.empty(pitch * rows, np.uint8)
+        ctx.d2h(got, dptr)
+        want = np.zeros(pitch * rows, np.uint8)                      # surfaces are zeroed at init
+        if fmt == "argb":
+            # the reference's flat copy ignores the pitch (nv_enc.cpp:1096); we honour it
+            want.reshape(rows, pitch)[:, :w * 4] = src.reshape(h, w * 4)
+        else:
+            assert oracle.nvenc_upload(src, code, w, h, want, pitch) == 0
+        assert np.array_equal(got, want)
+    # surfaces stay locked until released, exactly 10 of them (MAX_NV_ENC_FRAME_NUM, nv_enc.cpp:916-927,90-93)
+    src = synth.random_bytes(n_in, 1)
+    for _ in range(7):
+        assert enc.enc_frame(src)[0] == 0
+    assert enc.enc_frame(src)[0] == -1
+    assert enc.release_surface() == 0
+    assert enc.enc_frame(src)[0] == 0
+    enc.deinit()
+
+
+# --------------------------------------------------------------------------------------------
+# host-delivery pipeline
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("op", ["i420", "nv12", "rgb", "fused", "pack"])
+def test_pipeline_batches(J, ctx, op):
+    w, h, pitch, batch, nb = 640, 360, 768, 5, 7
+    surf_bytes, tight_bytes, rgb_bytes = pitch * h * 3 // 2, w * h * 3 // 2, 3 * w * h
+    chk = oracle.best()
+    if op == "pack":
+        shape = ctx.job_nvenc(w, h, pitch, 0x10)
+        in_bytes, out_bytes = tight_bytes, surf_bytes
+    elif op in ("rgb", "fused"):
+        shape = ctx.job_rgb(w, h, pitch, 3 * w, op == "fused")
+        in_bytes, out_bytes = surf_bytes, (rgb_bytes if op == "rgb" else tight_bytes)
+    else:
+        shape = ctx.job_nvdec(w, h, pitch, 1 if op == "i420" else 0)
+        in_bytes, out_bytes = surf_bytes, tight_bytes
+    shape.n_frames = batch
+    pipe = J.Pipeline(ctx, shape, surf_bytes, depth=3)
+    hin = ctx.alloc_host(nb * batch * in_bytes)
+    hout = ctx.alloc_host(nb * batch * out_bytes)
+    hout2 = ctx.alloc_host(nb * batch * rgb_bytes) if op == "fused" else None
+    frames = []
+    for i in range(nb * batch):
+        f = synth.i420_frame(w, h, 14, i) if op == "pack" else synth.nv12_surface(w, h, pitch, 14, i)
+        frames.append(f)
+        hin.array[i * in_bytes:(i + 1) * in_bytes] = f
+    for b in range(nb):
+        n = batch if b != nb - 1 else batch - 2             # ragged last batch
+        pipe.submit(hin.array[b * batch * in_bytes:], hout.array[b * batch * out_bytes:], n,
+                    host_out2=hout2.array[b * batch * rgb_bytes:] if hout2 else None)
+    pipe.drain()
+    total = nb * batch - 2
+    assert pipe.h2d_bytes == total * in_bytes
+    assert pipe.d2h_bytes == total * (out_bytes + (rgb_bytes if op == "fused" else 0))
+    for i in range(total):
+        got = hout.array[i * out_bytes:(i + 1) * out_bytes]
+        if op == "pack":
+            want = np.zeros(out_bytes, np.uint8)
+            oracle.nvenc_upload(frames[i], 0x10, w, h, want, pitch)
+        elif op == "rgb":
+            want = np.empty(out_bytes, np.uint8)
+            oracle.nv12_to_rgb24(frames[i], pitch, w, h, want, 3 * w)
+        else:
+            want = np.empty(out_bytes, np.uint8)
+            chk.nvdec_output_frame(frames[i], pitch, w, h, 0 if op == "nv12" else 1, want, out_bytes)
+        assert np.array_equal(got, want), f"frame {i}"
+        if op == "fused":
+            want2 = np.empty(rgb_bytes, np.uint8)
+            oracle.nv12_to_rgb24(frames[i], pitch, w, h, want2, 3 * w)
+            assert np.array_equal(hout2.array[i * rgb_bytes:(i + 1) * rgb_bytes], want2)
+    pipe.close()
+    for b in (hin, hout, hout2):
+        if b:
+            b.free()
+
+
+# --------------------------------------------------------------------------------------------
+# BASELINE.json sizes: size-independent properties + sampled oracle comparison
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("geom", [(1920, 1080, 2048, 300), (3840, 2160, 4096, 64)])
+def test_full_size_round_trip_and_samples(ctx, geom):
+    """NV12 -(de-interleave)-> I420 -(pack)-> NV12 must reproduce every active byte of all frames and
+    leave the padding of the destination surfaces untouched; sampled frames are checked against the
+    reference function byte for byte."""
+    w, h, pitch, n = geom
+    surf_bytes, tight_bytes = pitch * h * 3 // 2, w * h * 3 // 2
+    chk = oracle.best()
+    base = [synth.nv12_surface(w, h, pitch, 15, f) for f in range(8)]          # 8 distinct surfaces, tiled
+    host = np.concatenate([base[f % 8] for f in range(n)])
+    dsurf = ctx.upload(host)
+    dtight = ctx.alloc(n * tight_bytes)
+    dback = ctx.alloc(n * surf_bytes)
+    ctx.memset(dback, synth.PAD_BYTE, n * surf_bytes)
+    j = ctx.job_nvdec(w, h, pitch, 1)
+    j.n_frames, j.surf.base, j.surf.stride, j.tight.base, j.tight.stride = n, dsurf, surf_bytes, dtight, tight_bytes
+    ctx.convert(j)
+    k = ctx.job_nvenc(w, h, pitch, 0x10)
+    # nv_enc places V at y_len*5/4 == w*h + (w/2)*(h/2) for these even sizes, same layout as the I420 above
+    k.n_frames, k.surf.base, k.surf.stride, k.tight.base, k.tight.stride = n, dback, surf_bytes, dtight, tight_bytes
+    ctx.convert(k)
+    back = np.empty(n * surf_bytes, np.uint8)
+    ctx.d2h(back, dback)
+    assert np.array_equal(back, host)            # synthetic padding is 0xCD on both sides, so whole surfaces match
+    tight = np.empty(n * tight_bytes, np.uint8)
+    ctx.d2h(tight, dtight)
+    want = np.empty(tight_bytes, np.uint8)
+    for f in (0, 1, 7, n // 2, n - 1):
+        chk.nvdec_output_frame(base[f % 8], pitch, w, h, 1, want, tight_bytes)
+        assert np.array_equal(tight[f * tight_bytes:(f + 1) * tight_bytes], want)
+    # checksum of checksums: every frame that shares a source surface has identical output
+    sums = tight.reshape(n, tight_bytes)[:, ::4099].astype(np.uint64).sum(axis=1)
+    for f in range(n):
+        assert sums[f] == sums[f % 8]
+    for d in (dsurf, dtight, dback):
+        ctx.free(d)

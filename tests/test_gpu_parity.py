@@ -1,0 +1,141 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the oracle and the golden vectors.
+
+Bit-exact bar: every output byte AND every sentinel byte (slack after the frame, surface padding)
+must equal what the reference's CPU code produces on the same synthetic input.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import cases as K
+import gpu_runner as G
+import oracle
+from jmcodec_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat_sha256.json")))
+GPU_CASES = [c for c in K.all_cases() if not (c["op"] == "nvenc" and c["fmt"] in ("argb", "abgr"))]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import jmcodec_b200 as J
+    c = J.Ctx(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("c", GPU_CASES, ids=K.case_id)
+def test_matches_golden_and_oracle(ctx, c):
+    out = G.run_case_gpu(ctx, c)
+    g = GOLD[K.case_id(c)]
+    assert out.size == g["nbytes"]
+    if K.sha(out) != g["sha256"]:
+        _, _, ref = K.run_case(oracle.best() if c["op"] in K.REF_OPS else oracle.port(), c)
+        bad = np.flatnonzero(out != ref)
+        pytest.fail(f"{bad.size} byte(s) differ from the oracle, first at {bad[:8]}: got {out[bad[:8]]} want {ref[bad[:8]]}")
+
+
+@pytest.mark.parametrize("c", [c for c in K.rgb_cases()], ids=K.case_id)
+def test_fused_i420_rgb(ctx, c):
+    """Fused op: RGB identical to the RGB-only op, I420 identical to the nv_dec I420 oracle."""
+    rgb, tight = G.gpu_rgb(ctx, c, fused=True)
+    assert K.sha(rgb) == GOLD[K.case_id(c)]["sha256"]
+    want = np.full(tight.size, synth.OUT_FILL, np.uint8)
+    oracle.best().nvdec_output_frame(K.rgb_input(c), c["pitch"], c["w"], c["h"], 1, want, want.size)
+    assert np.array_equal(tight, want)
+
+
+@pytest.mark.parametrize("mode", ["stride", "list", "list_aligned_flag", "list_misaligned"])
+@pytest.mark.parametrize("op", ["i420", "nv12", "pack", "rgb"])
+def test_batched_launch(ctx, op, mode):
+    """One launch over a batch: frame strides and device pointer lists (aligned / deliberately odd)."""
+    import jmcodec_b200 as J
+    w, h, pitch, n = 96, 34, 128, 7
+    surf_bytes = pitch * h * 3 // 2
+    tight_bytes = w * h * 3 // 2
+    rgb_bytes = 3 * w * h
+    skew = 1 if mode == "list_misaligned" else 0          # odd byte offset defeats every vector path
+    sstride, tstride, rstride = surf_bytes + 256 + skew, tight_bytes + 64 + skew, rgb_bytes + 32 + skew
+    chk = oracle.best()
+    surfs = [synth.nv12_surface(w, h, pitch, 9, f) for f in range(n)]
+    tights = [synth.i420_frame(w, h, 9, f) for f in range(n)]
+    if op == "pack":
+        src = np.full(n * tstride, 0x11, np.uint8)
+        for f in range(n):
+            src[f * tstride:f * tstride + tight_bytes] = tights[f]
+        dsrc = ctx.upload(src)
+        ddst = ctx.alloc(n * sstride)
+        ctx.memset(ddst, synth.PAD_BYTE, n * sstride)
+        j = ctx.job_nvenc(w, h, pitch, 0x10)
+        j.tight.base, j.tight.stride, j.surf.base, j.surf.stride = dsrc, tstride, ddst, sstride
+        out_stride, out_total = sstride, n * sstride
+    else:
+        src = np.full(n * sstride, 0x11, np.uint8)
+        for f in range(n):
+            src[f * sstride:f * sstride + surf_bytes] = surfs[f]
+        dsrc = ctx.upload(src)
+        if op == "rgb":
+            ddst = ctx.alloc(n * rstride)
+            ctx.memset(ddst, synth.OUT_FILL, n * rstride)
+            j = ctx.job_rgb(w, h, pitch, 3 * w, False)
+            j.rgb.base, j.rgb.stride = ddst, rstride
+            out_stride, out_total = rstride, n * rstride
+        else:
+            ddst = ctx.alloc(n * tstride)
+            ctx.memset(ddst, synth.OUT_FILL, n * tstride)
+            j = ctx.job_nvdec(w, h, pitch, 1 if op == "i420" else 0)
+            j.tight.base, j.tight.stride = ddst, tstride
+            out_stride, out_total = tstride, n * tstride
+        j.surf.base, j.surf.stride = dsrc, sstride
+    j.n_frames = n
+    lists = []
+    if mode != "stride":
+        for fs in (j.surf, j.tight, j.rgb):
+            if fs.base:
+                d = G.device_ptr_array(ctx, [fs.base + f * fs.stride for f in range(n)])
+                lists.append(d)
+                fs.list, fs.base, fs.stride = d, None, 0
+        if mode == "list_aligned_flag":
+            j.flags = J.lib.JOB_ALIGNED16
+    ctx.convert(j)
+    got = np.empty(out_total, np.uint8)
+    ctx.d2h(got, ddst)
+    for f in range(n):
+        g = got[f * out_stride:(f + 1) * out_stride]
+        if op == "pack":
+            want = np.full(out_stride, synth.PAD_BYTE, np.uint8)
+            oracle.nvenc_upload(tights[f], 0x10, w, h, want, pitch)
+        elif op == "rgb":
+            want = np.full(out_stride, synth.OUT_FILL, np.uint8)
+            oracle.nv12_to_rgb24(surfs[f], pitch, w, h, want, 3 * w)
+        else:
+            want = np.full(out_stride, synth.OUT_FILL, np.uint8)
+            chk.nvdec_output_frame(surfs[f], pitch, w, h, 1 if op == "i420" else 0, want, want.size)
+        assert np.array_equal(g, want), f"frame {f}"
+    for d in [dsrc, ddst] + lists:
+        ctx.free(d)
+
+
+def test_bad_jobs_are_rejected(ctx):
+    import jmcodec_b200 as J
+    j = ctx.job_nvdec(64, 64, 64, 1)
+    j.n_frames = 1
+    with pytest.raises(J.JmcError):
+        ctx.convert(j)                      # no frame sets
+    with pytest.raises(J.JmcError):
+        ctx.job_nvdec(64, 64, 32, 1)        # pitch < width
+    with pytest.raises(J.JmcError):
+        ctx.job_rgb(64, 64, 64, 100, False)  # rgb_pitch < 3w
+    d = ctx.alloc(1 << 16)
+    j = ctx.job_rgb(1, 8, 16, 3, False)
+    j.n_frames, j.surf.base, j.rgb.base = 1, d, d
+    with pytest.raises(J.JmcError):
+        ctx.convert(j)                      # RGB needs w,h >= 2 (oracle returns -1)
+    j = ctx.job_nvdec(0, 0, 0, 1)
+    j.n_frames, j.surf.base, j.tight.base = 1, d, d
+    ctx.convert(j)                          # empty frame: nothing to do, not an error
+    ctx.free(d)
