@@ -266,8 +266,13 @@ int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec han
     if (*out_len < need) return -2;                            /* :773-774 */
     *out_len = 0;                                              /* :776 */
     cudaStream_t st = (cudaStream_t)jmc_ctx_stream(c->ctx, 0);
-    /* Only the tight frame crosses PCIe.  Pinned out_buf: direct DMA; pageable: the driver stages it. */
-    if (need > 0 && cudaMemcpyAsync(out_buf, c->d_tight, (size_t)need, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
+    /* Only the tight frame crosses PCIe.  Pinned out_buf: direct DMA; pageable: the driver stages it.
+     * For odd sizes the reference writes fewer than w*h*3/2 bytes and leaves the rest of out_buf
+     * untouched (h>>1 chroma rows, w>>1 samples: nv_dec.cpp:792-796,807-818): copy exactly those. */
+    const size_t luma = (size_t)c->cur_w * c->cur_h;
+    const size_t written = c->out_fmt == 0 ? luma + (size_t)(c->cur_h >> 1) * c->cur_w
+                                           : luma + 2 * (size_t)(c->cur_w >> 1) * (c->cur_h >> 1);
+    if (written > 0 && cudaMemcpyAsync(out_buf, c->d_tight, written, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
     if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
     *out_len = need;                                           /* :824 */
     return need;                                               /* :827 */

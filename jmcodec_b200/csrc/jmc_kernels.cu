@@ -85,8 +85,8 @@ static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     if (total == 0) return JMC_OK;
     if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }
     p.total_tiles = (uint32_t)total;
-    const uint32_t max_grid = (uint32_t)ctx->sm_count * PlaneCfg::BLOCKS_PER_SM;
-    const uint32_t grid = p.total_tiles < max_grid ? p.total_tiles : max_grid;
+    const uint32_t grid = p.total_tiles;             /* one CTA per 16 KB tile (see Cfg256x4) */
+    (void)ctx->sm_count;
     const bool wide = all_wide(j, p);
     const int k1 = p.part[1].kind == PART_NONE ? PART_COPY : p.part[1].kind;
 #define JMC_LAUNCH(TT, K1)                                                                               \
@@ -133,8 +133,7 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     p.total_tasks = (uint32_t)total;
     constexpr uint32_t WARPS = RgbCfg::THREADS / 32;
     const uint32_t blocks_needed = (p.total_tasks + WARPS - 1) / WARPS;
-    const uint32_t max_grid = (uint32_t)ctx->sm_count * RgbCfg::BLOCKS_PER_SM;
-    const uint32_t grid = blocks_needed < max_grid ? blocks_needed : max_grid;
+    const uint32_t grid = blocks_needed;             /* one warp per (row pair, 512-pixel segment) task */
     rgb_kernel<RgbCfg><<<grid, RgbCfg::THREADS, 0, stream>>>(p);
     JMC_CUDA(cudaGetLastError());
     ctx->launches++;

@@ -3,8 +3,8 @@
  *
  * Everything here is HBM-bound byte movement (arithmetic intensity ~0; ~6 int-ops/B for RGB),
  * so the design rules are: 16-byte coalesced vector accesses, several independent loads in
- * flight per thread before the first store, a persistent grid sized in multiples of the SM
- * count looping over fixed-size tiles, ONE launch per batch of frames, no tensor cores.
+ * flight per thread before the first store, fixed-size tiles with one CTA per tile (measured
+ * faster than a persistent loop, see Cfg256x4), ONE launch per batch of frames, no tensor cores.
  *
  * Two kernels:
  *   planes_kernel : 2-D copy (strip/add pitch), U/V de-interleave (prmt 0x6420/0x7531) and
@@ -154,11 +154,15 @@ __device__ __forceinline__ int vec_width(uint64_t bits)
     return (int)(low & (0u - low));
 }
 
+/* Chosen by tools/sweep.cu on B200 (profiles/sweep_r1.md): 256 threads x 4 vectors = one 16 KB tile
+ * per CTA, ONE CTA PER TILE (a persistent grid-stride loop measured 14% slower: the hardware CTA
+ * scheduler overlaps the next tile's loads with this tile's draining stores better than a loop
+ * does), L1::no_allocate loads, evict-first (.cs) stores. */
 struct Cfg256x4 {
     static constexpr int THREADS = 256;
     static constexpr int UNROLL = 4;      /* 16-byte vectors per thread in flight */
     static constexpr int LDP = 1;
-    static constexpr int STP = 0;
+    static constexpr int STP = 1;
     static constexpr int BLOCKS_PER_SM = 4;
 };
 
@@ -427,9 +431,9 @@ __device__ __forceinline__ void rgb4(uint32_t yw, int r0, int g0, int b0, int r1
 
 __device__ __forceinline__ uint8_t clip8_dev(int v) { return (uint8_t)min(max(v, 0), 255); }
 
-struct RgbCfg {
-    static constexpr int THREADS = 256;
-    static constexpr int BLOCKS_PER_SM = 4;
+struct RgbCfg {                           /* tools/sweep.cu: 128 x 8 CTAs/SM, one warp task per warp */
+    static constexpr int THREADS = 128;
+    static constexpr int BLOCKS_PER_SM = 8;
     static constexpr int LDP = 1;
     static constexpr int STP = 0;
 };
