@@ -404,10 +404,22 @@ int jmc_pipeline_submit(jmc_pipeline *p, const void *host_in, const void *dev_in
     if (host_in) {
         /* upload stream: the slot's input buffer is free once its previous conversion has run */
         JMC_CUDA(cudaStreamWaitEvent(c->stream[1], s.converted, 0));
-        JMC_CUDA(cudaMemcpyAsync(s.d_in, host_in, p->in_bytes * n, cudaMemcpyHostToDevice, c->stream[1]));
+        const jmc_job &g = p->shape;
+        const bool rows_only = op_is_decode_side(g.op) && g.width < g.pitch && g.surf_y_off == 0 &&
+                               g.surf_uv_off == (int64_t)g.pitch * g.height && p->in_bytes % (size_t)g.pitch == 0;
+        if (rows_only) {
+            /* NV12 surfaces back to back = one 2-D array of `pitch`-byte rows: the DMA engine skips the
+             * padding, so only width/pitch of the bytes cross PCIe (measured: same GB/s of useful bytes). */
+            const size_t rows = p->in_bytes / (size_t)g.pitch * n;
+            JMC_CUDA(cudaMemcpy2DAsync(s.d_in, (size_t)g.pitch, host_in, (size_t)g.pitch, (size_t)g.width, rows,
+                                       cudaMemcpyHostToDevice, c->stream[1]));
+            p->h2d += (size_t)g.width * rows;
+        } else {
+            JMC_CUDA(cudaMemcpyAsync(s.d_in, host_in, p->in_bytes * n, cudaMemcpyHostToDevice, c->stream[1]));
+            p->h2d += p->in_bytes * n;
+        }
         JMC_CUDA(cudaEventRecord(s.uploaded, c->stream[1]));
         JMC_CUDA(cudaStreamWaitEvent(c->stream[0], s.uploaded, 0));
-        p->h2d += p->in_bytes * n;
         src = s.d_in;
     }
     /* convert stream: the slot's output buffers are free once their previous delivery has run */

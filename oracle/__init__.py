@@ -79,6 +79,8 @@ class _Ref:
         L.jmref_nvdec_run.restype = C.c_double
         L.jmref_intelenc_run.argtypes = [_u8p, C.c_size_t, C.c_int, _u8p, C.c_size_t, C.c_int] + [C.c_int] * 5
         L.jmref_intelenc_run.restype = C.c_double
+        L.jmref_nvenc_convert.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, C.c_int, _u8p, C.c_int, _ip]
+        L.jmref_nvenc_convert.restype = C.c_int
         self.L = L
         self.kind = "reference"
         self._nvdec = L.jmref_nvdec_output_frame
@@ -156,10 +158,20 @@ def best() -> Checker:
     return ref() if have_ref() else port()
 
 
-# functions that exist only in the port (no CPU code in the reference to compile)
 def nvenc_upload(in_buf, fmt, w, h, surf, stride):
+    """C restatement of nv_enc.cpp:1023-1103 (device side restated on the CPU)."""
     return port().impl.L.jmo_nvenc_upload(_ptr(in_buf), fmt, w, h, _ptr(surf), stride)
 
+
+def ref_nvenc_convert(in_buf, fmt, w, h, surf, stride):
+    """The reference's own nvenc_convert_yuv_data_to_nv12() run against a fake CUDA driver
+    (oracle/ref_nvenc_driver.cpp).  Returns (ret, InterleaveUV launches issued)."""
+    n = C.c_int(0)
+    r = ref().impl.L.jmref_nvenc_convert(_ptr(in_buf), int(in_buf.size), fmt, w, h, _ptr(surf), stride, C.byref(n))
+    return r, n.value
+
+
+# exists only in the port: the reference has no YUV->RGB code at all
 
 def nv12_to_rgb24(surf, pitch, w, h, rgb, rgb_pitch):
     return port().impl.L.jmo_nv12_to_rgb24(_ptr(surf), pitch, w, h, _ptr(rgb), rgb_pitch)

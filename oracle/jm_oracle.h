@@ -10,8 +10,10 @@
  * Parity status: NV12->NV12/I420, NV12/I420->pitched NV12 are PINNED against the unmodified
  * reference translation units compiled into oracle/_ref/libjmref.so (tests/test_oracle_vs_ref.py)
  * and against SHA-256 known-answer vectors generated from them (tests/golden/).
- * jmo_nvenc_upload restates nv_enc/nv_enc.cpp:1023-1103 whose InterleaveUV PTX is absent from the
- * reference tree: pinned only by the call-site arguments.  jmo_nv12_to_rgb24 is a builder-defined
+ * jmo_nvenc_upload restates nv_enc/nv_enc.cpp:1023-1103: PINNED against the reference's own
+ * nvenc_convert_yuv_data_to_nv12() executed over a fake CUDA driver (oracle/ref_nvenc_driver.cpp);
+ * only the InterleaveUV kernel body (PTX absent from the reference tree) is emulated there, from the
+ * 8 launch arguments at nv_enc.cpp:1070.  jmo_nv12_to_rgb24 is a builder-defined
  * BT.601 spec: PARITY UNPINNED (the reference has no YUV->RGB code; SDL2 does it).
  *
  * All citations are relative to /root/reference.

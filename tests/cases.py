@@ -169,10 +169,13 @@ def nvenc_surface_bytes(c):
     return s * h if c["fmt"] in ("argb", "abgr") else s * (h * 3 // 2 + 1)
 
 
-def run_nvenc(_chk, c):
+def run_nvenc(chk, c):
     import oracle
     surf = np.full(nvenc_surface_bytes(c), synth.PAD_BYTE, np.uint8)
-    r = oracle.nvenc_upload(nvenc_input(c), NVENC_FMTS[c["fmt"]], c["w"], c["h"], surf, c["stride"])
+    if chk.kind == "reference":       # the reference's own host code over a fake CUDA driver
+        r, _ = oracle.ref_nvenc_convert(nvenc_input(c), NVENC_FMTS[c["fmt"]], c["w"], c["h"], surf, c["stride"])
+    else:
+        r = oracle.nvenc_upload(nvenc_input(c), NVENC_FMTS[c["fmt"]], c["w"], c["h"], surf, c["stride"])
     return r, surf.size, surf
 
 
@@ -191,7 +194,7 @@ def run_rgb(_chk, c):
 RUNNERS = {"nvdec": run_nvdec, "inteldec": run_inteldec, "intelenc": run_intelenc,
            "nvenc": run_nvenc, "rgb24": run_rgb}
 # ops for which the unmodified reference has CPU code that oracle/_ref executes
-REF_OPS = ("nvdec", "inteldec", "intelenc")
+REF_OPS = ("nvdec", "inteldec", "intelenc", "nvenc")
 
 
 def run_case(chk, c):

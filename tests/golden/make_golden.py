@@ -8,9 +8,10 @@ jmcodec_b200/synth.py.  Each entry records the reference's return code, *out_len
 of the whole output buffer INCLUDING its 0xA5 / 0xCD pre-filled slack and padding, so bytes the
 reference leaves untouched are pinned too.  Small cases also carry the raw bytes (hex).
 
-Entries with "source": "port" have no executable reference code (nv_enc device path: InterleaveUV
-PTX absent from the tree; RGB24: no YUV->RGB in the reference at all) and come from the C
-restatement oracle/jm_oracle.c; the RGB ones are marked "parity": "unpinned".
+The nv_enc entries come from the reference's own nvenc_convert_yuv_data_to_nv12() executed against a
+fake CUDA driver (oracle/ref_nvenc_driver.cpp; only the absent InterleaveUV PTX is emulated).
+Entries with "source": "port" have no executable reference code (RGB24: no YUV->RGB in the reference
+at all); they come from the C restatement oracle/jm_oracle.c and are marked "parity": "unpinned".
 
 Run in the dev container (needs /root/reference or a prebuilt oracle/_ref):
     python tests/golden/make_golden.py
