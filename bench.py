@@ -269,6 +269,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel table and the CPU baseline")
+    ap.add_argument("--e2e-sub", type=int, default=0, help="frames per pipeline batch in the e2e leg (default: auto)")
+    ap.add_argument("--e2e-depth", type=int, default=3, help="pipeline slots in the e2e leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     name = args.workload
@@ -344,8 +346,10 @@ def main():
 
     # ---- e2e: pinned host surfaces -> H2D -> convert -> D2H tight frames, overlapped ----------------
     sub = 30 if n % 30 == 0 else (16 if n % 16 == 0 else n)       # frames per pipeline batch
+    if args.e2e_sub and n % args.e2e_sub == 0:
+        sub = args.e2e_sub
     shape = build_job(ctx, op, w, h, pitch, sub, None, None, None)
-    pipe = J.Pipeline(ctx, shape, pitch * h * 3 // 2, depth=3)
+    pipe = J.Pipeline(ctx, shape, pitch * h * 3 // 2, depth=args.e2e_depth)
     ev0, ev1 = J.Event(ctx), J.Event(ctx)
 
     def e2e_step():
@@ -414,7 +418,7 @@ def main():
                          "traffic": recorded_traffic(name), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_launch},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
-                    "ms_per_step": e2e_ms_max / args.steps, "frames_per_pipeline_batch": sub, "pipeline_depth": 3,
+                    "ms_per_step": e2e_ms_max / args.steps, "frames_per_pipeline_batch": sub, "pipeline_depth": args.e2e_depth,
                     "pcie_gbs_each_way": [h2d_step / (e2e_ms_max / args.steps * 1e-3) / 1e9, d2h_step / (e2e_ms_max / args.steps * 1e-3) / 1e9]},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),

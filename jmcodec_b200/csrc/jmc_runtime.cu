@@ -405,7 +405,8 @@ int jmc_pipeline_submit(jmc_pipeline *p, const void *host_in, const void *dev_in
         /* upload stream: the slot's input buffer is free once its previous conversion has run */
         JMC_CUDA(cudaStreamWaitEvent(c->stream[1], s.converted, 0));
         const jmc_job &g = p->shape;
-        const bool rows_only = op_is_decode_side(g.op) && g.width < g.pitch && g.surf_y_off == 0 &&
+        static const bool allow_2d = !(getenv("JMC_PIPELINE_H2D_2D") && atoi(getenv("JMC_PIPELINE_H2D_2D")) == 0);
+        const bool rows_only = allow_2d && op_is_decode_side(g.op) && g.width < g.pitch && g.surf_y_off == 0 &&
                                g.surf_uv_off == (int64_t)g.pitch * g.height && p->in_bytes % (size_t)g.pitch == 0;
         if (rows_only) {
             /* NV12 surfaces back to back = one 2-D array of `pitch`-byte rows: the DMA engine skips the

@@ -8,7 +8,7 @@
  * never links or calls it and has no CPU fallback.
  *
  * Parity status: NV12->NV12/I420, NV12/I420->pitched NV12 are PINNED against the unmodified
- * reference translation units compiled into oracle/_ref/libjmref.so (tests/test_oracle_vs_ref.py)
+ * reference translation units compiled into oracle/_ref/libjmref.so (tests/test_oracle.py)
  * and against SHA-256 known-answer vectors generated from them (tests/golden/).
  * jmo_nvenc_upload restates nv_enc/nv_enc.cpp:1023-1103: PINNED against the reference's own
  * nvenc_convert_yuv_data_to_nv12() executed over a fake CUDA driver (oracle/ref_nvenc_driver.cpp);
