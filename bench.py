@@ -261,6 +261,41 @@ def device_only(ctx, name, rank, iters, warmup):
     return res
 
 
+def dropin_api_fps(J, ctx, device, w=1920, h=1080, pitch=2048, frames=200):
+    """Frames/s of the per-frame drop-in API, called as test_nv_dec.cpp:215-218 calls it
+    (jm_nvdec_decode_frame then jm_nvdec_output_frame, one frame at a time, one handle, one thread)."""
+    from jmcodec_b200 import synth
+    need = w * h * 3 // 2
+    surfs = [synth.nv12_surface(w, h, pitch, 7, f) for f in range(4)]
+    res = {}
+    # (a) the reference's calling convention: pageable packet in, pageable frame out
+    dec = J.NvDec(device)
+    dec.init(J.NvDec.CODEC_RAW_NV12, 1)
+    pkts = [J.NvDec.raw_packet(s, w, h, pitch) for s in surfs]
+    out = np.empty(need, np.uint8)
+    for i in range(10):
+        dec.decode_frame(pkts[i % 4]); dec.output_frame(out, need)
+    t0 = time.perf_counter()
+    for i in range(frames):
+        dec.decode_frame(pkts[i % 4]); dec.output_frame(out, need)
+    res["host_packet_pageable_out_fps"] = round(frames / (time.perf_counter() - t0), 1)
+    # (b) what an NVDEC front-end yields: device-resident surface in, pinned frame out
+    dptrs = [ctx.upload(s) for s in surfs]
+    dpk = [J.NvDec.raw_packet(None, w, h, pitch, device_ptr=d) for d in dptrs]
+    pinned = dec.alloc_host(need)
+    for i in range(10):
+        dec.decode_frame(dpk[i % 4]); dec.output_frame(pinned, need)
+    t0 = time.perf_counter()
+    for i in range(frames * 5):
+        dec.decode_frame(dpk[i % 4]); dec.output_frame(pinned, need)
+    res["device_surface_pinned_out_fps"] = round(frames * 5 / (time.perf_counter() - t0), 1)
+    dec.free_host(pinned)
+    dec.deinit()
+    for d in dptrs:
+        ctx.free(d)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -384,7 +419,7 @@ def main():
     pipe.close()
 
     # ---- extras on rank 0, N=1: per-kernel device table + CPU baseline ------------------------------
-    kernels, cpu = None, None
+    kernels, cpu, batch_sweep, dropin = None, None, None, None
     if rank == 0 and world == 1 and not args.no_extras:
         for d in (d_in, d_out, d_out2):
             if d:
@@ -395,6 +430,15 @@ def main():
             r = device_only(ctx, k, rank, 10, 3)
             kernels[k] = {"frames_per_s": round(r["frames_per_s"], 1), "gbs": round(r["gbs"], 1),
                           "frac_of_peak": round(r["gbs"] / peak, 4), "ms_per_launch": round(r["ms_per_launch"], 4)}
+        # launch-bound -> bandwidth-bound: frames per launch sweep
+        batch_sweep = {}
+        for nb in (1, 8, 64, 300):
+            WORKLOADS["_sweep"] = ("i420", 1920, 1080, 2048, nb)
+            r = device_only(ctx, "_sweep", rank, 50 if nb < 64 else 10, 5)
+            batch_sweep[str(nb)] = {"frames_per_s": round(r["frames_per_s"], 1), "gbs": round(r["gbs"], 1),
+                                    "us_per_launch": round(r["ms_per_launch"] * 1e3, 2)}
+        del WORKLOADS["_sweep"]
+        dropin = dropin_api_fps(J, ctx, local)
         threads = len(os.sched_getaffinity(0))
         if op == "i420":
             f1, kind = cpu_reference_fps(w, h, pitch, 1500, 1, distinct)
@@ -428,6 +472,8 @@ def main():
             line["cpu_baseline"] = cpu
         if kernels:
             line["kernels"] = kernels
+            line["frames_per_launch_sweep_1080p"] = batch_sweep
+            line["dropin_api_1080p"] = dropin
         print(json.dumps(line))
     for b in (hin, hout, hout2):
         if b:

@@ -11,9 +11,12 @@
  *     as sm_100a CUDA kernels (NV12 -> tight NV12 / I420 on the device, only the tight frame
  *     crosses PCIe) instead of cuMemcpyDtoH of the padded surface + a CPU loop
  *     (nv_dec.cpp:452, :782-820);
+ *   - bitstream codecs (0..7) go through NVDEC exactly as in the reference (parser + decoder
+ *     callbacks, nv_dec.cpp:23-52,278-403,496-540), bound at run time from libnvcuvid.so.1 (or
+ *     $JMC_NVCUVID_LIB); the mapped device surface feeds the kernel directly;
  *   - codec_type JM_NVDEC_CODEC_RAW_NV12 accepts already-decoded pitched NV12 surfaces as
  *     "packets" (host bytes or a device pointer), which is how the path is exercised where no
- *     NVDEC bitstream front-end is available;
+ *     NVDEC engine is exposed;
  *   - jm_nvdec_set_device() picks the GPU (the reference hard-codes device 0, nv_dec.cpp:209).
  * There is no CPU fallback: without a CUDA device jm_nvdec_init fails.
  */
@@ -76,7 +79,7 @@ JMDLL_FUNC handle_nvdec jm_nvdec_create_handle(void);
  *               i.e. I420 (nv_dec.cpp:814-815)
  *   extra_data: sps/pps buffer, NULL is OK
  *   return: 0 - successful, else failed (-2 no CUDA device, -3 bad device id as
- *           nvdec_cuda_init nv_dec.cpp:219-231; -4 no NVDEC parser library for a bitstream codec)
+ *           nvdec_cuda_init nv_dec.cpp:219-231; -4 NVDEC library/engine unavailable for a bitstream codec)
  */
 JMDLL_FUNC int jm_nvdec_init(int codec_type, int out_fmt, char *extra_data, int len, handle_nvdec handle);
 

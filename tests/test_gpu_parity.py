@@ -139,3 +139,103 @@ def test_bad_jobs_are_rejected(ctx):
     j.n_frames, j.surf.base, j.tight.base = 1, d, d
     ctx.convert(j)                          # empty frame: nothing to do, not an error
     ctx.free(d)
+
+
+def _rand_geoms(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(n):
+        w = int(rng.integers(1, 200))
+        h = int(rng.integers(1, 120))
+        pitch = w + int(rng.integers(0, 70))
+        out.append((w, h, pitch, int(rng.integers(0, 16)), int(rng.integers(0, 16)), int(rng.integers(0, 16))))
+    return out
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_geometries_against_oracle(ctx, seed):
+    """Random sizes, pitches and buffer skews (every alignment class) for all four YUV ops: one frame each,
+    sentinel-checked, against the oracle."""
+    chk = oracle.best()
+    for (w, h, pitch, ks, kt, kr) in _rand_geoms(40, 1000 + seed):
+        surf = synth.nv12_surface(w, h, pitch, 21, w * 131 + h)
+        tight_in = synth.i420_frame(w, h, 22, w * 17 + h)
+        cap = w * h * 3 // 2 + K.SLACK
+        nsurf = pitch * (h * 3 // 2 + 1)
+        # device buffers at skewed (possibly odd) addresses
+        dsurf = ctx.alloc(surf.size + 64)
+        ctx.h2d(dsurf + ks, surf)
+        for fmt in (0, 1):
+            dout = ctx.alloc(cap + 64)
+            ctx.memset(dout, synth.OUT_FILL, cap + 64)
+            j = ctx.job_nvdec(w, h, pitch, fmt)
+            j.n_frames, j.surf.base, j.tight.base = 1, dsurf + ks, dout + kt
+            ctx.convert(j)
+            got = np.empty(cap, np.uint8)
+            ctx.d2h(got, dout + kt)
+            want = np.full(cap, synth.OUT_FILL, np.uint8)
+            chk.nvdec_output_frame(surf, pitch, w, h, fmt, want, cap)
+            assert np.array_equal(got, want), (w, h, pitch, ks, kt, fmt)
+            ctx.free(dout)
+        dtin = ctx.alloc(tight_in.size + 64)
+        ctx.h2d(dtin + kt, tight_in)
+        for code in (0x1, 0x10):
+            ds = ctx.alloc(nsurf + 64)
+            ctx.memset(ds, synth.PAD_BYTE, nsurf + 64)
+            j = ctx.job_nvenc(w, h, pitch, code)
+            j.n_frames, j.surf.base, j.tight.base = 1, ds + ks, dtin + kt
+            ctx.convert(j)
+            got = np.empty(nsurf, np.uint8)
+            ctx.d2h(got, ds + ks)
+            want = np.full(nsurf, synth.PAD_BYTE, np.uint8)
+            # tight_in is w*h*3/2 bytes; the yv12 path may read up to y_len*5/4 + (w/2)*(h/2) <= that
+            oracle.nvenc_upload(tight_in, code, w, h, want, pitch)
+            assert np.array_equal(got, want), (w, h, pitch, ks, kt, hex(code))
+            ctx.free(ds)
+        if w >= 2 and h >= 2:
+            rp = 3 * w + kr
+            rcap = rp * h + K.SLACK
+            for fused in (False, True):
+                drgb = ctx.alloc(rcap + 64)
+                ctx.memset(drgb, synth.OUT_FILL, rcap + 64)
+                dt = ctx.alloc(cap + 64)
+                ctx.memset(dt, synth.OUT_FILL, cap + 64)
+                j = ctx.job_rgb(w, h, pitch, rp, fused)
+                j.n_frames, j.surf.base, j.rgb.base, j.tight.base = 1, dsurf + ks, drgb + kr, dt + kt
+                ctx.convert(j)
+                got = np.empty(rcap, np.uint8)
+                ctx.d2h(got, drgb + kr)
+                want = np.full(rcap, synth.OUT_FILL, np.uint8)
+                oracle.nv12_to_rgb24(surf, pitch, w, h, want, rp)
+                assert np.array_equal(got, want), (w, h, pitch, ks, kr, fused)
+                gt = np.empty(cap, np.uint8)
+                ctx.d2h(gt, dt + kt)
+                wt = np.full(cap, synth.OUT_FILL, np.uint8)
+                if fused:
+                    chk.nvdec_output_frame(surf, pitch, w, h, 1, wt, cap)
+                assert np.array_equal(gt, wt), (w, h, pitch, "fused tight", fused)
+                ctx.free(drgb), ctx.free(dt)
+        ctx.free(dsurf), ctx.free(dtin)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_random_intel_crops_against_oracle(ctx, seed):
+    """Random MFX-style surfaces with crop rectangles, both directions (intel_dec / intel_enc rules)."""
+    chk = oracle.best()
+    rng = np.random.default_rng(2000 + seed)
+    for _ in range(40):
+        pitch = int(rng.integers(8, 40)) * 8
+        rows = int(rng.integers(4, 40)) * 2
+        cw = int(rng.integers(1, pitch))
+        ch = int(rng.integers(1, rows))
+        cx = int(rng.integers(0, pitch - cw + 1))
+        cy = int(rng.integers(0, rows - ch + 1))
+        c = dict(pitch=pitch, rows=rows, cx=cx, cy=cy, cw=cw, ch=ch)
+        for fmt in (0, 1):
+            cc = dict(c, op="inteldec", fmt=fmt)
+            _, _, want = K.run_inteldec(chk, cc)
+            assert np.array_equal(G.gpu_inteldec(ctx, cc), want), cc
+        for i420 in (0, 1):
+            cc = dict(c, op="intelenc", i420=i420)
+            _, _, want = K.run_intelenc(chk, cc)
+            assert np.array_equal(G.gpu_intelenc(ctx, cc), want), cc
