@@ -111,6 +111,9 @@ _SIGS = {
     "jmc_pipeline_drain": (C.c_int, [C.c_void_p]),
     "jmc_pipeline_h2d_bytes": (C.c_uint64, [C.c_void_p]),
     "jmc_pipeline_d2h_bytes": (C.c_uint64, [C.c_void_p]),
+    # jmc_annexb.h
+    "jmc_annexb_find_prefix": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "jmc_annexb_find_nalu": (C.c_void_p, [C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     # jm_nv_dec.h
     "jm_nvdec_create_handle": (C.c_void_p, []),
     "jm_nvdec_init": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_int, C.c_void_p]),

@@ -103,3 +103,21 @@ double jmref_nvdec_run(const unsigned char *surf_base, size_t surf_stride, int n
 }
 
 } /* extern "C" */
+
+/* NAL splitter of the reference's test program (test_nv_dec/test_nv_dec.cpp:30-86), compiled from
+ * the unmodified source into this library with main() renamed. */
+int find_nalu_prefix(unsigned char *buf_start, int buf_size, int *prefix_len);
+unsigned char *find_nalu(unsigned char *buf, int size, int *nalu_len);
+
+extern "C" {
+__attribute__((visibility("default")))
+int jmref_find_nalu_prefix(unsigned char *buf, int size, int *prefix_len) { return find_nalu_prefix(buf, size, prefix_len); }
+
+/* returns the offset of the NAL in buf, or -1 when the reference returns NULL */
+__attribute__((visibility("default")))
+int jmref_find_nalu(unsigned char *buf, int size, int *nalu_len)
+{
+    unsigned char *p = find_nalu(buf, size, nalu_len);
+    return p ? (int)(p - buf) : -1;
+}
+}

@@ -29,7 +29,7 @@ def lib():
 
 
 def test_every_declared_symbol_is_exported(lib):
-    declared = _declared("jmc_cuda.h") | _declared("jm_nv_dec.h") | _declared("jmnv_enc.h")
+    declared = _declared("jmc_cuda.h") | _declared("jm_nv_dec.h") | _declared("jmnv_enc.h") | _declared("jmc_annexb.h")
     assert len(declared) >= 55
     out = subprocess.run(["nm", "-D", "--defined-only", J.lib_path()], capture_output=True, text=True, check=True).stdout
     exported = {ln.split()[-1] for ln in out.splitlines() if " T " in ln}
