@@ -1,6 +1,8 @@
 /*
  * jmc_kernels.cu -- turns a jmc_job into ONE kernel launch (see jmc_kernels.cuh for the kernels).
  */
+#include <stdlib.h>
+
 #include "jmc_internal.h"
 #include "jmc_kernels.cuh"
 
@@ -41,6 +43,57 @@ static Part make_part(int kind, uint32_t rows, uint32_t row_elems, int64_t p_off
     p.rdiv.m = (uint32_t)(((1ull << (31 + s)) + d - 1) / d);
     p.rdiv.pad_ = 0;
     return p;
+}
+
+static bool getenv_flag(const char *name)
+{
+    const char *e = getenv(name);
+    return e && atoi(e) != 0;
+}
+
+/* Bulk-copy-engine kernel (cp.async.bulk): returns 1 when the geometry does not fit it. */
+static int launch_bulk(jmc_ctx *ctx, const PlaneParams &pp, int k1, cudaStream_t stream)
+{
+    BulkParams b;
+    b.pitched = pp.pitched;
+    b.tight = pp.tight;
+    b.n_frames = pp.n_frames;
+    b.part[0] = pp.part[0];
+    b.part[1] = pp.part[1];
+    /* shared memory per row of a tile: luma/NV12-chroma rows need row_elems bytes, SPLIT/MERGE rows
+     * 2*row_elems interleaved + row_elems per planar half */
+    const uint32_t row0 = pp.part[0].row_elems;
+    const uint32_t row1 = pp.part[1].kind == PART_NONE ? 0 : (pp.part[1].kind == PART_COPY ? pp.part[1].row_elems : 4 * pp.part[1].row_elems);
+    const uint32_t per_row = row0 > row1 ? row0 : row1;
+    if (per_row == 0 || per_row > 96 * 1024) return 1;
+    uint32_t rows = 8;                               /* tools/sweep.cu: 8-row tiles are the optimum at 1080p and 4K */
+    while (rows > 1 && (size_t)rows * per_row > 96 * 1024) rows >>= 1;
+    b.rows_per_tile = rows;
+    b.tiles[0] = pp.part[0].kind == PART_NONE ? 0 : (pp.part[0].rows + rows - 1) / rows;
+    b.tiles[1] = pp.part[1].kind == PART_NONE ? 0 : (pp.part[1].rows + rows - 1) / rows;
+    const uint64_t total = (uint64_t)(b.tiles[0] + b.tiles[1]) * b.n_frames;
+    if (total == 0) return JMC_OK;
+    if (total > 0x7fffffffull) return 1;
+    const size_t smem = (size_t)rows * per_row;
+    const uint32_t grid = (uint32_t)total;
+#define JMC_BULK(TT, K1)                                                                                          \
+    do {                                                                                                          \
+        static bool attr_done[64];                                                                                \
+        if (ctx->device < 64 && !attr_done[ctx->device]) {                                                        \
+            JMC_CUDA(cudaFuncSetAttribute(bulk_planes_kernel<TT, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
+            attr_done[ctx->device] = true;                                                                        \
+        }                                                                                                         \
+        bulk_planes_kernel<TT, K1><<<grid, BULK_THREADS, smem, stream>>>(b);                                      \
+    } while (0)
+    if (pp.to_tight) {
+        if (k1 == PART_SPLIT) JMC_BULK(true, PART_SPLIT); else JMC_BULK(true, PART_COPY);
+    } else {
+        if (k1 == PART_MERGE) JMC_BULK(false, PART_MERGE); else JMC_BULK(false, PART_COPY);
+    }
+#undef JMC_BULK
+    JMC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return JMC_OK;
 }
 
 /* Can the host prove that every access of this job is 16-byte aligned?  (1080p, 4K, 720p ... are.) */
@@ -89,6 +142,10 @@ static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     (void)ctx->sm_count;
     const bool wide = all_wide(j, p);
     const int k1 = p.part[1].kind == PART_NONE ? PART_COPY : p.part[1].kind;
+    if (wide && !getenv_flag("JMC_NO_BULK")) {
+        int r = launch_bulk(ctx, p, k1, stream);
+        if (r != 1) return r;                        /* 1: geometry does not fit the bulk kernel, use LDG/STG */
+    }
 #define JMC_LAUNCH(TT, K1)                                                                               \
     do {                                                                                                 \
         if (wide) planes_kernel<PlaneCfg, TT, K1, true><<<grid, PlaneCfg::THREADS, 0, stream>>>(p);      \

@@ -369,6 +369,150 @@ __global__ void __launch_bounds__(C::THREADS, WIDE_ONLY ? C::BLOCKS_PER_SM : 2) 
 }
 
 /* ========================================================================================== */
+/* Bulk-copy-engine variant of the plane kernel (cp.async.bulk, SASS UBLKCP: the 1-D form of TMA). */
+/* ========================================================================================== */
+/* Used whenever the host has proved 16-byte alignment of everything (1080p, 4K, ...).  A tile is
+ * `rows_per_tile` rows of one part; one CTA per tile:
+ *   pitched -> tight : one bulk load per row (global, pitched) into CONTIGUOUS shared memory, then
+ *                      ONE bulk store of the whole tile (the tight side is contiguous);
+ *   tight -> pitched : one bulk load of the whole tile, one bulk store per row;
+ *   SPLIT / MERGE    : the same, with the threads de-/interleaving shared -> shared (prmt) in between.
+ * No register staging, no per-thread address arithmetic for the copies; measured +0.8 % (1080p) to
+ * +1.7 % (4K) over the LDG/STG kernel (profiles/r1_sweep3_bulk_copy.csv). */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)),
+        "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      /* smem may be released once it has been read */
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+struct BulkParams {
+    FrameSet pitched, tight;
+    uint32_t n_frames;
+    uint32_t rows_per_tile;
+    uint32_t tiles[2];        /* tiles per frame of part 0 / part 1 */
+    Part part[2];             /* Part::tiles unused here */
+};
+
+constexpr int BULK_THREADS = 128;
+
+template <bool TO_TIGHT, int KIND1>
+__global__ void __launch_bounds__(BULK_THREADS) bulk_planes_kernel(const __grid_constant__ BulkParams p)
+{
+    extern __shared__ __align__(128) uint8_t bulk_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t tpf = p.tiles[0] + p.tiles[1];
+    const uint32_t f = blockIdx.x / tpf;
+    uint32_t r = blockIdx.x - f * tpf;
+    const bool second = r >= p.tiles[0];
+    if (second) r -= p.tiles[0];
+    const Part &pt = second ? p.part[1] : p.part[0];
+    uint8_t *pp = frame_ptr(p.pitched, f) + pt.p_off;
+    uint8_t *tp = frame_ptr(p.tight, f);
+    const uint32_t r0 = r * p.rows_per_tile;
+    const uint32_t nr = min(p.rows_per_tile, pt.rows - r0);
+    const uint32_t re = pt.row_elems;
+    const size_t pitch = (size_t)pt.p_pitch;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+
+    if (!second || KIND1 == PART_COPY) {
+        if (threadIdx.x != 0) return;                     /* the copy engine does all the work */
+        uint8_t *t = tp + pt.a_off + (size_t)r0 * re;
+        mbar_expect_tx(&bar, nr * re);
+        if (TO_TIGHT) {
+            for (uint32_t i = 0; i < nr; i++) bulk_g2s(bulk_smem + (size_t)i * re, pp + (size_t)(r0 + i) * pitch, re, &bar);
+            mbar_wait(&bar, 0);
+            bulk_s2g(t, bulk_smem, nr * re);
+        } else {
+            bulk_g2s(bulk_smem, t, nr * re, &bar);
+            mbar_wait(&bar, 0);
+            for (uint32_t i = 0; i < nr; i++) bulk_s2g(pp + (size_t)(r0 + i) * pitch, bulk_smem + (size_t)i * re, re);
+        }
+        bulk_commit_wait_read();
+    } else {
+        /* chroma: re = pairs per row, 2*re interleaved bytes per pitched row */
+        uint8_t *s_uv = bulk_smem;
+        uint8_t *s_u = bulk_smem + (size_t)p.rows_per_tile * 2 * re;
+        uint8_t *s_v = s_u + (size_t)p.rows_per_tile * re;
+        uint8_t *tu = tp + pt.a_off + (size_t)r0 * re, *tv = tp + pt.b_off + (size_t)r0 * re;
+        const uint32_t nvec = nr * re / 16;               /* 16 bytes of U and of V per step */
+        if (KIND1 == PART_SPLIT) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar, nr * 2 * re);
+                for (uint32_t i = 0; i < nr; i++) bulk_g2s(s_uv + (size_t)i * 2 * re, pp + (size_t)(r0 + i) * pitch, 2 * re, &bar);
+            }
+            mbar_wait(&bar, 0);
+            for (uint32_t v = threadIdx.x; v < nvec; v += BULK_THREADS) {
+                const uint4 a = *(const uint4 *)(s_uv + (size_t)v * 32), b = *(const uint4 *)(s_uv + (size_t)v * 32 + 16);
+                uint4 u, w;
+                u.x = __byte_perm(a.x, a.y, 0x6420); w.x = __byte_perm(a.x, a.y, 0x7531);
+                u.y = __byte_perm(a.z, a.w, 0x6420); w.y = __byte_perm(a.z, a.w, 0x7531);
+                u.z = __byte_perm(b.x, b.y, 0x6420); w.z = __byte_perm(b.x, b.y, 0x7531);
+                u.w = __byte_perm(b.z, b.w, 0x6420); w.w = __byte_perm(b.z, b.w, 0x7531);
+                *(uint4 *)(s_u + (size_t)v * 16) = u;
+                *(uint4 *)(s_v + (size_t)v * 16) = w;
+            }
+            fence_async_smem();                           /* generic-proxy writes -> visible to the copy engine */
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                bulk_s2g(tu, s_u, nr * re);
+                bulk_s2g(tv, s_v, nr * re);
+                bulk_commit_wait_read();
+            }
+        } else {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&bar, nr * 2 * re);
+                bulk_g2s(s_u, tu, nr * re, &bar);
+                bulk_g2s(s_v, tv, nr * re, &bar);
+            }
+            mbar_wait(&bar, 0);
+            for (uint32_t v = threadIdx.x; v < nvec; v += BULK_THREADS) {
+                const uint4 u = *(const uint4 *)(s_u + (size_t)v * 16), w = *(const uint4 *)(s_v + (size_t)v * 16);
+                uint4 a, b;
+                a.x = __byte_perm(u.x, w.x, 0x5140); a.y = __byte_perm(u.x, w.x, 0x7362);
+                a.z = __byte_perm(u.y, w.y, 0x5140); a.w = __byte_perm(u.y, w.y, 0x7362);
+                b.x = __byte_perm(u.z, w.z, 0x5140); b.y = __byte_perm(u.z, w.z, 0x7362);
+                b.z = __byte_perm(u.w, w.w, 0x5140); b.w = __byte_perm(u.w, w.w, 0x7362);
+                *(uint4 *)(s_uv + (size_t)v * 32) = a;
+                *(uint4 *)(s_uv + (size_t)v * 32 + 16) = b;
+            }
+            fence_async_smem();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (uint32_t i = 0; i < nr; i++) bulk_s2g(pp + (size_t)(r0 + i) * pitch, s_uv + (size_t)i * 2 * re, 2 * re);
+                bulk_commit_wait_read();
+            }
+        }
+    }
+}
+
+/* ========================================================================================== */
 /* NV12 -> RGB24 (+ optional I420)                                                            */
 /* ========================================================================================== */
 struct RgbParams {

@@ -239,3 +239,13 @@ def test_random_intel_crops_against_oracle(ctx, seed):
             cc = dict(c, op="intelenc", i420=i420)
             _, _, want = K.run_intelenc(chk, cc)
             assert np.array_equal(G.gpu_intelenc(ctx, cc), want), cc
+
+
+@pytest.mark.parametrize("c", [c for c in GPU_CASES if c["op"] in ("nvdec", "nvenc", "intelenc", "inteldec")
+                               and (c.get("w", c.get("cw", 0)) % 32 == 0) and c.get("kind", "random") == "random"], ids=K.case_id)
+def test_ldg_stg_kernel_still_matches(ctx, c, monkeypatch):
+    """16-byte-aligned geometries normally take the bulk-copy (cp.async.bulk) kernel; JMC_NO_BULK=1
+    routes them through the LDG/STG vector kernel, which must give the same bytes."""
+    monkeypatch.setenv("JMC_NO_BULK", "1")
+    out = G.run_case_gpu(ctx, c)
+    assert K.sha(out) == GOLD[K.case_id(c)]["sha256"]

@@ -139,6 +139,152 @@ __global__ void plain_copy(const uint4 *__restrict__ s, uint4 *__restrict__ d, s
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d[i] = s[i];
 }
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Experiment: the same NV12 -> I420 conversion with the bulk-copy engine (cp.async.bulk, "1-D TMA").
+ * Luma tile: ROWS row loads (pitch -> contiguous smem) + ONE contiguous bulk store.  Chroma tile:
+ * row loads, threads de-interleave smem -> smem with prmt, two bulk stores.  One CTA per tile.
+ * ---------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)),
+        "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_wait_read()
+{
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+struct BulkParams {
+    const uint8_t *src; size_t src_stride; uint8_t *dst; size_t dst_stride;
+    int w, h, pitch, n_frames, rows_y, rows_c;
+    uint32_t tiles_y, tiles_c;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) bulk_i420_kernel(const __grid_constant__ BulkParams p)
+{
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t tpf = p.tiles_y + p.tiles_c;
+    const uint32_t f = blockIdx.x / tpf;
+    uint32_t r = blockIdx.x - f * tpf;
+    const uint8_t *sp = p.src + (size_t)f * p.src_stride;
+    uint8_t *dp = p.dst + (size_t)f * p.dst_stride;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (r < p.tiles_y) {
+        if (threadIdx.x != 0) return;
+        const int r0 = r * p.rows_y, nr = min(p.rows_y, p.h - r0);
+        mbar_expect_tx(&bar, (uint32_t)nr * p.w);
+        for (int i = 0; i < nr; i++) bulk_g2s(smem + (size_t)i * p.w, sp + (size_t)(r0 + i) * p.pitch, p.w, &bar);
+        mbar_wait(&bar, 0);
+        bulk_s2g(dp + (size_t)r0 * p.w, smem, (uint32_t)nr * p.w);
+        bulk_commit_wait_read();
+    } else {
+        r -= p.tiles_y;
+        const int ch = p.h >> 1, cw = p.w >> 1;
+        const int r0 = r * p.rows_c, nr = min(p.rows_c, ch - r0);
+        uint8_t *s_uv = smem, *s_u = smem + (size_t)p.rows_c * p.w, *s_v = s_u + (size_t)p.rows_c * cw;
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, (uint32_t)nr * p.w);
+            for (int i = 0; i < nr; i++) bulk_g2s(s_uv + (size_t)i * p.w, sp + (size_t)p.pitch * p.h + (size_t)(r0 + i) * p.pitch, p.w, &bar);
+        }
+        mbar_wait(&bar, 0);
+        const int nvec = nr * cw / 16;                       /* 16 output bytes of U (and V) per step */
+        for (int v = threadIdx.x; v < nvec; v += THREADS) {
+            const uint4 a = *(const uint4 *)(s_uv + (size_t)v * 32), b = *(const uint4 *)(s_uv + (size_t)v * 32 + 16);
+            uint4 u, w4;
+            u.x = __byte_perm(a.x, a.y, 0x6420); w4.x = __byte_perm(a.x, a.y, 0x7531);
+            u.y = __byte_perm(a.z, a.w, 0x6420); w4.y = __byte_perm(a.z, a.w, 0x7531);
+            u.z = __byte_perm(b.x, b.y, 0x6420); w4.z = __byte_perm(b.x, b.y, 0x7531);
+            u.w = __byte_perm(b.z, b.w, 0x6420); w4.w = __byte_perm(b.z, b.w, 0x7531);
+            *(uint4 *)(s_u + (size_t)v * 16) = u;
+            *(uint4 *)(s_v + (size_t)v * 16) = w4;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const size_t luma = (size_t)p.w * p.h;
+            bulk_s2g(dp + luma + (size_t)r0 * cw, s_u, (uint32_t)nr * cw);
+            bulk_s2g(dp + luma + (size_t)cw * ch + (size_t)r0 * cw, s_v, (uint32_t)nr * cw);
+            bulk_commit_wait_read();
+        }
+    }
+}
+
+struct BulkRun { BulkParams p; uint32_t grid; size_t smem; };
+template <int THREADS> static void launch_bulk(void *arg)
+{
+    BulkRun *r = (BulkRun *)arg;
+    bulk_i420_kernel<THREADS><<<r->grid, THREADS, r->smem>>>(r->p);
+}
+
+template <int THREADS> static void run_bulk(int rows_y, int rows_c, bool verify)
+{
+    for (const Geom &g : GEOMS) {
+        BulkRun r;
+        memset(&r, 0, sizeof(r));
+        const size_t surf = (size_t)g.pitch * g.h * 3 / 2, tight = (size_t)g.w * g.h * 3 / 2;
+        r.p = { g_a, surf, g_b, tight, g.w, g.h, g.pitch, g.n, rows_y, rows_c,
+                (uint32_t)((g.h + rows_y - 1) / rows_y), (uint32_t)((g.h / 2 + rows_c - 1) / rows_c) };
+        r.grid = (r.p.tiles_y + r.p.tiles_c) * g.n;
+        const size_t sy = (size_t)rows_y * g.w, sc = (size_t)rows_c * g.w * 2;
+        r.smem = sy > sc ? sy : sc;
+        CK(cudaFuncSetAttribute(bulk_i420_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem));
+        float ms = time_launches(launch_bulk<THREADS>, &r, 20);
+        const double bytes = 3.0 * g.w * g.h * g.n;
+        printf("bulk,%s,T%d,rowsY%d,rowsC%d,smem%zu,grid%u,%.4f ms,%.1f GB/s", g.name, THREADS, rows_y, rows_c, r.smem, r.grid, ms, bytes / ms / 1e6);
+        if (verify) {
+            /* compare with the plane kernel's output on frames 0 and n-1 */
+            std::vector<uint8_t> a(tight), b(tight);
+            int bad = 0;
+            for (int f : {0, g.n - 1}) {
+                CK(cudaMemcpy(a.data(), g_b + (size_t)f * tight, tight, cudaMemcpyDeviceToHost));
+                PlaneRun pr;
+                memset(&pr, 0, sizeof(pr));
+                typedef Cfg<256, 4, 1, 1, 4> C;
+                pr.p.pitched = { g_a, surf, nullptr };
+                pr.p.tight = { g_c, tight, nullptr };
+                pr.p.n_frames = g.n; pr.p.to_tight = 1;
+                pr.p.part[0] = mk_part<C>(PART_COPY, g.h, g.w, 0, g.pitch, 0, 0);
+                pr.p.part[1] = mk_part<C>(PART_SPLIT, g.h / 2, g.w / 2, (int64_t)g.pitch * g.h, g.pitch, (int64_t)g.w * g.h, (int64_t)g.w * g.h * 5 / 4);
+                pr.p.tiles_per_frame = pr.p.part[0].tiles + pr.p.part[1].tiles;
+                pr.p.total_tiles = pr.p.tiles_per_frame * g.n;
+                pr.grid = pr.p.total_tiles;
+                launch_planes<C, true, PART_SPLIT>(&pr);
+                CK(cudaDeviceSynchronize());
+                CK(cudaMemcpy(b.data(), g_c + (size_t)f * tight, tight, cudaMemcpyDeviceToHost));
+                bad += memcmp(a.data(), b.data(), tight) != 0;
+            }
+            printf(",%s", bad ? "MISMATCH" : "bit-exact vs planes_kernel");
+        }
+        printf("\n");
+        fflush(stdout);
+    }
+}
+
 int main(int argc, char **argv)
 {
     const char *only = argc > 1 ? argv[1] : "all";
@@ -199,6 +345,23 @@ int main(int argc, char **argv)
         run_planes<Cfg<256, 4, 1, 0, 4>>("gops", 2, ALL);
         run_planes<Cfg<256, 2, 1, 0, 8>>("gops", 1, ALL);
         run_planes<Cfg<256, 2, 1, 0, 8>>("gops", 2, ALL);
+    }
+    if (!strcmp(only, "all") || !strcmp(only, "bulk")) {
+        /* distinct content so that the comparison means something */
+        {
+            std::vector<uint8_t> h((size_t)64 << 20);
+            uint32_t x = 12345;
+            for (auto &v : h) { x = x * 1664525u + 1013904223u; v = (uint8_t)(x >> 24); }
+            for (size_t off = 0; off + h.size() <= sz; off += h.size()) CK(cudaMemcpy(g_a + off, h.data(), h.size(), cudaMemcpyHostToDevice));
+        }
+        run_bulk<128>(8, 8, true);
+        run_bulk<128>(4, 4, false);
+        run_bulk<128>(16, 8, false);
+        run_bulk<128>(8, 4, false);
+        run_bulk<256>(8, 8, false);
+        run_bulk<64>(8, 8, false);
+        run_bulk<128>(2, 2, false);
+        run_planes<Cfg<256, 4, 1, 1, 4>>("cmp", 0, 1 << 20);
     }
     if (!strcmp(only, "all") || !strcmp(only, "rgb")) {
         for (int fused = 0; fused < 2; fused++) {
