@@ -188,6 +188,39 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     if (total == 0) return JMC_OK;
     if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }
     p.total_tasks = (uint32_t)total;
+    /* bulk-copy-engine variant: everything 16-byte aligned, chroma rows 16-byte multiples (w % 32 == 0),
+     * 10*w bytes of shared memory */
+    {
+        uint64_t bits = (uint64_t)j->surf_y_off | (uint64_t)j->surf_uv_off | (uint32_t)j->pitch | (uint32_t)j->rgb_pitch | (uint32_t)j->width;
+        if (fused) bits |= (uint32_t)(j->width >> 1);            /* U / V rows are bulk-stored too */
+        const jmc_frames *sets[3] = { &j->surf, &j->rgb, fused ? &j->tight : nullptr };
+        bool ok = !getenv_flag("JMC_NO_BULK") && (size_t)j->width * 10 <= 96 * 1024;
+        for (int i = 0; i < 3 && ok; i++) {
+            if (!sets[i]) continue;
+            if (sets[i]->list) ok = (j->flags & JMC_JOB_ALIGNED16) != 0;
+            else bits |= (uint64_t)(uintptr_t)sets[i]->base | (uint64_t)sets[i]->stride;
+        }
+        if (fused) bits |= (uint64_t)j->tight_u_off | (uint64_t)j->tight_v_off;
+        if (ok && (bits & 15) == 0) {
+            RgbBulkParams b;
+            b.surf = p.surf; b.tight = p.tight; b.rgb = p.rgb;
+            b.n_frames = p.n_frames; b.width = p.width; b.height = p.height; b.pitch = p.pitch;
+            b.y_off = p.y_off; b.uv_off = p.uv_off; b.u_off = p.u_off; b.v_off = p.v_off;
+            b.rgb_pitch = p.rgb_pitch; b.fused = p.fused; b.row_pairs = p.row_pairs;
+            const uint64_t ctas = (uint64_t)b.row_pairs * b.n_frames;
+            if (ctas <= 0x7fffffffull) {
+                static bool attr_done[64];
+                if (ctx->device < 64 && !attr_done[ctx->device]) {
+                    JMC_CUDA(cudaFuncSetAttribute(rgb_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+                    attr_done[ctx->device] = true;
+                }
+                rgb_bulk_kernel<<<(uint32_t)ctas, RGB_BULK_THREADS, (size_t)j->width * 10, stream>>>(b);
+                JMC_CUDA(cudaGetLastError());
+                ctx->launches++;
+                return JMC_OK;
+            }
+        }
+    }
     constexpr uint32_t WARPS = RgbCfg::THREADS / 32;
     const uint32_t blocks_needed = (p.total_tasks + WARPS - 1) / WARPS;
     const uint32_t grid = blocks_needed;             /* one warp per (row pair, 512-pixel segment) task */

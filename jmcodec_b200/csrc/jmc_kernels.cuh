@@ -690,4 +690,101 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
     }
 }
 
+
+/* ---- bulk-copy-engine variant of the RGB kernel ------------------------------------------------
+ * One CTA per (frame, row pair), whole width: three bulk loads (two luma rows, one chroma row) into
+ * shared memory, threads convert shared -> shared (same dp2a / cvt.pack.sat arithmetic as above, 16
+ * pixels x 2 rows per step), then two bulk stores of 3*w bytes (plus, fused: ONE 2*w-byte store of
+ * the two luma rows straight from the input buffer, and the de-interleaved U / V rows).
+ * Needs 9*w (+ w fused) bytes of shared memory and everything 16-byte aligned; the host checks. */
+struct RgbBulkParams {
+    FrameSet surf, tight, rgb;
+    uint32_t n_frames;
+    int32_t width, height, pitch;
+    int64_t y_off, uv_off;
+    int64_t u_off, v_off;
+    int32_t rgb_pitch;
+    int32_t fused;
+    uint32_t row_pairs;
+};
+
+constexpr int RGB_BULK_THREADS = 128;
+
+__global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid_constant__ RgbBulkParams p)
+{
+    extern __shared__ __align__(128) uint8_t rs[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t f = blockIdx.x / p.row_pairs;
+    const uint32_t rp = blockIdx.x - f * p.row_pairs;
+    const uint32_t w = (uint32_t)p.width, h = (uint32_t)p.height, cw = w >> 1, ch = h >> 1;
+    const uint32_t y0 = rp * 2;
+    const bool two = y0 + 1 < h;
+    const uint32_t cy = min(rp, ch - 1);
+    const uint8_t *sp = frame_ptr(p.surf, f);
+    uint8_t *rgbp = frame_ptr(p.rgb, f) + (size_t)y0 * p.rgb_pitch;
+    uint8_t *s_y = rs;                    /* 2*w : luma rows y0, y0+1 (contiguous: also the fused luma store) */
+    uint8_t *s_uv = rs + 2 * (size_t)w;   /* w   */
+    uint8_t *s_rgb = rs + 3 * (size_t)w;  /* 6*w : two RGB rows */
+    uint8_t *s_u = rs + 9 * (size_t)w;    /* w/2 + w/2 (fused) */
+    uint8_t *s_v = s_u + cw;
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        mbar_expect_tx(&bar, (two ? 3u : 2u) * w);
+        const uint8_t *yrow = sp + p.y_off + (size_t)y0 * p.pitch;
+        bulk_g2s(s_y, yrow, w, &bar);
+        if (two) bulk_g2s(s_y + w, yrow + p.pitch, w, &bar);
+        bulk_g2s(s_uv, sp + p.uv_off + (size_t)cy * p.pitch, w, &bar);
+    }
+    __syncthreads();
+    mbar_wait(&bar, 0);
+    const bool do_uv = p.fused && rp < ch;
+    for (uint32_t unit = threadIdx.x; unit < (w >> 4); unit += RGB_BULK_THREADS) {
+        const uint4 uv = *(const uint4 *)(s_uv + unit * 16);
+        const uint32_t uvw[4] = {uv.x, uv.y, uv.z, uv.w};
+        int cr[8], cg[8], cb[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            cr[2 * j] = dp2a_lo(COEF_RV, uvw[j], RGB_CR);  cr[2 * j + 1] = dp2a_hi(COEF_RV, uvw[j], RGB_CR);
+            cg[2 * j] = dp2a_lo(COEF_GUV, uvw[j], RGB_CG); cg[2 * j + 1] = dp2a_hi(COEF_GUV, uvw[j], RGB_CG);
+            cb[2 * j] = dp2a_lo(COEF_BU, uvw[j], RGB_CB);  cb[2 * j + 1] = dp2a_hi(COEF_BU, uvw[j], RGB_CB);
+        }
+        if (do_uv) {
+            uint2 u, v;
+            u.x = __byte_perm(uv.x, uv.y, 0x6420); v.x = __byte_perm(uv.x, uv.y, 0x7531);
+            u.y = __byte_perm(uv.z, uv.w, 0x6420); v.y = __byte_perm(uv.z, uv.w, 0x7531);
+            *(uint2 *)(s_u + unit * 8) = u;
+            *(uint2 *)(s_v + unit * 8) = v;
+        }
+#pragma unroll
+        for (int row = 0; row < 2; row++) {
+            if (row == 1 && !two) break;
+            const uint4 yy = *(const uint4 *)(s_y + (size_t)row * w + unit * 16);
+            const uint32_t yw[4] = {yy.x, yy.y, yy.z, yy.w};
+            uint32_t o[12];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                rgb4(yw[j], cr[2 * j], cg[2 * j], cb[2 * j], cr[2 * j + 1], cg[2 * j + 1], cb[2 * j + 1], o + 3 * j);
+            uint4 *d = (uint4 *)(s_rgb + (size_t)row * 3 * w + unit * 48);
+            d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            d[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        bulk_s2g(rgbp, s_rgb, 3 * w);
+        if (two) bulk_s2g(rgbp + p.rgb_pitch, s_rgb + 3 * (size_t)w, 3 * w);
+        if (p.fused) {
+            uint8_t *tp = frame_ptr(p.tight, f);
+            bulk_s2g(tp + (size_t)y0 * w, s_y, (two ? 2u : 1u) * w);     /* tight luma rows are contiguous */
+            if (do_uv) {
+                bulk_s2g(tp + p.u_off + (size_t)rp * cw, s_u, cw);
+                bulk_s2g(tp + p.v_off + (size_t)rp * cw, s_v, cw);
+            }
+        }
+        bulk_commit_wait_read();
+    }
+}
+
 } /* namespace jmc */

@@ -249,3 +249,18 @@ def test_ldg_stg_kernel_still_matches(ctx, c, monkeypatch):
     monkeypatch.setenv("JMC_NO_BULK", "1")
     out = G.run_case_gpu(ctx, c)
     assert K.sha(out) == GOLD[K.case_id(c)]["sha256"]
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("c", [c for c in K.rgb_cases() if c["w"] % 16 == 0 and c["kind"] == "random"], ids=K.case_id)
+def test_rgb_ldg_stg_kernel_still_matches(ctx, c, fused, monkeypatch):
+    """Same for the RGB kernels: JMC_NO_BULK=1 selects the warp-per-task LDG/STG kernel."""
+    monkeypatch.setenv("JMC_NO_BULK", "1")
+    if fused:
+        rgb, tight = G.gpu_rgb(ctx, c, fused=True)
+        want = np.full(tight.size, synth.OUT_FILL, np.uint8)
+        oracle.best().nvdec_output_frame(K.rgb_input(c), c["pitch"], c["w"], c["h"], 1, want, want.size)
+        assert np.array_equal(tight, want)
+    else:
+        rgb = G.gpu_rgb(ctx, c)
+    assert K.sha(rgb) == GOLD[K.case_id(c)]["sha256"]
