@@ -243,3 +243,22 @@ def test_full_size_round_trip_and_samples(ctx, geom):
         assert sums[f] == sums[f % 8]
     for d in (dsurf, dtight, dback):
         ctx.free(d)
+
+
+# --------------------------------------------------------------------------------------------
+# tools/jm_streams: the whole-box driver written in C++ against include/jmc_cuda.h only
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["e2e", "device"])
+def test_cpp_streams_driver(mode):
+    import json
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "jm_streams")
+    if not os.path.exists(exe):
+        pytest.skip("tools/jm_streams not built")
+    p = subprocess.run([exe, "--gpus", "1", "--streams", "5", "--frames", "24", "--batch", "10", "--width", "640", "--height", "360",
+                        "--pitch", "768", "--mode", mode], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr
+    d = json.loads(p.stdout)
+    assert d["mode"] == mode and d["n_gpus"] == 1 and d["frames"] == 5 * 24
+    assert d["per_gpu"][0]["streams"] == 5 and d["frames_per_s"] > 0
