@@ -262,3 +262,76 @@ def test_cpp_streams_driver(mode):
     d = json.loads(p.stdout)
     assert d["mode"] == mode and d["n_gpus"] == 1 and d["frames"] == 5 * 24
     assert d["per_gpu"][0]["streams"] == 5 and d["frames_per_s"] > 0
+
+
+def test_many_handles_many_threads(J):
+    """One handle per host thread, several handles per process (SURVEY.md 8b "Threading"): four threads
+    decode their own streams concurrently on one GPU; every frame must still be bit-exact."""
+    import threading
+    w, h, pitch, n = 352, 288, 512, 12
+    need = w * h * 3 // 2
+    chk = oracle.best()
+    errors = []
+
+    def worker(tid):
+        try:
+            dec = J.NvDec(0)
+            assert dec.init(J.NvDec.CODEC_RAW_NV12, tid % 2) == 0
+            out = np.empty(need, np.uint8)
+            want = np.empty(need, np.uint8)
+            for f in range(n):
+                s = synth.nv12_surface(w, h, pitch, 40 + tid, f)
+                assert dec.decode_frame(J.NvDec.raw_packet(s, w, h, pitch)) == (0, 1)
+                assert dec.output_frame(out, need) == (need, need)
+                chk.nvdec_output_frame(s, pitch, w, h, tid % 2, want, need)
+                assert np.array_equal(out, want), (tid, f)
+            dec.deinit()
+        except Exception as e:      # noqa: BLE001
+            errors.append((tid, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+
+
+def test_8k_frames_take_the_bulk_path_with_smaller_tiles(ctx):
+    """7680x4320: rows per tile shrink to fit shared memory (bulk planes) and 10*w bytes still fit (bulk RGB)."""
+    w, h, pitch = 7680, 4320, 7680
+    chk = oracle.best()
+    s = synth.nv12_surface(w, h, pitch, 50, 0)
+    need = w * h * 3 // 2
+    ds = ctx.upload(s)
+    dt = ctx.alloc(need)
+    drgb = ctx.alloc(3 * w * h)
+    j = ctx.job_rgb(w, h, pitch, 3 * w, True)
+    j.n_frames, j.surf.base, j.tight.base, j.rgb.base = 1, ds, dt, drgb
+    ctx.convert(j)
+    got = np.empty(need, np.uint8)
+    ctx.d2h(got, dt)
+    want = np.empty(need, np.uint8)
+    chk.nvdec_output_frame(s, pitch, w, h, 1, want, need)
+    assert np.array_equal(got, want)
+    rgb = np.empty(3 * w * h, np.uint8)
+    ctx.d2h(rgb, drgb)
+    wrgb = np.empty(3 * w * h, np.uint8)
+    oracle.nv12_to_rgb24(s, pitch, w, h, wrgb, 3 * w)
+    assert np.array_equal(rgb, wrgb)
+    ctx.memset(dt, 0, need)
+    j2 = ctx.job_nvdec(w, h, pitch, 1)
+    j2.n_frames, j2.surf.base, j2.tight.base = 1, ds, dt
+    ctx.convert(j2)
+    ctx.d2h(got, dt)
+    assert np.array_equal(got, want)
+    # and back: pack the I420 frame into a fresh surface
+    dback = ctx.alloc(s.size)
+    k = ctx.job_nvenc(w, h, pitch, 0x10)
+    k.n_frames, k.surf.base, k.tight.base = 1, dback, dt
+    ctx.convert(k)
+    back = np.empty(s.size, np.uint8)
+    ctx.d2h(back, dback)
+    assert np.array_equal(back, s)
+    for d in (ds, dt, drgb, dback):
+        ctx.free(d)
