@@ -692,11 +692,11 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
 
 
 /* ---- bulk-copy-engine variant of the RGB kernel ------------------------------------------------
- * One CTA per (frame, row pair), whole width: three bulk loads (two luma rows, one chroma row) into
- * shared memory, threads convert shared -> shared (same dp2a / cvt.pack.sat arithmetic as above, 16
- * pixels x 2 rows per step), then two bulk stores of 3*w bytes (plus, fused: ONE 2*w-byte store of
- * the two luma rows straight from the input buffer, and the de-interleaved U / V rows).
- * Needs 9*w (+ w fused) bytes of shared memory and everything 16-byte aligned; the host checks. */
+ * One CTA per (frame, row pair, column segment of <= 2048 pixels): three bulk loads (two luma rows,
+ * one chroma row) into shared memory, threads convert shared -> shared (same dp2a / cvt.pack.sat
+ * arithmetic as above, 16 pixels x 2 rows per step), then two bulk stores of 3*seg bytes (plus, fused:
+ * the two luma rows straight from the input buffer and the de-interleaved U / V rows).
+ * 10*seg_w bytes of shared memory (<= 20 KB, ~11 CTAs per SM); everything 16-byte aligned, host-checked. */
 struct RgbBulkParams {
     FrameSet surf, tight, rgb;
     uint32_t n_frames;
@@ -706,6 +706,8 @@ struct RgbBulkParams {
     int32_t rgb_pitch;
     int32_t fused;
     uint32_t row_pairs;
+    uint32_t segs;            /* column segments per row pair */
+    uint32_t seg_w;           /* pixels per segment (multiple of 32); the last one takes the remainder */
 };
 
 constexpr int RGB_BULK_THREADS = 128;
@@ -714,26 +716,31 @@ __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid
 {
     extern __shared__ __align__(128) uint8_t rs[];
     __shared__ __align__(8) uint64_t bar;
-    const uint32_t f = blockIdx.x / p.row_pairs;
-    const uint32_t rp = blockIdx.x - f * p.row_pairs;
-    const uint32_t w = (uint32_t)p.width, h = (uint32_t)p.height, cw = w >> 1, ch = h >> 1;
+    const uint32_t per_frame = p.row_pairs * p.segs;
+    const uint32_t f = blockIdx.x / per_frame;
+    const uint32_t t = blockIdx.x - f * per_frame;
+    const uint32_t rp = t / p.segs, seg = t - rp * p.segs;
+    const uint32_t W = (uint32_t)p.width, h = (uint32_t)p.height, cw = W >> 1, ch = h >> 1;
+    const uint32_t x0 = seg * p.seg_w;                     /* first pixel of this segment */
+    const uint32_t w = min(p.seg_w, W - x0);               /* pixels in this segment (multiple of 16) */
     const uint32_t y0 = rp * 2;
     const bool two = y0 + 1 < h;
     const uint32_t cy = min(rp, ch - 1);
     const uint8_t *sp = frame_ptr(p.surf, f);
-    uint8_t *rgbp = frame_ptr(p.rgb, f) + (size_t)y0 * p.rgb_pitch;
-    uint8_t *s_y = rs;                    /* 2*w : luma rows y0, y0+1 (contiguous: also the fused luma store) */
-    uint8_t *s_uv = rs + 2 * (size_t)w;   /* w   */
-    uint8_t *s_rgb = rs + 3 * (size_t)w;  /* 6*w : two RGB rows */
-    uint8_t *s_u = rs + 9 * (size_t)w;    /* w/2 + w/2 (fused) */
-    uint8_t *s_v = s_u + cw;
+    uint8_t *rgbp = frame_ptr(p.rgb, f) + (size_t)y0 * p.rgb_pitch + 3 * (size_t)x0;
+    const uint32_t sw = p.seg_w;                           /* shared-memory row stride */
+    uint8_t *s_y = rs;                    /* 2*sw : luma rows y0, y0+1 */
+    uint8_t *s_uv = rs + 2 * (size_t)sw;  /* sw   */
+    uint8_t *s_rgb = rs + 3 * (size_t)sw; /* 6*sw : two RGB rows */
+    uint8_t *s_u = rs + 9 * (size_t)sw;   /* sw/2 + sw/2 (fused) */
+    uint8_t *s_v = s_u + (sw >> 1);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
         mbar_expect_tx(&bar, (two ? 3u : 2u) * w);
-        const uint8_t *yrow = sp + p.y_off + (size_t)y0 * p.pitch;
+        const uint8_t *yrow = sp + p.y_off + (size_t)y0 * p.pitch + x0;
         bulk_g2s(s_y, yrow, w, &bar);
-        if (two) bulk_g2s(s_y + w, yrow + p.pitch, w, &bar);
-        bulk_g2s(s_uv, sp + p.uv_off + (size_t)cy * p.pitch, w, &bar);
+        if (two) bulk_g2s(s_y + sw, yrow + p.pitch, w, &bar);
+        bulk_g2s(s_uv, sp + p.uv_off + (size_t)cy * p.pitch + x0, w, &bar);
     }
     __syncthreads();
     mbar_wait(&bar, 0);
@@ -758,13 +765,13 @@ __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid
 #pragma unroll
         for (int row = 0; row < 2; row++) {
             if (row == 1 && !two) break;
-            const uint4 yy = *(const uint4 *)(s_y + (size_t)row * w + unit * 16);
+            const uint4 yy = *(const uint4 *)(s_y + (size_t)row * sw + unit * 16);
             const uint32_t yw[4] = {yy.x, yy.y, yy.z, yy.w};
             uint32_t o[12];
 #pragma unroll
             for (int j = 0; j < 4; j++)
                 rgb4(yw[j], cr[2 * j], cg[2 * j], cb[2 * j], cr[2 * j + 1], cg[2 * j + 1], cb[2 * j + 1], o + 3 * j);
-            uint4 *d = (uint4 *)(s_rgb + (size_t)row * 3 * w + unit * 48);
+            uint4 *d = (uint4 *)(s_rgb + (size_t)row * 3 * sw + unit * 48);
             d[0] = make_uint4(o[0], o[1], o[2], o[3]);
             d[1] = make_uint4(o[4], o[5], o[6], o[7]);
             d[2] = make_uint4(o[8], o[9], o[10], o[11]);
@@ -774,13 +781,14 @@ __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid
     __syncthreads();
     if (threadIdx.x == 0) {
         bulk_s2g(rgbp, s_rgb, 3 * w);
-        if (two) bulk_s2g(rgbp + p.rgb_pitch, s_rgb + 3 * (size_t)w, 3 * w);
+        if (two) bulk_s2g(rgbp + p.rgb_pitch, s_rgb + 3 * (size_t)sw, 3 * w);
         if (p.fused) {
             uint8_t *tp = frame_ptr(p.tight, f);
-            bulk_s2g(tp + (size_t)y0 * w, s_y, (two ? 2u : 1u) * w);     /* tight luma rows are contiguous */
+            bulk_s2g(tp + (size_t)y0 * W + x0, s_y, w);
+            if (two) bulk_s2g(tp + (size_t)(y0 + 1) * W + x0, s_y + sw, w);
             if (do_uv) {
-                bulk_s2g(tp + p.u_off + (size_t)rp * cw, s_u, cw);
-                bulk_s2g(tp + p.v_off + (size_t)rp * cw, s_v, cw);
+                bulk_s2g(tp + p.u_off + (size_t)rp * cw + (x0 >> 1), s_u, w >> 1);
+                bulk_s2g(tp + p.v_off + (size_t)rp * cw + (x0 >> 1), s_v, w >> 1);
             }
         }
         bulk_commit_wait_read();
