@@ -466,6 +466,7 @@ int jm_nvdec_decode_frame(unsigned char *in_buf, int in_data_len, int *got_frame
     if (got_frame) *got_frame = 0;
     if (!c || !got_frame) return 0;
     if (!c->inited || !c->ctx || !c->queue) return 0;         /* decoder never created: the reference swallows -1 (nv_dec.cpp:414-417,491-493) */
+    if (jmc_bind_thread(c->ctx)) return 0;                     /* the reference pushes its context around every call (nv_dec.cpp:378,423) */
     if (!c->is_eof) {                                          /* nv_dec.cpp:486-488 */
         const bool cuvid = c->codec_type != JM_NVDEC_CODEC_RAW_NV12;
         if (in_buf && in_data_len > 0) {
@@ -485,6 +486,7 @@ int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec han
     nvdec_b200 *c = (nvdec_b200 *)handle;
     if (!c || !c->have_cur) return -1;                         /* nv_dec.cpp:757-758 */
     if (!c->d_tight || !out_buf || !out_len) return -1;        /* :768-771 */
+    if (jmc_bind_thread(c->ctx)) return -1;
     const int need = c->cur_w * c->cur_h * 3 / 2;
     if (*out_len < need) return -2;                            /* :773-774 */
     *out_len = 0;                                              /* :776 */

@@ -23,5 +23,9 @@ int jmc_cuda_fail(cudaError_t e, const char *what);
         if (e_ != cudaSuccess) return jmc_cuda_fail(e_, #call); \
     } while (0)
 
+/* Make ctx's device (its primary CUDA context) current on the calling thread.  Every entry point that
+ * touches CUDA outside jmc_* calls this first: a handle may be used from any one thread at a time. */
+int jmc_bind_thread(const jmc_ctx *ctx);
+
 /* kernels (jmc_kernels.cu) */
 int jmc_launch_job(jmc_ctx *ctx, const jmc_job *job, cudaStream_t stream);

@@ -73,6 +73,10 @@ static int bind(const jmc_ctx *c)
 }
 #define JMC_BIND(c) do { int r_ = bind(c); if (r_) return r_; } while (0)
 
+} /* extern "C" */
+int jmc_bind_thread(const jmc_ctx *c) { return bind(c); }
+extern "C" {
+
 int jmc_ctx_destroy(jmc_ctx *c)
 {
     JMC_BIND(c);

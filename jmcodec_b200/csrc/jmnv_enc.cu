@@ -134,6 +134,7 @@ int jm_nvenc_enc_frame(const unsigned char *in_yuv_buf, const int yuv_len, int *
     if (got_packet) *got_packet = 0;
     if (!c || !c->inited) return -1;
     if (!in_yuv_buf || yuv_len <= 0) return 0;                        /* EOS, nv_enc.cpp:113-117 */
+    if (jmc_bind_thread(c->ctx)) return JM_NVENC_ERR_GENERIC;          /* CCudaAutoLock, nv_enc.cpp:1025 */
 
     int idx = -1;                                                     /* nvenc_get_free_frame, :916-927 */
     for (int i = 0; i < JM_NVENC_NUM_SURFACES; i++) if (!c->surf[i].lock_count) { idx = i; break; }

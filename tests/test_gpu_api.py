@@ -335,3 +335,53 @@ def test_8k_frames_take_the_bulk_path_with_smaller_tiles(ctx):
     assert np.array_equal(back, s)
     for d in (ds, dt, drgb, dback):
         ctx.free(d)
+
+
+def test_handles_on_two_devices_interleaved(J):
+    """Handles bound to different GPUs, driven alternately from ONE thread and then from two threads:
+    every API entry must re-bind its own device (the reference pushes/pops its context per call)."""
+    import threading
+    if J.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    w, h, pitch = 320, 200, 384
+    need = w * h * 3 // 2
+    chk = oracle.best()
+    decs = [J.NvDec(d) for d in (0, 1)]
+    for d in decs:
+        assert d.init(J.NvDec.CODEC_RAW_NV12, 1) == 0
+    enc = J.NvEnc(1)
+    assert enc.init(w, h, J.NvEnc.FMT_YV12) == 0
+    out, want = np.empty(need, np.uint8), np.empty(need, np.uint8)
+    for f in range(6):
+        dec = decs[f % 2]
+        s = synth.nv12_surface(w, h, pitch, 60, f)
+        assert dec.decode_frame(J.NvDec.raw_packet(s, w, h, pitch)) == (0, 1)
+        assert enc.enc_frame(synth.i420_frame(w, h, 61, f))[0] == 0        # touches device 1 in between
+        enc.release_surface()
+        assert dec.output_frame(out, need) == (need, need)
+        chk.nvdec_output_frame(s, pitch, w, h, 1, want, need)
+        assert np.array_equal(out, want), f
+
+    errors = []
+
+    def worker(dev):
+        try:
+            o, wn = np.empty(need, np.uint8), np.empty(need, np.uint8)
+            for f in range(8):
+                s = synth.nv12_surface(w, h, pitch, 62 + dev, f)
+                assert decs[dev].decode_frame(J.NvDec.raw_packet(s, w, h, pitch)) == (0, 1)
+                assert decs[dev].output_frame(o, need) == (need, need)
+                chk.nvdec_output_frame(s, pitch, w, h, 1, wn, need)
+                assert np.array_equal(o, wn), (dev, f)
+        except Exception as e:      # noqa: BLE001
+            errors.append((dev, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(d,)) for d in (0, 1)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
+    for d in decs:
+        d.deinit()
+    enc.deinit()
