@@ -139,7 +139,6 @@ static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }
     p.total_tiles = (uint32_t)total;
     const uint32_t grid = p.total_tiles;             /* one CTA per 16 KB tile (see Cfg256x4) */
-    (void)ctx->sm_count;
     const bool wide = all_wide(j, p);
     const int k1 = p.part[1].kind == PART_NONE ? PART_COPY : p.part[1].kind;
     if (wide && !getenv_flag("JMC_NO_BULK")) {
