@@ -145,46 +145,35 @@ __global__ void plain_copy(const uint4 *__restrict__ s, uint4 *__restrict__ d, s
  * Luma tile: ROWS row loads (pitch -> contiguous smem) + ONE contiguous bulk store.  Chroma tile:
  * row loads, threads de-interleave smem -> smem with prmt, two bulk stores.  One CTA per tile.
  * ---------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+__device__ __forceinline__ uint64_t policy_evict_first()
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void bulk_g2s_hint(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar, uint64_t pol)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(dst_smem)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(pol) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void bulk_s2g_hint(void *dst, const void *src_smem, uint32_t bytes, uint64_t pol)
 {
-    asm volatile(
-        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)),
-        "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst, const void *src_smem, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit_wait_read()
-{
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(smem_u32(src_smem)), "r"(bytes), "l"(pol) : "memory");
 }
 
-struct BulkParams {
+struct XBulkParams {
     const uint8_t *src; size_t src_stride; uint8_t *dst; size_t dst_stride;
     int w, h, pitch, n_frames, rows_y, rows_c;
     uint32_t tiles_y, tiles_c;
 };
 
-template <int THREADS>
-__global__ void __launch_bounds__(THREADS) bulk_i420_kernel(const __grid_constant__ BulkParams p)
+/* HINT bit 0: evict_first on loads, bit 1: evict_first on stores */
+template <int THREADS, int HINT = 0>
+__global__ void __launch_bounds__(THREADS) bulk_i420_kernel(const __grid_constant__ XBulkParams p)
 {
+    const uint64_t pol = HINT ? policy_evict_first() : 0;
+#define G2S(d, s_, n, b) do { if (HINT & 1) bulk_g2s_hint(d, s_, n, b, pol); else bulk_g2s(d, s_, n, b); } while (0)
+#define S2G(d, s_, n) do { if (HINT & 2) bulk_s2g_hint(d, s_, n, pol); else bulk_s2g(d, s_, n); } while (0)
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t bar;
     const uint32_t tpf = p.tiles_y + p.tiles_c;
@@ -198,9 +187,9 @@ __global__ void __launch_bounds__(THREADS) bulk_i420_kernel(const __grid_constan
         if (threadIdx.x != 0) return;
         const int r0 = r * p.rows_y, nr = min(p.rows_y, p.h - r0);
         mbar_expect_tx(&bar, (uint32_t)nr * p.w);
-        for (int i = 0; i < nr; i++) bulk_g2s(smem + (size_t)i * p.w, sp + (size_t)(r0 + i) * p.pitch, p.w, &bar);
+        for (int i = 0; i < nr; i++) G2S(smem + (size_t)i * p.w, sp + (size_t)(r0 + i) * p.pitch, p.w, &bar);
         mbar_wait(&bar, 0);
-        bulk_s2g(dp + (size_t)r0 * p.w, smem, (uint32_t)nr * p.w);
+        S2G(dp + (size_t)r0 * p.w, smem, (uint32_t)nr * p.w);
         bulk_commit_wait_read();
     } else {
         r -= p.tiles_y;
@@ -209,7 +198,7 @@ __global__ void __launch_bounds__(THREADS) bulk_i420_kernel(const __grid_constan
         uint8_t *s_uv = smem, *s_u = smem + (size_t)p.rows_c * p.w, *s_v = s_u + (size_t)p.rows_c * cw;
         if (threadIdx.x == 0) {
             mbar_expect_tx(&bar, (uint32_t)nr * p.w);
-            for (int i = 0; i < nr; i++) bulk_g2s(s_uv + (size_t)i * p.w, sp + (size_t)p.pitch * p.h + (size_t)(r0 + i) * p.pitch, p.w, &bar);
+            for (int i = 0; i < nr; i++) G2S(s_uv + (size_t)i * p.w, sp + (size_t)p.pitch * p.h + (size_t)(r0 + i) * p.pitch, p.w, &bar);
         }
         mbar_wait(&bar, 0);
         const int nvec = nr * cw / 16;                       /* 16 output bytes of U (and V) per step */
@@ -227,24 +216,26 @@ __global__ void __launch_bounds__(THREADS) bulk_i420_kernel(const __grid_constan
         __syncthreads();
         if (threadIdx.x == 0) {
             const size_t luma = (size_t)p.w * p.h;
-            bulk_s2g(dp + luma + (size_t)r0 * cw, s_u, (uint32_t)nr * cw);
-            bulk_s2g(dp + luma + (size_t)cw * ch + (size_t)r0 * cw, s_v, (uint32_t)nr * cw);
+            S2G(dp + luma + (size_t)r0 * cw, s_u, (uint32_t)nr * cw);
+            S2G(dp + luma + (size_t)cw * ch + (size_t)r0 * cw, s_v, (uint32_t)nr * cw);
             bulk_commit_wait_read();
         }
     }
 }
+#undef G2S
+#undef S2G
 
-struct BulkRun { BulkParams p; uint32_t grid; size_t smem; };
-template <int THREADS> static void launch_bulk(void *arg)
+struct XBulkRun { XBulkParams p; uint32_t grid; size_t smem; };
+template <int THREADS, int HINT> static void launch_bulk(void *arg)
 {
-    BulkRun *r = (BulkRun *)arg;
-    bulk_i420_kernel<THREADS><<<r->grid, THREADS, r->smem>>>(r->p);
+    XBulkRun *r = (XBulkRun *)arg;
+    bulk_i420_kernel<THREADS, HINT><<<r->grid, THREADS, r->smem>>>(r->p);
 }
 
-template <int THREADS> static void run_bulk(int rows_y, int rows_c, bool verify)
+template <int THREADS, int HINT = 0> static void run_bulk(int rows_y, int rows_c, bool verify)
 {
     for (const Geom &g : GEOMS) {
-        BulkRun r;
+        XBulkRun r;
         memset(&r, 0, sizeof(r));
         const size_t surf = (size_t)g.pitch * g.h * 3 / 2, tight = (size_t)g.w * g.h * 3 / 2;
         r.p = { g_a, surf, g_b, tight, g.w, g.h, g.pitch, g.n, rows_y, rows_c,
@@ -252,10 +243,10 @@ template <int THREADS> static void run_bulk(int rows_y, int rows_c, bool verify)
         r.grid = (r.p.tiles_y + r.p.tiles_c) * g.n;
         const size_t sy = (size_t)rows_y * g.w, sc = (size_t)rows_c * g.w * 2;
         r.smem = sy > sc ? sy : sc;
-        CK(cudaFuncSetAttribute(bulk_i420_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem));
-        float ms = time_launches(launch_bulk<THREADS>, &r, 20);
+        CK(cudaFuncSetAttribute(bulk_i420_kernel<THREADS, HINT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)r.smem));
+        float ms = time_launches(launch_bulk<THREADS, HINT>, &r, 20);
         const double bytes = 3.0 * g.w * g.h * g.n;
-        printf("bulk,%s,T%d,rowsY%d,rowsC%d,smem%zu,grid%u,%.4f ms,%.1f GB/s", g.name, THREADS, rows_y, rows_c, r.smem, r.grid, ms, bytes / ms / 1e6);
+        printf("bulk,%s,T%d,hint%d,rowsY%d,rowsC%d,smem%zu,grid%u,%.4f ms,%.1f GB/s", g.name, THREADS, HINT, rows_y, rows_c, r.smem, r.grid, ms, bytes / ms / 1e6);
         if (verify) {
             /* compare with the plane kernel's output on frames 0 and n-1 */
             std::vector<uint8_t> a(tight), b(tight);
@@ -361,6 +352,10 @@ int main(int argc, char **argv)
         run_bulk<256>(8, 8, false);
         run_bulk<64>(8, 8, false);
         run_bulk<128>(2, 2, false);
+        run_bulk<128, 1>(8, 8, true);
+        run_bulk<128, 2>(8, 8, true);
+        run_bulk<128, 3>(8, 8, true);
+        run_bulk<128, 0>(8, 8, false);
         run_planes<Cfg<256, 4, 1, 1, 4>>("cmp", 0, 1 << 20);
     }
     if (!strcmp(only, "all") || !strcmp(only, "rgb")) {
