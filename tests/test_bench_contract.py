@@ -1,0 +1,58 @@
+"""The bench.py JSON contract (what the driver parses), checked on the CPU for the reference arm and
+on the GPU for the product arm."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches"}
+
+
+def _run(args, timeout):
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, p.stdout          # exactly ONE JSON line
+    return json.loads(lines[0])
+
+
+def test_reference_arm_line():
+    d = _run(["--impl", "reference", "--steps", "2", "--warmup", "1"], 300)
+    assert BASE_KEYS <= set(d)
+    assert d["impl"] == "reference" and d["gpu_launches"] == 0
+    assert d["metric"] == "NV12->I420 frames/s" and d["unit"] == "frames/s" and d["higher_is_better"] is True
+    assert d["dtype"] == "u8" and d["data"] == "synthetic" and d["vs_baseline"] is None
+    assert d["config"]["workload"] == "nv12_to_i420_1080p_x300_pitch2048" and "model" not in d["config"]
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["value"] > 100
+
+
+def test_reference_arm_other_ranks_are_silent():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                       capture_output=True, text=True, timeout=120, cwd=ROOT, env=env)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+@pytest.mark.gpu
+def test_product_arm_line():
+    d = _run(["--steps", "3", "--warmup", "3", "--no-extras"], 600)
+    assert BASE_KEYS <= set(d) and "impl" not in d
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] == 3 and d["scaling"] == "weak"
+    assert d["gpu_launches"] == 3                                   # one launch per step
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["algorithmic_bytes_per_launch"] == 300 * 6220800       # 3*w*h per frame
+    assert r["achieved"] > 0.7 * r["peak"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 300 * 1920 * 1620 and e["d2h_bytes_per_step"] == 300 * 3110400
+    assert 0 < e["value"] < d["value"]
+    c = d["clocks"]
+    assert c["sm_max_mhz"] and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
+    assert d["verified_bit_exact"] is True

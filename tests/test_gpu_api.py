@@ -385,3 +385,36 @@ def test_handles_on_two_devices_interleaved(J):
     for d in decs:
         d.deinit()
     enc.deinit()
+
+
+def test_full_size_rgb_batch_samples(ctx):
+    """64 x 4K through the display ops in one launch each: sampled frames against the oracle, and the
+    fused op's RGB identical to the RGB-only op's for every frame (size-independent cross-check)."""
+    w, h, pitch, n = 3840, 2160, 4096, 64
+    surf_bytes, tight_bytes, rgb_bytes = pitch * h * 3 // 2, w * h * 3 // 2, 3 * w * h
+    base = [synth.nv12_surface(w, h, pitch, 16, f) for f in range(4)]
+    dsurf = ctx.alloc(n * surf_bytes)
+    for f in range(n):
+        ctx.h2d(dsurf + f * surf_bytes, base[f % 4])
+    drgb1, drgb2, dt = ctx.alloc(n * rgb_bytes), ctx.alloc(n * rgb_bytes), ctx.alloc(n * tight_bytes)
+    j = ctx.job_rgb(w, h, pitch, 3 * w, False)
+    j.n_frames, j.surf.base, j.surf.stride, j.rgb.base, j.rgb.stride = n, dsurf, surf_bytes, drgb1, rgb_bytes
+    ctx.convert(j)
+    k = ctx.job_rgb(w, h, pitch, 3 * w, True)
+    k.n_frames, k.surf.base, k.surf.stride, k.rgb.base, k.rgb.stride = n, dsurf, surf_bytes, drgb2, rgb_bytes
+    k.tight.base, k.tight.stride = dt, tight_bytes
+    ctx.convert(k)
+    a, b = np.empty(rgb_bytes, np.uint8), np.empty(rgb_bytes, np.uint8)
+    want = np.empty(rgb_bytes, np.uint8)
+    tight, twant = np.empty(tight_bytes, np.uint8), np.empty(tight_bytes, np.uint8)
+    for f in (0, 1, 2, 3, 31, 63):
+        ctx.d2h(a, drgb1 + f * rgb_bytes)
+        ctx.d2h(b, drgb2 + f * rgb_bytes)
+        assert np.array_equal(a, b)
+        oracle.nv12_to_rgb24(base[f % 4], pitch, w, h, want, 3 * w)
+        assert np.array_equal(a, want)
+        ctx.d2h(tight, dt + f * tight_bytes)
+        oracle.best().nvdec_output_frame(base[f % 4], pitch, w, h, 1, twant, tight_bytes)
+        assert np.array_equal(tight, twant)
+    for d in (dsurf, drgb1, drgb2, dt):
+        ctx.free(d)
