@@ -139,3 +139,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")) or f == "Makefile":
                 txt = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in txt and "jm_oracle" not in txt and "libjmref" not in txt, f
+
+
+def test_headers_are_valid_c99_and_cxx(tmp_path):
+    """The boundary is a C ABI: every public header must compile as strict C99 and as C++, and the C
+    example must link against the library."""
+    src = tmp_path / "inc.c"
+    src.write_text('#include "jm_nv_dec.h"\n#include "jmnv_enc.h"\n#include "jmc_cuda.h"\n#include "jmc_annexb.h"\n'
+                   "int main(void) { jmc_job j; nv_enc_param p; jm_nvdec_raw_packet k; (void)j; (void)p; (void)k; return 0; }\n")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", INC, "-fsyntax-only", str(src)], check=True)
+    subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-I", INC, "-x", "c++", "-fsyntax-only", str(src)], check=True)
+    exe = tmp_path / "decode_raw"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", INC, os.path.join(ROOT, "examples", "decode_raw.c"),
+                    "-L", os.path.dirname(J.lib_path()), "-ljmcodec_b200", "-Wl,-rpath," + os.path.dirname(J.lib_path()), "-o", str(exe)], check=True)
+    p = subprocess.run([str(exe)], capture_output=True, text=True)
+    if _no_gpu():
+        assert p.returncode == 1 and "no CUDA device" in p.stderr       # fails loudly, no CPU fallback
+    else:
+        assert p.returncode == 0 and "decoded 8 of 8 frames, exit=1" in p.stdout
