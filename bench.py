@@ -415,6 +415,32 @@ def main():
         want = np.empty(out_b, np.uint8)
         oracle.best().nvdec_output_frame(distinct[(n - 1) % N_DISTINCT], pitch, w, h, 1 if op == "i420" else 0, want, out_b)
         verified = verified and bool(np.array_equal(hout.array[(n - 1) * out_b:n * out_b], want))
+    # ---- the reference's real data flow: surfaces already in HBM (NVDEC wrote them), only the tight
+    #      frames travel: convert + D2H, no H2D (reported beside e2e, never instead of it) ----------------
+    decode_path = None
+    if op in ("i420", "nv12", "rgb", "fused"):
+        def resident_step():
+            for b in range(n // sub):
+                pipe.submit(None, hout.array[b * sub * out_b:], sub, dev_in=d_in + b * sub * in_b,
+                            host_out2=hout2.array[b * sub * out2_b:] if hout2 else None)
+        for _ in range(args.warmup):
+            resident_step()
+        pipe.drain()
+        barrier()
+        d1 = pipe.d2h_bytes
+        sampler.region(True)
+        ev0.record(0)
+        for _ in range(args.steps):
+            resident_step()
+        ev1.record(2)
+        dp_ms = ev0.elapsed_ms(ev1)
+        pipe.drain()
+        sampler.region(False)
+        barrier()
+        dp_units, dp_ms_max = aggregate(n * args.steps, dp_ms, dev)
+        decode_path = {"value": dp_units / (dp_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 0,
+                       "d2h_bytes_per_step": int((pipe.d2h_bytes - d1) // args.steps), "ms_per_step": dp_ms_max / args.steps,
+                       "note": "surfaces resident in HBM as after NVDEC; kernel + pinned D2H of the tight frames only"}
     sampler.stop()
     pipe.close()
 
@@ -464,6 +490,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
                     "ms_per_step": e2e_ms_max / args.steps, "frames_per_pipeline_batch": sub, "pipeline_depth": args.e2e_depth,
                     "pcie_gbs_each_way": [h2d_step / (e2e_ms_max / args.steps * 1e-3) / 1e9, d2h_step / (e2e_ms_max / args.steps * 1e-3) / 1e9]},
+            "e2e_device_resident_input": decode_path,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "verified_bit_exact": verified,
