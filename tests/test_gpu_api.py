@@ -418,3 +418,61 @@ def test_full_size_rgb_batch_samples(ctx):
         assert np.array_equal(tight, twant)
     for d in (dsurf, drgb1, drgb2, dt):
         ctx.free(d)
+
+
+def test_pipeline_argument_errors_and_depth_one(J, ctx):
+    w, h, pitch, batch = 64, 32, 64, 4
+    surf_bytes, tight_bytes = pitch * h * 3 // 2, w * h * 3 // 2
+    shape = ctx.job_nvdec(w, h, pitch, 1)
+    shape.n_frames = batch
+    with pytest.raises(J.JmcError):
+        J.Pipeline(ctx, shape, 0, depth=2)                  # surf_bytes == 0
+    with pytest.raises(J.JmcError):
+        J.Pipeline(ctx, shape, surf_bytes, depth=0)
+    pipe = J.Pipeline(ctx, shape, surf_bytes, depth=1)      # a single slot: every submit waits for the previous one
+    hin, hout = ctx.alloc_host(batch * surf_bytes), ctx.alloc_host(batch * tight_bytes)
+    with pytest.raises(J.JmcError):
+        pipe.submit(hin.array, hout.array, batch + 1)       # more frames than the slot holds
+    with pytest.raises(J.JmcError):
+        pipe.submit(None, hout.array, batch)                # neither host nor device input
+    with pytest.raises(J.JmcError):
+        pipe.wait(5)
+    chk = oracle.best()
+    want = np.empty(tight_bytes, np.uint8)
+    for rep in range(5):
+        frames = [synth.nv12_surface(w, h, pitch, 70 + rep, f) for f in range(batch)]
+        hin.array[:] = np.concatenate(frames)
+        slot = pipe.submit(hin.array, hout.array, batch)
+        assert slot == 0
+        pipe.wait(slot)
+        for f in range(batch):
+            chk.nvdec_output_frame(frames[f], pitch, w, h, 1, want, tight_bytes)
+            assert np.array_equal(hout.array[f * tight_bytes:(f + 1) * tight_bytes], want)
+    pipe.close()
+    hin.free(), hout.free()
+
+
+def test_raw_packet_fuzz_never_crashes(J):
+    """Malformed packets are dropped (got_frame 0), never crash, and do not wedge the handle."""
+    rng = np.random.default_rng(9)
+    dec = J.NvDec(0)
+    assert dec.init(J.NvDec.CODEC_RAW_NV12, 1) == 0
+    w, h, pitch = 32, 16, 32
+    good = J.NvDec.raw_packet(synth.nv12_surface(w, h, pitch, 80, 0), w, h, pitch)
+    for i in range(200):
+        bad = good.copy()
+        k = int(rng.integers(0, 4))
+        if k == 0:
+            bad = bad[:int(rng.integers(0, bad.size))]                         # truncated
+        elif k == 1:
+            bad[int(rng.integers(0, 32))] ^= int(rng.integers(1, 256))         # corrupted header byte
+        elif k == 2:
+            bad = rng.integers(0, 256, size=int(rng.integers(1, 200)), dtype=np.uint8)
+        else:
+            bad[4:16] = np.array([-5, 7, 3], dtype="<i4").view(np.uint8)       # negative width, pitch < width
+        r, got = dec.decode_frame(np.ascontiguousarray(bad))
+        assert r == 0 and got in (0, 1)
+    out = np.empty(w * h * 3 // 2, np.uint8)
+    assert dec.decode_frame(good) == (0, 1)
+    assert dec.output_frame(out, out.size) == (out.size, out.size)
+    dec.deinit()
