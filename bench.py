@@ -469,8 +469,17 @@ def main():
         if op == "i420":
             f1, kind = cpu_reference_fps(w, h, pitch, 1500, 1, distinct)
             fN, _ = cpu_reference_fps(w, h, pitch, 300 * max(1, min(threads, 64)), threads, distinct)
+            import oracle
+            S = np.stack(distinct)
+            o3out = np.zeros((max(N_DISTINCT, threads), w * h * 3 // 2), np.uint8)
+            nfr = 300 * max(1, min(threads, 64))
+            oracle.ref_best_effort_run(S, o3out, pitch, w, h, 1, 64, threads)
+            t3 = oracle.ref_best_effort_run(S, o3out, pitch, w, h, 1, nfr, threads)
+            t31 = oracle.ref_best_effort_run(S, o3out, pitch, w, h, 1, 1500, 1)
             cpu = {"value": fN, "unit": "frames/s", "cores": threads, "kind": kind,
                    "value_1thread": f1,
+                   "best_effort_o3_avx2": None if not t3 else {"value": nfr / t3, "value_1thread": 1500 / t31 if t31 else None,
+                                                                "note": "same unmodified nv_dec.cpp, gcc -O3 -mavx2 instead of the reference's -O2/MaxSpeed"},
                    "sample": f"jm_nvdec_output_frame out_fmt=1 on {w}x{h} pitch {pitch}: 1500 frames on 1 thread, "
                              f"{300 * max(1, min(threads, 64))} frames on {threads} threads (one handle per thread), "
                              f"{N_DISTINCT} distinct surfaces"}

@@ -21,6 +21,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(_HERE, "libjmoracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libjmref.so")
+REF_O3_SO = os.path.join(_HERE, "_ref", "libjmref_o3avx2.so")      # same sources, gcc -O3 -mavx2 ("best-effort CPU")
 
 _u8p = C.POINTER(C.c_uint8)
 _ip = C.POINTER(C.c_int)
@@ -151,6 +152,24 @@ def ref() -> Checker:
     if _ref is None:
         _ref = Checker(_Ref())
     return _ref
+
+
+def ref_best_effort_run(surfs, out, pitch, w, h, out_fmt, frames, nthreads):
+    """Timed loop of the reference function built with -O3 -mavx2 (BASELINE.md 3 "best-effort CPU").
+    Returns seconds, or None if that build is absent or the CPU lacks AVX2."""
+    if not os.path.exists(REF_O3_SO):
+        return None
+    try:
+        if "avx2" not in open("/proc/cpuinfo").read():
+            return None
+    except OSError:
+        return None
+    L = C.CDLL(REF_O3_SO)
+    L.jmref_nvdec_run.argtypes = [_u8p, C.c_size_t, C.c_int, _u8p, C.c_size_t, C.c_int] + [C.c_int] * 6
+    L.jmref_nvdec_run.restype = C.c_double
+    t = L.jmref_nvdec_run(_ptr(surfs), surfs.shape[1], surfs.shape[0], _ptr(out), out.shape[1], out.shape[0],
+                          pitch, w, h, out_fmt, frames, nthreads)
+    return t if t > 0 else None
 
 
 def best() -> Checker:
