@@ -91,17 +91,24 @@ def aggregate(units: int, ms: float, device):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled via NVML while the timed regions run."""
+    """SM clock / throttle reasons sampled while the timed regions run: NVML in a thread (2 ms period),
+    or, if NVML is unusable, the nvidia-smi loop of B200_PROFILING.md (200 ms period, whole run)."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz, self._run, self._on = [], set(), None, False, False
+        self.index, self.proc, self.source = index, None, "nvml"
         try:
+            if os.environ.get("JMC_BENCH_NO_NVML"):
+                raise RuntimeError("NVML disabled by JMC_BENCH_NO_NVML")
             import pynvml as nv
             nv.nvmlInit()
             self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
         except Exception:
-            self.nv = None
+            self.nv, self.source = None, "nvidia-smi"
 
     def _loop(self):
         nv = self.nv
@@ -127,6 +134,14 @@ class ClockSampler:
             self._run = True
             self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
+        else:
+            import subprocess
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                              "--format=csv,noheader,nounits", "-lms", "200"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            except Exception:
+                self.proc = None
 
     def region(self, on):
         self._on = on
@@ -135,12 +150,31 @@ class ClockSampler:
         if self.nv and self._run:
             self._run = False
             self.t.join()
+        elif self.proc:
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                out = ""
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for ln in out.splitlines():
+                f = [x.strip() for x in ln.split(",")]
+                try:
+                    self.samples.append(int(f[0]))
+                    self.max_mhz = int(f[1])
+                    for nme, v in zip(names, f[2:6]):
+                        if v.lower().startswith("active"):
+                            self.reasons.add(nme)
+                except (ValueError, IndexError):
+                    continue
+            busy = [x for x in self.samples if self.max_mhz and x > 0.5 * self.max_mhz]
+            self.samples = busy or self.samples
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0, "source": self.source}
         return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
-                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+                "reasons": sorted(self.reasons), "samples": len(self.samples), "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------
