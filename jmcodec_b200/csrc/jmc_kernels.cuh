@@ -582,6 +582,45 @@ struct RgbCfg {                           /* tools/sweep.cu: 128 x 8 CTAs/SM, on
     static constexpr int STP = 0;
 };
 
+/* store the first nbytes (<= 4*NW) of a register chunk at dst, as wide as dst's alignment allows */
+template <int NW> __device__ __forceinline__ void store_prefix(uint8_t *dst, const uint32_t (&wd)[NW], uint32_t nbytes)
+{
+    const uint32_t a = (uint32_t)(uintptr_t)dst;
+    if (NW == 4 && nbytes == 16 && (a & 7) == 0) {
+        if ((a & 15) == 0) *(uint4 *)dst = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        else { *(uint2 *)dst = make_uint2(wd[0], wd[1]); *(uint2 *)(dst + 8) = make_uint2(wd[2], wd[3]); }
+        return;
+    }
+    if (NW == 2 && nbytes == 8 && (a & 3) == 0) {
+        if ((a & 7) == 0) *(uint2 *)dst = make_uint2(wd[0], wd[1]);
+        else { *(uint32_t *)dst = wd[0]; *(uint32_t *)(dst + 4) = wd[1]; }
+        return;
+    }
+    const uint32_t nfull = (a & 3) == 0 ? (nbytes >> 2) : 0;              /* leading bytes that can go out as words */
+#pragma unroll
+    for (int i = 0; i < NW; i++)
+        if ((uint32_t)i < nfull) *(uint32_t *)(dst + 4 * i) = wd[i];
+#pragma unroll
+    for (int i = 0; i < 4 * NW; i++)
+        if ((uint32_t)i >= 4 * nfull && (uint32_t)i < nbytes) dst[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
+}
+
+/* copy nbytes from warp-private shared memory to global, V bytes per lane per step */
+template <int V, int STP> __device__ __forceinline__ void warp_flush(uint8_t *g, const uint8_t *st, uint32_t nbytes, uint32_t lane)
+{
+#pragma unroll
+    for (int k = 0; k < 1536 / (32 * V); k++) {
+        const uint32_t c = (k * 32 + lane) * V;
+        if (c < nbytes) {
+            if (V == 16) st16<STP>(g + c, *(const uint4 *)(st + c));
+            else if (V == 8) st8<STP>(g + c, *(const uint2 *)(st + c));
+            else if (V == 4) *(uint32_t *)(g + c) = *(const uint32_t *)(st + c);
+            else if (V == 2) *(uint16_t *)(g + c) = *(const uint16_t *)(st + c);
+            else g[c] = st[c];
+        }
+    }
+}
+
 template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const __grid_constant__ RgbParams p)
 {
@@ -605,32 +644,31 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
         const uint8_t *crow = sp + p.uv_off + (size_t)cy * p.pitch;
         uint8_t *orow = rgbp + (size_t)y0 * p.rgb_pitch;
 
-        uint64_t bits = (uint64_t)(uintptr_t)(sp + p.y_off) | (uint64_t)(uintptr_t)(sp + p.uv_off) | (uint32_t)p.pitch |
-                        (uint64_t)(uintptr_t)rgbp | (uint32_t)p.rgb_pitch | (uint32_t)w;
-        bool fast = (bits & 15) == 0;
-        if (p.fused)
-            fast = fast && (((uint64_t)(uintptr_t)tp & 15) == 0) && (((uint64_t)(uintptr_t)(tp + p.u_off) | (uint64_t)(uintptr_t)(tp + p.v_off)) & 7) == 0;
+        /* vector path: 16-byte loads need an aligned surface whose rows can be over-read up to the next
+         * multiple of 16 (always true for decoder surfaces); the stores adapt to whatever alignment the
+         * tight / RGB rows have (1080-wide portrait video: 8-byte RGB rows, 4-byte chroma rows). */
+        const uint64_t sbits = (uint64_t)(uintptr_t)(sp + p.y_off) | (uint64_t)(uintptr_t)(sp + p.uv_off) | (uint32_t)p.pitch;
+        const bool vec = (sbits & 15) == 0 && (w & 1) == 0 && p.pitch >= ((w + 15) & ~15);
 
-        if (fast) {
-            const uint32_t units_row = (uint32_t)w >> 4;
-            const uint32_t unit = seg * 32 + lane;
-            const uint32_t nvalid = min(32u, units_row - seg * 32);      /* lanes with work in this warp */
-            const bool act = lane < nvalid;
+        if (vec) {
+            const uint32_t px0 = (seg * 32 + lane) * 16;
+            const uint32_t npx = px0 < (uint32_t)w ? min(16u, (uint32_t)w - px0) : 0u;     /* valid pixels of this lane (even) */
+            const uint32_t seg_px = min(512u, (uint32_t)w - seg * 512);                    /* valid pixels of this warp */
             uint4 ya = make_uint4(0, 0, 0, 0), yb = ya, uv = ya;
-            if (act) {
-                ya = ld16<C::LDP>(yrow + unit * 16);
-                uv = ld16<C::LDP>(crow + unit * 16);
-                if (two) yb = ld16<C::LDP>(yrow + p.pitch + unit * 16);
+            if (npx) {
+                ya = ld16<C::LDP>(yrow + px0);
+                uv = ld16<C::LDP>(crow + px0);
+                if (two) yb = ld16<C::LDP>(yrow + p.pitch + px0);
             }
-            if (p.fused && act) {
-                st16<C::STP>(tp + (size_t)y0 * w + unit * 16, ya);
-                if (two) st16<C::STP>(tp + (size_t)(y0 + 1) * w + unit * 16, yb);
+            if (p.fused && npx) {
+                const uint32_t y_a[4] = {ya.x, ya.y, ya.z, ya.w}, y_b[4] = {yb.x, yb.y, yb.z, yb.w};
+                store_prefix<4>(tp + (size_t)y0 * w + px0, y_a, npx);
+                if (two) store_prefix<4>(tp + (size_t)(y0 + 1) * w + px0, y_b, npx);
                 if (rp < (uint32_t)ch) {
-                    uint2 u, v;
-                    u.x = __byte_perm(uv.x, uv.y, 0x6420); v.x = __byte_perm(uv.x, uv.y, 0x7531);
-                    u.y = __byte_perm(uv.z, uv.w, 0x6420); v.y = __byte_perm(uv.z, uv.w, 0x7531);
-                    st8<C::STP>(tp + p.u_off + (size_t)rp * cw + unit * 8, u);
-                    st8<C::STP>(tp + p.v_off + (size_t)rp * cw + unit * 8, v);
+                    const uint32_t u[2] = {__byte_perm(uv.x, uv.y, 0x6420), __byte_perm(uv.z, uv.w, 0x6420)};
+                    const uint32_t v[2] = {__byte_perm(uv.x, uv.y, 0x7531), __byte_perm(uv.z, uv.w, 0x7531)};
+                    store_prefix<2>(tp + p.u_off + (size_t)rp * cw + (px0 >> 1), u, npx >> 1);
+                    store_prefix<2>(tp + p.v_off + (size_t)rp * cw + (px0 >> 1), v, npx >> 1);
                 }
             }
             /* chroma terms of the 8 pairs this thread owns */
@@ -659,14 +697,17 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
                 s4[2] = make_uint4(o[8], o[9], o[10], o[11]);
                 __syncwarp();
                 uint8_t *g = orow + (size_t)row * p.rgb_pitch + (size_t)seg * (32 * 48);
-#pragma unroll
-                for (int k = 0; k < 3; k++) {
-                    const uint32_t c = k * 32 + lane;                 /* 16-byte chunk of the warp's 1536-byte span */
-                    if (c < nvalid * 3) st16<C::STP>(g + c * 16, *(const uint4 *)(st + c * 16));
+                const uint32_t nbytes = 3 * seg_px;                               /* a multiple of 6 */
+                switch (vec_width((uint64_t)(uintptr_t)g | nbytes)) {
+                case 16: warp_flush<16, C::STP>(g, st, nbytes, lane); break;
+                case 8:  warp_flush<8, C::STP>(g, st, nbytes, lane); break;
+                case 4:  warp_flush<4, C::STP>(g, st, nbytes, lane); break;
+                case 2:  warp_flush<2, C::STP>(g, st, nbytes, lane); break;
+                default: warp_flush<1, C::STP>(g, st, nbytes, lane); break;
                 }
             }
         } else {
-            /* any geometry: one pixel per lane per step, byte accesses */
+            /* odd widths, unaligned or too-tight surfaces: one pixel per lane per step, byte accesses */
             const uint32_t x_begin = seg * 512, x_end = min((uint32_t)w, x_begin + 512);
             for (uint32_t x = x_begin + lane; x < x_end; x += 32) {
                 const uint32_t cx = min(x >> 1, (uint32_t)(cw - 1));

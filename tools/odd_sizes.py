@@ -1,0 +1,17 @@
+"""Device-resident rate of the any-alignment kernels on sizes that are not multiples of 16/32 (developer tool)."""
+import json, sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench, jmcodec_b200 as J
+ctx = J.Ctx(0)
+peak, _ = bench.peaks()
+for name, spec in {
+    "1080x1920 portrait p1088": ("i420", 1080, 1920, 1088, 150), "1080x1920 portrait p1280": ("i420", 1080, 1920, 1280, 150),
+    "1366x768 p1536": ("i420", 1366, 768, 1536, 300), "854x480 p1024": ("i420", 854, 480, 1024, 600),
+    "1918x1078 p2048": ("i420", 1918, 1078, 2048, 300), "1919x1079 p2048": ("i420", 1919, 1079, 2048, 300),
+    "720x480 p768": ("i420", 720, 480, 768, 800), "1280x720 p1280": ("i420", 1280, 720, 1280, 600),
+    "pack 1080x1920 p1088": ("pack", 1080, 1920, 1088, 150), "rgb 1080x1920 p1088": ("rgb", 1080, 1920, 1088, 150),
+    "rgb 1366x768 p1536": ("rgb", 1366, 768, 1536, 300),
+}.items():
+    bench.WORKLOADS["_x"] = spec
+    r = bench.device_only(ctx, "_x", 0, 10, 3)
+    print(f"{name:28s} {r['frames_per_s']:12.0f} fps {r['gbs']:8.1f} GB/s  {r['gbs']/peak:.3f} of peak")
