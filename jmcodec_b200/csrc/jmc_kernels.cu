@@ -96,6 +96,70 @@ static int launch_bulk(jmc_ctx *ctx, const PlaneParams &pp, int k1, cudaStream_t
     return JMC_OK;
 }
 
+/* Would the any-alignment kernel be reduced to <= 4-byte luma or <= 2-byte chroma accesses on this job?
+ * (Then the row-staged kernel wins: measured 0.41-0.59 -> 0.69-0.87 of peak on 1366/854/1918/1919-wide
+ * frames; with 8-byte luma / 4-byte chroma vectors - 1080-wide portrait, 720x480 - the plain kernel is
+ * faster, 0.96 vs 0.67-0.74.)  Pointer lists are taken as 16-byte aligned only with JMC_JOB_ALIGNED16. */
+static bool narrow_vectors(const jmc_job *j, const PlaneParams &p)
+{
+    uint64_t common = 0;
+    const jmc_frames *sets[2] = { &j->surf, &j->tight };
+    for (int i = 0; i < 2; i++) {
+        if (sets[i]->list) { if (!(j->flags & JMC_JOB_ALIGNED16)) return false; }     /* unknown: keep the per-frame in-kernel choice */
+        else common |= (uint64_t)(uintptr_t)sets[i]->base | (uint64_t)sets[i]->stride;
+    }
+    auto width = [](uint64_t bits) { const uint32_t low = (uint32_t)bits & 15u; return low == 0 ? 16u : (low & (0u - low)); };
+    const Part &y = p.part[0], &c = p.part[1];
+    const uint32_t vy = y.kind == PART_NONE ? 16u : width(common | (uint64_t)y.p_off | (uint32_t)y.p_pitch | (uint64_t)y.a_off | y.row_elems);
+    uint32_t vc = 16u;
+    if (c.kind == PART_COPY) vc = width(common | (uint64_t)c.p_off | (uint32_t)c.p_pitch | (uint64_t)c.a_off | c.row_elems) / 2;
+    else if (c.kind != PART_NONE) vc = width(common | (uint64_t)c.p_off | (uint32_t)c.p_pitch | (uint64_t)c.a_off | (uint64_t)c.b_off | c.row_elems);
+    return vy <= 4 || vc <= 2;
+}
+
+/* Row-staged kernel for widths that are not multiples of 16: needs only the SURFACE side aligned
+ * (base, pitch, plane offsets multiples of 16; rows over-readable up to the next multiple of 16).
+ * Returns 1 when that does not hold. */
+static int launch_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, int k1, cudaStream_t stream)
+{
+    if (j->surf.list) { if (!(j->flags & JMC_JOB_ALIGNED16)) return 1; }
+    else if (((uint64_t)(uintptr_t)j->surf.base | (uint64_t)j->surf.stride) & 15) return 1;
+    RowsParams r;
+    r.pitched = pp.pitched;
+    r.tight = pp.tight;
+    r.n_frames = pp.n_frames;
+    uint64_t per_frame = 0;
+    for (int i = 0; i < 2; i++) {
+        const Part &pt = pp.part[i];
+        r.part[i] = pt;
+        r.segs[i] = r.tasks[i] = 0;
+        if (pt.kind == PART_NONE) continue;
+        const uint32_t row_bytes = pt.kind == PART_COPY ? pt.row_elems : 2 * pt.row_elems;      /* surface bytes per row */
+        if (((uint64_t)pt.p_off | (uint32_t)pt.p_pitch) & 15) return 1;
+        if ((uint32_t)pt.p_pitch < ((row_bytes + 15) & ~15u)) return 1;
+        r.segs[i] = (row_bytes + ROWS_SEG - 1) / ROWS_SEG;
+        const uint64_t t = (uint64_t)pt.rows * r.segs[i];
+        if (t > 0x3fffffffull) return 1;
+        r.tasks[i] = (uint32_t)t;
+        per_frame += t;
+    }
+    const uint64_t total = per_frame * r.n_frames;
+    if (total == 0) return JMC_OK;
+    if (total > 0x7fffffffull) return 1;
+    r.total_tasks = (uint32_t)total;
+    const uint32_t grid = (r.total_tasks + ROWS_THREADS / 32 - 1) / (ROWS_THREADS / 32);
+    if (pp.to_tight) {
+        if (k1 == PART_SPLIT) rows_kernel<true, PART_SPLIT><<<grid, ROWS_THREADS, 0, stream>>>(r);
+        else rows_kernel<true, PART_COPY><<<grid, ROWS_THREADS, 0, stream>>>(r);
+    } else {
+        if (k1 == PART_MERGE) rows_kernel<false, PART_MERGE><<<grid, ROWS_THREADS, 0, stream>>>(r);
+        else rows_kernel<false, PART_COPY><<<grid, ROWS_THREADS, 0, stream>>>(r);
+    }
+    JMC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return JMC_OK;
+}
+
 /* Can the host prove that every access of this job is 16-byte aligned?  (1080p, 4K, 720p ... are.) */
 static bool all_wide(const jmc_job *j, const PlaneParams &p)
 {
@@ -144,6 +208,10 @@ static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     if (wide && !getenv_flag("JMC_NO_BULK")) {
         int r = launch_bulk(ctx, p, k1, stream);
         if (r != 1) return r;                        /* 1: geometry does not fit the bulk kernel, use LDG/STG */
+    }
+    if (!wide && !getenv_flag("JMC_NO_ROWS") && narrow_vectors(j, p)) {
+        int r = launch_rows(ctx, j, p, k1, stream);
+        if (r != 1) return r;                        /* 1: surface side not 16-byte friendly, use the any-alignment kernel */
     }
 #define JMC_LAUNCH(TT, K1)                                                                               \
     do {                                                                                                 \

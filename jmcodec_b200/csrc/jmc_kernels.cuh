@@ -512,6 +512,211 @@ __global__ void __launch_bounds__(BULK_THREADS) bulk_planes_kernel(const __grid_
     }
 }
 
+/* store the first nbytes (<= 4*NW) of a register chunk at dst, as wide as dst's alignment allows */
+template <int NW> __device__ __forceinline__ void store_prefix(uint8_t *dst, const uint32_t (&wd)[NW], uint32_t nbytes)
+{
+    const uint32_t a = (uint32_t)(uintptr_t)dst;
+    if (NW == 4 && nbytes == 16 && (a & 7) == 0) {
+        if ((a & 15) == 0) *(uint4 *)dst = make_uint4(wd[0], wd[1], wd[2], wd[3]);
+        else { *(uint2 *)dst = make_uint2(wd[0], wd[1]); *(uint2 *)(dst + 8) = make_uint2(wd[2], wd[3]); }
+        return;
+    }
+    if (NW == 2 && nbytes == 8 && (a & 3) == 0) {
+        if ((a & 7) == 0) *(uint2 *)dst = make_uint2(wd[0], wd[1]);
+        else { *(uint32_t *)dst = wd[0]; *(uint32_t *)(dst + 4) = wd[1]; }
+        return;
+    }
+    const uint32_t nfull = (a & 3) == 0 ? (nbytes >> 2) : 0;              /* leading bytes that can go out as words */
+#pragma unroll
+    for (int i = 0; i < NW; i++)
+        if ((uint32_t)i < nfull) *(uint32_t *)(dst + 4 * i) = wd[i];
+#pragma unroll
+    for (int i = 0; i < 4 * NW; i++)
+        if ((uint32_t)i >= 4 * nfull && (uint32_t)i < nbytes) dst[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
+}
+
+/* ========================================================================================== */
+/* Row-staged plane kernel: full-width accesses for sizes that are NOT multiples of 16           */
+/* ========================================================================================== */
+/* Decoder/encoder surfaces are always 16-byte aligned with a 16-byte-multiple pitch, whatever the
+ * picture width; only the tight side (rows of w or w/2 bytes back to back) lands on odd addresses
+ * when w is not a multiple of 16/32 (1366, 854, 1080-wide portrait chroma, odd sizes).  One warp per
+ * (row, 2 KB segment): 16-byte loads/stores on the surface side, a pass through warp-private shared
+ * memory, and on the tight side 16-byte accesses to the ALIGNED body of the segment, re-aligned by a
+ * funnel shift (classic unaligned memcpy), with byte accesses only for the <16-byte head and tail. */
+constexpr int ROWS_THREADS = 128;
+constexpr int ROWS_SEG = 2048;                       /* surface bytes per warp task */
+constexpr int ROWS_SMEM_A = ROWS_SEG + 32, ROWS_SMEM_B = ROWS_SEG / 2 + 32;
+
+struct RowsParams {
+    FrameSet pitched, tight;
+    uint32_t n_frames;
+    uint32_t tasks[2];        /* warp tasks per frame of part 0 / part 1 (rows * segments) */
+    uint32_t segs[2];         /* segments per row */
+    uint32_t total_tasks;
+    Part part[2];
+};
+
+/* smem[0..nbytes) -> dst (any alignment) */
+__device__ __forceinline__ void warp_store_shifted(uint8_t *dst, const uint8_t *sm, uint32_t nbytes, uint32_t lane)
+{
+    const uint32_t head = min(nbytes, (16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u);
+    const uint32_t body = (nbytes - head) & ~15u;
+    if (lane < head) dst[lane] = sm[lane];
+    const uint32_t sh = 8 * (head & 3);
+    const uint32_t *w32 = (const uint32_t *)sm + (head >> 2);
+    for (uint32_t j = lane; j < body / 16; j += 32) {
+        const uint32_t *q = w32 + 4 * j;
+        const uint32_t a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
+        uint4 o;
+        o.x = __funnelshift_r(a, b, sh); o.y = __funnelshift_r(b, c, sh);
+        o.z = __funnelshift_r(c, d, sh); o.w = __funnelshift_r(d, e, sh);
+        *(uint4 *)(dst + head + 16 * (size_t)j) = o;
+    }
+    const uint32_t t0 = head + body;
+    if (lane < nbytes - t0) dst[t0 + lane] = sm[t0 + lane];
+}
+
+/* src (any alignment) -> smem[0..nbytes); never reads outside [src, src + nbytes) */
+__device__ __forceinline__ void warp_load_shifted(uint8_t *sm, const uint8_t *src, uint32_t nbytes, uint32_t lane)
+{
+    const uint32_t s = (uint32_t)(uintptr_t)src & 15u;
+    const uint32_t nchunks = nbytes / 16;                       /* full 16-byte chunks of smem */
+    if (s == 0) {
+        for (uint32_t j = lane; j < nchunks; j += 32) *(uint4 *)(sm + 16 * j) = __ldg((const uint4 *)(src + 16 * (size_t)j));
+    } else {
+        /* smem chunk j = src[16j, 16j+16) = bytes s.. of the aligned pair (A, A+16), A = src - s + 16j.
+         * j = 0 would read s bytes before src, the last chunk 16-s bytes after the end: those two go bytewise. */
+        const uint8_t *al = src - s;
+        const uint32_t sh = 8 * (s & 3), ws = s >> 2;
+        for (uint32_t j = lane; j < nchunks; j += 32) {
+            if (j == 0 || 16 * j + 32 > nbytes + s) continue;    /* handled below */
+            const uint4 A = __ldg((const uint4 *)(al + 16 * (size_t)j)), B = __ldg((const uint4 *)(al + 16 * (size_t)j + 16));
+            const uint32_t v[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+            uint32_t x0, x1, x2, x3, x4;
+            switch (ws) {                                        /* warp-uniform */
+            case 0: x0 = v[0]; x1 = v[1]; x2 = v[2]; x3 = v[3]; x4 = v[4]; break;
+            case 1: x0 = v[1]; x1 = v[2]; x2 = v[3]; x3 = v[4]; x4 = v[5]; break;
+            case 2: x0 = v[2]; x1 = v[3]; x2 = v[4]; x3 = v[5]; x4 = v[6]; break;
+            default: x0 = v[3]; x1 = v[4]; x2 = v[5]; x3 = v[6]; x4 = v[7]; break;
+            }
+            uint4 o;
+            o.x = __funnelshift_r(x0, x1, sh); o.y = __funnelshift_r(x1, x2, sh);
+            o.z = __funnelshift_r(x2, x3, sh); o.w = __funnelshift_r(x3, x4, sh);
+            *(uint4 *)(sm + 16 * j) = o;
+        }
+        /* first chunk and the (at most two) last chunks whose aligned pair would cross the end */
+        if (lane < 16 && nchunks > 0) sm[lane] = src[lane];
+        const uint32_t jf = nbytes + s >= 32 ? (nbytes + s - 32) / 16 + 1 : 1;
+        for (uint32_t j = max(jf, 1u); j < nchunks; j++)
+            if (lane < 16) sm[16 * j + lane] = src[16 * (size_t)j + lane];
+    }
+    const uint32_t t0 = nchunks * 16;
+    if (lane < nbytes - t0) sm[t0 + lane] = src[t0 + lane];
+}
+
+template <bool TO_TIGHT, int KIND1>
+__global__ void __launch_bounds__(ROWS_THREADS, 8) rows_kernel(const __grid_constant__ RowsParams p)
+{
+    constexpr int WARPS = ROWS_THREADS / 32;
+    __shared__ __align__(16) uint8_t sA[WARPS][ROWS_SMEM_A];
+    __shared__ __align__(16) uint8_t sB[WARPS][ROWS_SMEM_B];
+    __shared__ __align__(16) uint8_t sC[WARPS][ROWS_SMEM_B];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t task = blockIdx.x * WARPS + wib;
+    if (task >= p.total_tasks) return;
+    const uint32_t tpf = p.tasks[0] + p.tasks[1];
+    const uint32_t f = task / tpf;
+    uint32_t r = task - f * tpf;
+    const bool second = r >= p.tasks[0];
+    if (second) r -= p.tasks[0];
+    const Part &pt = second ? p.part[1] : p.part[0];
+    const uint32_t segs = second ? p.segs[1] : p.segs[0];
+    const uint32_t row = r / segs, seg = r - row * segs;
+    uint8_t *A = sA[wib], *B = sB[wib], *Cc = sC[wib];
+    uint8_t *prow = frame_ptr(p.pitched, f) + pt.p_off + (size_t)row * (uint32_t)pt.p_pitch + (size_t)seg * ROWS_SEG;
+    uint8_t *tp = frame_ptr(p.tight, f);
+
+    if (!second || KIND1 == PART_COPY) {
+        const uint32_t nbytes = min((uint32_t)ROWS_SEG, pt.row_elems - seg * ROWS_SEG);
+        uint8_t *trow = tp + pt.a_off + (size_t)row * pt.row_elems + (size_t)seg * ROWS_SEG;
+        if (TO_TIGHT) {
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const uint32_t c = (k * 32 + lane) * 16; if (c < nbytes) v[k] = ld16<1>(prow + c); }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const uint32_t c = (k * 32 + lane) * 16; if (c < nbytes) *(uint4 *)(A + c) = v[k]; }
+            __syncwarp();
+            warp_store_shifted(trow, A, nbytes, lane);
+        } else {
+            warp_load_shifted(A, trow, nbytes, lane);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t c = (k * 32 + lane) * 16;
+                if (c + 16 <= nbytes) *(uint4 *)(prow + c) = *(const uint4 *)(A + c);
+                else if (c < nbytes) { const uint4 t = *(const uint4 *)(A + c); const uint32_t wd[4] = {t.x, t.y, t.z, t.w}; store_prefix<4>(prow + c, wd, nbytes - c); }
+            }
+        }
+    } else {
+        /* chroma: elements are pairs; a segment is ROWS_SEG interleaved bytes = ROWS_SEG/2 pairs */
+        const uint32_t npairs = min((uint32_t)ROWS_SEG / 2, pt.row_elems - seg * (ROWS_SEG / 2));
+        uint8_t *tu = tp + pt.a_off + (size_t)row * pt.row_elems + (size_t)seg * (ROWS_SEG / 2);
+        uint8_t *tv = tp + pt.b_off + (size_t)row * pt.row_elems + (size_t)seg * (ROWS_SEG / 2);
+        if (KIND1 == PART_SPLIT) {
+            uint4 v[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const uint32_t c = (k * 32 + lane) * 16; if (c < 2 * npairs) v[k] = ld16<1>(prow + c); }
+#pragma unroll
+            for (int k = 0; k < 4; k++) { const uint32_t c = (k * 32 + lane) * 16; if (c < 2 * npairs) *(uint4 *)(A + c) = v[k]; }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const uint32_t c = k * 32 + lane;                          /* 32-byte chunk -> 16 U + 16 V */
+                if (32 * c < 2 * npairs) {
+                    const uint4 a = *(const uint4 *)(A + 32 * c), b = *(const uint4 *)(A + 32 * c + 16);
+                    uint4 u, w;
+                    u.x = __byte_perm(a.x, a.y, 0x6420); w.x = __byte_perm(a.x, a.y, 0x7531);
+                    u.y = __byte_perm(a.z, a.w, 0x6420); w.y = __byte_perm(a.z, a.w, 0x7531);
+                    u.z = __byte_perm(b.x, b.y, 0x6420); w.z = __byte_perm(b.x, b.y, 0x7531);
+                    u.w = __byte_perm(b.z, b.w, 0x6420); w.w = __byte_perm(b.z, b.w, 0x7531);
+                    *(uint4 *)(B + 16 * c) = u;
+                    *(uint4 *)(Cc + 16 * c) = w;
+                }
+            }
+            __syncwarp();
+            warp_store_shifted(tu, B, npairs, lane);
+            warp_store_shifted(tv, Cc, npairs, lane);
+        } else {
+            warp_load_shifted(B, tu, npairs, lane);
+            warp_load_shifted(Cc, tv, npairs, lane);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                const uint32_t c = k * 32 + lane;
+                if (16 * c < npairs) {
+                    const uint4 u = *(const uint4 *)(B + 16 * c), w = *(const uint4 *)(Cc + 16 * c);
+                    uint4 a, b;
+                    a.x = __byte_perm(u.x, w.x, 0x5140); a.y = __byte_perm(u.x, w.x, 0x7362);
+                    a.z = __byte_perm(u.y, w.y, 0x5140); a.w = __byte_perm(u.y, w.y, 0x7362);
+                    b.x = __byte_perm(u.z, w.z, 0x5140); b.y = __byte_perm(u.z, w.z, 0x7362);
+                    b.z = __byte_perm(u.w, w.w, 0x5140); b.w = __byte_perm(u.w, w.w, 0x7362);
+                    *(uint4 *)(A + 32 * c) = a;
+                    *(uint4 *)(A + 32 * c + 16) = b;
+                }
+            }
+            __syncwarp();
+            const uint32_t nbytes = 2 * npairs;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t c = (k * 32 + lane) * 16;
+                if (c + 16 <= nbytes) *(uint4 *)(prow + c) = *(const uint4 *)(A + c);
+                else if (c < nbytes) { const uint4 t = *(const uint4 *)(A + c); const uint32_t wd[4] = {t.x, t.y, t.z, t.w}; store_prefix<4>(prow + c, wd, nbytes - c); }
+            }
+        }
+    }
+}
+
 /* ========================================================================================== */
 /* NV12 -> RGB24 (+ optional I420)                                                            */
 /* ========================================================================================== */
@@ -581,29 +786,6 @@ struct RgbCfg {                           /* tools/sweep.cu: 128 x 8 CTAs/SM, on
     static constexpr int LDP = 1;
     static constexpr int STP = 0;
 };
-
-/* store the first nbytes (<= 4*NW) of a register chunk at dst, as wide as dst's alignment allows */
-template <int NW> __device__ __forceinline__ void store_prefix(uint8_t *dst, const uint32_t (&wd)[NW], uint32_t nbytes)
-{
-    const uint32_t a = (uint32_t)(uintptr_t)dst;
-    if (NW == 4 && nbytes == 16 && (a & 7) == 0) {
-        if ((a & 15) == 0) *(uint4 *)dst = make_uint4(wd[0], wd[1], wd[2], wd[3]);
-        else { *(uint2 *)dst = make_uint2(wd[0], wd[1]); *(uint2 *)(dst + 8) = make_uint2(wd[2], wd[3]); }
-        return;
-    }
-    if (NW == 2 && nbytes == 8 && (a & 3) == 0) {
-        if ((a & 7) == 0) *(uint2 *)dst = make_uint2(wd[0], wd[1]);
-        else { *(uint32_t *)dst = wd[0]; *(uint32_t *)(dst + 4) = wd[1]; }
-        return;
-    }
-    const uint32_t nfull = (a & 3) == 0 ? (nbytes >> 2) : 0;              /* leading bytes that can go out as words */
-#pragma unroll
-    for (int i = 0; i < NW; i++)
-        if ((uint32_t)i < nfull) *(uint32_t *)(dst + 4 * i) = wd[i];
-#pragma unroll
-    for (int i = 0; i < 4 * NW; i++)
-        if ((uint32_t)i >= 4 * nfull && (uint32_t)i < nbytes) dst[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
-}
 
 /* copy nbytes from warp-private shared memory to global, V bytes per lane per step */
 template <int V, int STP> __device__ __forceinline__ void warp_flush(uint8_t *g, const uint8_t *st, uint32_t nbytes, uint32_t lane)

@@ -264,3 +264,48 @@ def test_rgb_ldg_stg_kernel_still_matches(ctx, c, fused, monkeypatch):
     else:
         rgb = G.gpu_rgb(ctx, c)
     assert K.sha(rgb) == GOLD[K.case_id(c)]["sha256"]
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_widths_on_aligned_surfaces(ctx, seed):
+    """The row-staged kernel: decoder-style surfaces (16-byte aligned, pitch a multiple of 16) with
+    arbitrary widths/heights and arbitrarily skewed tight buffers, all four YUV ops, vs the oracle."""
+    chk = oracle.best()
+    rng = np.random.default_rng(3000 + seed)
+    for _ in range(30):
+        w = int(rng.integers(1, 2600))
+        h = int(rng.integers(1, 24))
+        pitch = ((w + 15) & ~15) + 16 * int(rng.integers(0, 5))
+        kt = int(rng.integers(0, 16))
+        surf = synth.nv12_surface(w, h, pitch, 23, w * 31 + h)
+        tight_in = synth.i420_frame(w, h, 24, w * 13 + h)
+        cap = w * h * 3 // 2 + K.SLACK
+        nsurf = pitch * (h * 3 // 2 + 1)
+        dsurf = ctx.upload(surf)
+        for fmt in (0, 1):
+            dout = ctx.alloc(cap + 64)
+            ctx.memset(dout, synth.OUT_FILL, cap + 64)
+            j = ctx.job_nvdec(w, h, pitch, fmt)
+            j.n_frames, j.surf.base, j.tight.base = 1, dsurf, dout + kt
+            ctx.convert(j)
+            got = np.empty(cap, np.uint8)
+            ctx.d2h(got, dout + kt)
+            want = np.full(cap, synth.OUT_FILL, np.uint8)
+            chk.nvdec_output_frame(surf, pitch, w, h, fmt, want, cap)
+            assert np.array_equal(got, want), (w, h, pitch, kt, fmt)
+            ctx.free(dout)
+        dtin = ctx.alloc(tight_in.size + 64)
+        ctx.h2d(dtin + kt, tight_in)
+        for code in (0x1, 0x10):
+            ds = ctx.alloc(nsurf)
+            ctx.memset(ds, synth.PAD_BYTE, nsurf)
+            j = ctx.job_nvenc(w, h, pitch, code)
+            j.n_frames, j.surf.base, j.tight.base = 1, ds, dtin + kt
+            ctx.convert(j)
+            got = np.empty(nsurf, np.uint8)
+            ctx.d2h(got, ds)
+            want = np.full(nsurf, synth.PAD_BYTE, np.uint8)
+            oracle.nvenc_upload(tight_in, code, w, h, want, pitch)
+            assert np.array_equal(got, want), (w, h, pitch, kt, hex(code))
+            ctx.free(ds)
+        ctx.free(dsurf), ctx.free(dtin)
