@@ -309,3 +309,13 @@ def test_random_widths_on_aligned_surfaces(ctx, seed):
             assert np.array_equal(got, want), (w, h, pitch, kt, hex(code))
             ctx.free(ds)
         ctx.free(dsurf), ctx.free(dtin)
+
+
+@pytest.mark.parametrize("c", [c for c in GPU_CASES if c["op"] in ("nvdec", "nvenc") and c.get("kind", "random") == "random"
+                               and c["w"] % 16 != 0], ids=K.case_id)
+def test_any_alignment_kernel_still_matches(ctx, c, monkeypatch):
+    """Widths that are not multiples of 16 normally take the row-staged kernel when the surface is aligned;
+    JMC_NO_ROWS=1 keeps them on the any-alignment vector kernel, which must give the same bytes."""
+    monkeypatch.setenv("JMC_NO_ROWS", "1")
+    out = G.run_case_gpu(ctx, c)
+    assert K.sha(out) == GOLD[K.case_id(c)]["sha256"]
