@@ -36,7 +36,9 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (op, w, h, pitch, frames per launch)
     "nv12_to_i420_1080p_x300_pitch2048": ("i420", 1920, 1080, 2048, 300),
+    "nv12_to_i420_1080p_x300_pitch1920": ("i420", 1920, 1080, 1920, 300),      # no padding: shows what the pitch costs
     "nv12_to_i420_4k_x64_pitch4096": ("i420", 3840, 2160, 4096, 64),
+    "nv12_to_i420_4k_x64_pitch3840": ("i420", 3840, 2160, 3840, 64),
     "nv12_to_nv12_1080p_x300_pitch2048": ("nv12", 1920, 1080, 2048, 300),
     "i420_to_nv12_1080p_x300_pitch2048": ("pack", 1920, 1080, 2048, 300),
     "i420_to_nv12_4k_x64_pitch4096": ("pack", 3840, 2160, 4096, 64),
