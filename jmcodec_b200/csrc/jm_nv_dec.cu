@@ -315,6 +315,7 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
     jm_nvdec_raw_packet h;
     memcpy(&h, buf, sizeof(h));
     if (h.magic != JM_NVDEC_RAW_MAGIC || h.width < 0 || h.height < 0 || h.pitch < h.width) return -1;
+    if ((int64_t)h.pitch * h.height * 3 / 2 > 0x7fffffffll) return -1;     /* the API counts frame bytes in int (nv_dec.cpp:773) */
     if ((int)c->queue->size() >= NVDEC_MAX_FRAMES) return -1;            /* all decode surfaces in use */
     decoded_surface s;
     memset(&s, 0, sizeof(s));
