@@ -102,6 +102,7 @@ class ClockSampler:
     def __init__(self, index):
         self.samples, self.reasons, self.max_mhz, self._run, self._on = [], set(), None, False, False
         self.index, self.proc, self.source = index, None, "nvml"
+        self.period = float(os.environ.get("JMC_BENCH_CLOCK_PERIOD_MS", "2")) * 1e-3
         try:
             if os.environ.get("JMC_BENCH_NO_NVML"):
                 raise RuntimeError("NVML disabled by JMC_BENCH_NO_NVML")
@@ -129,7 +130,7 @@ class ClockSampler:
                             self.reasons.add(k)
                 except Exception:
                     pass
-            time.sleep(0.002)
+            time.sleep(self.period)
 
     def start(self):
         if self.nv:
