@@ -44,6 +44,7 @@ WORKLOADS = {
     "i420_to_nv12_4k_x64_pitch4096": ("pack", 3840, 2160, 4096, 64),
     "nv12_to_rgb24_4k_x64_pitch4096": ("rgb", 3840, 2160, 4096, 64),
     "nv12_to_i420_rgb24_4k_x64_pitch4096": ("fused", 3840, 2160, 4096, 64),
+    "nv12_to_argb32_4k_x64_pitch4096": ("argb", 3840, 2160, 4096, 64),
 }
 DEFAULT_WORKLOAD = "nv12_to_i420_1080p_x300_pitch2048"
 N_DISTINCT = 32          # distinct synthetic surfaces, tiled over the batch
@@ -248,6 +249,9 @@ def build_job(ctx, op, w, h, pitch, n, d_in, d_out, d_out2):
     elif op == "pack":
         j = ctx.job_nvenc(w, h, pitch, 0x10)
         j.tight.base, j.tight.stride, j.surf.base, j.surf.stride = d_in, tight_bytes, d_out, surf_bytes
+    elif op == "argb":
+        j = ctx.job_argb(w, h, pitch, 4 * w)
+        j.surf.base, j.surf.stride, j.rgb.base, j.rgb.stride = d_in, surf_bytes, d_out, 4 * w * h
     else:
         j = ctx.job_rgb(w, h, pitch, 3 * w, op == "fused")
         j.surf.base, j.surf.stride = d_in, surf_bytes
@@ -265,6 +269,8 @@ def io_bytes(op, w, h, pitch):
         return tight_bytes, surf_bytes, 0
     if op == "rgb":
         return surf_bytes, rgb, 0
+    if op == "argb":
+        return surf_bytes, 4 * w * h, 0
     if op == "fused":
         return surf_bytes, tight_bytes, rgb
     return surf_bytes, tight_bytes, 0
@@ -455,7 +461,7 @@ def main():
     # ---- the reference's real data flow: surfaces already in HBM (NVDEC wrote them), only the tight
     #      frames travel: convert + D2H, no H2D (reported beside e2e, never instead of it) ----------------
     decode_path = None
-    if op in ("i420", "nv12", "rgb", "fused"):
+    if op in ("i420", "nv12", "rgb", "fused", "argb"):
         def resident_step():
             for b in range(n // sub):
                 pipe.submit(None, hout.array[b * sub * out_b:], sub, dev_in=d_in + b * sub * in_b,

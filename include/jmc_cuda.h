@@ -81,7 +81,10 @@ typedef enum jmc_op {
     JMC_OP_I420_TO_SURF = 3,   /* + U/V interleave         nv_enc.cpp:1041-1081 (InterleaveUV), intel_enc.cpp:366-380 */
     /* display side (test_player.cpp:283-288 hands I420 to SDL2; builder-defined integer BT.601) */
     JMC_OP_NV12_TO_RGB24 = 4,
-    JMC_OP_NV12_TO_I420_RGB24 = 5  /* fused: one read of the surface, both outputs */
+    JMC_OP_NV12_TO_I420_RGB24 = 5, /* fused: one read of the surface, both outputs */
+    /* what the reference's disabled NV12ToARGB_drvapi hook would have produced on the device
+     * (nv_dec.cpp:244-265): packed 32-bit ARGB8888, i.e. bytes B,G,R,0xFF per pixel; same integer BT.601 */
+    JMC_OP_NV12_TO_ARGB32 = 6
 } jmc_op;
 
 /* Where frame f of a batch lives: base + f*stride, or list[f] (a DEVICE array of n_frames device
@@ -107,7 +110,7 @@ typedef struct jmc_job {
     int64_t    tight_v_off;   /* I420 ops: V plane offset (nv_dec: w*h+(w>>1)*(h>>1), :815)     */
     /* packed RGB24 destination of the display ops */
     jmc_frames rgb;
-    int32_t    rgb_pitch;     /* bytes per RGB row, >= 3*width                                  */
+    int32_t    rgb_pitch;     /* bytes per RGB row, >= 3*width (>= 4*width for ARGB32)          */
     uint32_t   flags;         /* JMC_JOB_*                                                      */
 } jmc_job;
 
@@ -128,6 +131,8 @@ JMC_API int jmc_job_intelenc(jmc_job *job, int pitch, int surf_rows, int crop_x,
 JMC_API int jmc_job_nvenc(jmc_job *job, int width, int height, int stride, int in_fmt);
 /* NV12_TO_RGB24 / NV12_TO_I420_RGB24 on an nv_dec-style surface (fused != 0 adds the I420 output). */
 JMC_API int jmc_job_rgb(jmc_job *job, int width, int height, int pitch, int rgb_pitch, int fused);
+/* NV12_TO_ARGB32 on an nv_dec-style surface; the ARGB frames go to job->rgb, row pitch argb_pitch >= 4*width. */
+JMC_API int jmc_job_argb(jmc_job *job, int width, int height, int pitch, int argb_pitch);
 /* Bytes of one tight frame as the reference computes it: w*h*3/2 (nv_dec.cpp:773,824). */
 JMC_API int64_t jmc_tight_bytes(int width, int height);
 /* Algorithmic bytes (read + write, padding excluded) one frame of `job` moves: the roofline numerator. */

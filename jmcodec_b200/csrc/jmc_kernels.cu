@@ -232,12 +232,13 @@ static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
 static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
 {
     const bool fused = j->op == JMC_OP_NV12_TO_I420_RGB24;
+    const bool argb = j->op == JMC_OP_NV12_TO_ARGB32;
     if (!frames_ok(j->surf) || !frames_ok(j->rgb) || (fused && !frames_ok(j->tight))) {
         jmc_set_error("jmc_convert: surf/rgb/tight frame set is empty");
         return JMC_ERR_INVALID;
     }
     if ((j->width >> 1) < 1 || (j->height >> 1) < 1) { jmc_set_error("jmc_convert: RGB needs width,height >= 2"); return JMC_ERR_INVALID; }
-    if (j->rgb_pitch < 3 * j->width) { jmc_set_error("jmc_convert: rgb_pitch < 3*width"); return JMC_ERR_INVALID; }
+    if (j->rgb_pitch < (argb ? 4 : 3) * j->width) { jmc_set_error("jmc_convert: rgb_pitch < %d*width", argb ? 4 : 3); return JMC_ERR_INVALID; }
     RgbParams p;
     p.surf = to_set(j->surf);
     p.tight = to_set(j->tight);
@@ -248,6 +249,7 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     p.u_off = j->tight_u_off; p.v_off = j->tight_v_off;
     p.rgb_pitch = j->rgb_pitch;
     p.fused = fused ? 1 : 0;
+    p.argb = argb ? 1 : 0;
     p.segs_per_row = ((uint32_t)j->width + 511) / 512;
     p.row_pairs = ((uint32_t)j->height + 1) / 2;
     p.tasks_per_frame = p.segs_per_row * p.row_pairs;
@@ -261,7 +263,7 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
         uint64_t bits = (uint64_t)j->surf_y_off | (uint64_t)j->surf_uv_off | (uint32_t)j->pitch | (uint32_t)j->rgb_pitch | (uint32_t)j->width;
         if (fused) bits |= (uint32_t)(j->width >> 1);            /* U / V rows are bulk-stored too */
         const jmc_frames *sets[3] = { &j->surf, &j->rgb, fused ? &j->tight : nullptr };
-        bool ok = !getenv_flag("JMC_NO_BULK");
+        bool ok = !getenv_flag("JMC_NO_BULK") && !argb;          /* ARGB32 runs on the vector kernel */
         for (int i = 0; i < 3 && ok; i++) {
             if (!sets[i]) continue;
             if (sets[i]->list) ok = (j->flags & JMC_JOB_ALIGNED16) != 0;
@@ -298,7 +300,8 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     constexpr uint32_t WARPS = RgbCfg::THREADS / 32;
     const uint32_t blocks_needed = (p.total_tasks + WARPS - 1) / WARPS;
     const uint32_t grid = blocks_needed;             /* one warp per (row pair, 512-pixel segment) task */
-    rgb_kernel<RgbCfg><<<grid, RgbCfg::THREADS, 0, stream>>>(p);
+    if (argb) rgb_kernel<RgbCfg, true><<<grid, RgbCfg::THREADS, 0, stream>>>(p);
+    else rgb_kernel<RgbCfg, false><<<grid, RgbCfg::THREADS, 0, stream>>>(p);
     JMC_CUDA(cudaGetLastError());
     ctx->launches++;
     return JMC_OK;
@@ -319,6 +322,7 @@ int jmc_launch_job(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
         return launch_planes(ctx, j, stream);
     case JMC_OP_NV12_TO_RGB24:
     case JMC_OP_NV12_TO_I420_RGB24:
+    case JMC_OP_NV12_TO_ARGB32:
         return launch_rgb(ctx, j, stream);
     default:
         jmc_set_error("jmc_convert: unknown op %d", j->op);

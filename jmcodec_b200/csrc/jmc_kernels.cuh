@@ -728,6 +728,7 @@ struct RgbParams {
     int64_t u_off, v_off;      /* tight I420 plane offsets (fused only) */
     int32_t rgb_pitch;
     int32_t fused;
+    int32_t argb;              /* 1: 4 bytes per pixel (B,G,R,0xFF) instead of packed R,G,B */
     uint32_t segs_per_row;     /* ceil(width / 512): one warp covers 512 pixels of a row pair */
     uint32_t row_pairs;        /* ceil(height / 2) */
     uint32_t tasks_per_frame;  /* row_pairs * segs_per_row */
@@ -778,6 +779,19 @@ __device__ __forceinline__ void rgb4(uint32_t yw, int r0, int g0, int b0, int r1
     out[2] = __byte_perm(pack_sat_u16(R3, B2), pack_sat_u16(B3, G3), 0x7531);   /* B2 R3 G3 B3 */
 }
 
+/* same 4 pixels -> 4 ARGB8888 words (bytes B,G,R,0xFF): sat_u16(65535) supplies the alpha byte */
+__device__ __forceinline__ void argb4(uint32_t yw, int r0, int g0, int b0, int r1, int g1, int b1, uint32_t *out)
+{
+    const int R0 = dp2a_lo(COEF_Y_EVEN, yw, r0), G0 = dp2a_lo(COEF_Y_EVEN, yw, g0), B0 = dp2a_lo(COEF_Y_EVEN, yw, b0);
+    const int R1 = dp2a_lo(COEF_Y_ODD, yw, r0), G1 = dp2a_lo(COEF_Y_ODD, yw, g0), B1 = dp2a_lo(COEF_Y_ODD, yw, b0);
+    const int R2 = dp2a_hi(COEF_Y_EVEN, yw, r1), G2 = dp2a_hi(COEF_Y_EVEN, yw, g1), B2 = dp2a_hi(COEF_Y_EVEN, yw, b1);
+    const int R3 = dp2a_hi(COEF_Y_ODD, yw, r1), G3 = dp2a_hi(COEF_Y_ODD, yw, g1), B3 = dp2a_hi(COEF_Y_ODD, yw, b1);
+    out[0] = __byte_perm(pack_sat_u16(G0, B0), pack_sat_u16(65535, R0), 0x7531);
+    out[1] = __byte_perm(pack_sat_u16(G1, B1), pack_sat_u16(65535, R1), 0x7531);
+    out[2] = __byte_perm(pack_sat_u16(G2, B2), pack_sat_u16(65535, R2), 0x7531);
+    out[3] = __byte_perm(pack_sat_u16(G3, B3), pack_sat_u16(65535, R3), 0x7531);
+}
+
 __device__ __forceinline__ uint8_t clip8_dev(int v) { return (uint8_t)min(max(v, 0), 255); }
 
 struct RgbCfg {                           /* tools/sweep.cu: 128 x 8 CTAs/SM, one warp task per warp */
@@ -803,11 +817,11 @@ template <int V, int STP> __device__ __forceinline__ void warp_flush(uint8_t *g,
     }
 }
 
-template <class C>
+template <class C, bool ARGB>
 __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const __grid_constant__ RgbParams p)
 {
     constexpr int WARPS = C::THREADS / 32;
-    __shared__ __align__(16) uint8_t stage[WARPS][32 * 48];
+    __shared__ __align__(16) uint8_t stage[WARPS][32 * 80];      /* RGB24: 48 B per lane; ARGB32: 64 B at an 80-byte stride */
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t warps_total = gridDim.x * WARPS;
     const int w = p.width, h = p.height, cw = w >> 1, ch = h >> 1;
@@ -868,6 +882,32 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
                 if (row == 1 && !two) break;
                 const uint4 yy = row ? yb : ya;
                 const uint32_t yw[4] = {yy.x, yy.y, yy.z, yy.w};
+                if (ARGB) {
+                    __syncwarp();
+                    uint4 *s4 = (uint4 *)(st + lane * 80);                        /* 80-byte stride: conflict-free 16-byte stores */
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {                                 /* one luma word = 4 pixels = one 16-byte store */
+                        uint32_t o[4];
+                        argb4(yw[j], cr[2 * j], cg[2 * j], cb[2 * j], cr[2 * j + 1], cg[2 * j + 1], cb[2 * j + 1], o);
+                        s4[j] = make_uint4(o[0], o[1], o[2], o[3]);
+                    }
+                    __syncwarp();
+                    uint8_t *g = orow + (size_t)row * p.rgb_pitch + (size_t)seg * (32 * 64);
+                    const uint32_t nb = 4 * seg_px;                               /* a multiple of 8 */
+                    if ((((uint32_t)(uintptr_t)g | nb) & 15) == 0) {
+#pragma unroll
+                        for (int k = 0; k < 4; k++) {
+                            const uint32_t c = k * 32 + lane;                     /* 16-byte chunk: lane c/4, part c%4 */
+                            if (16 * c < nb) st16<C::STP>(g + 16 * c, *(const uint4 *)(st + (c >> 2) * 80 + (c & 3) * 16));
+                        }
+                    } else if (((uint32_t)(uintptr_t)g & 3) == 0) {
+                        for (uint32_t c = lane; 4 * c < nb; c += 32)
+                            *(uint32_t *)(g + 4 * c) = *(const uint32_t *)(st + (c >> 4) * 80 + (c & 15) * 4);
+                    } else {
+                        for (uint32_t c = lane; c < nb; c += 32) g[c] = st[(c >> 6) * 80 + (c & 63)];
+                    }
+                    continue;
+                }
                 uint32_t o[12];
 #pragma unroll
                 for (int j = 0; j < 4; j++)
@@ -898,10 +938,16 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
                 for (uint32_t row = 0; row < (two ? 2u : 1u); row++) {
                     const int Y = yrow[(size_t)row * p.pitch + x];
                     const int c = Y - 16;
-                    uint8_t *o = orow + (size_t)row * p.rgb_pitch + 3 * (size_t)x;
-                    o[0] = clip8_dev((298 * c + 409 * e + 128) >> 8);
-                    o[1] = clip8_dev((298 * c - 100 * d - 208 * e + 128) >> 8);
-                    o[2] = clip8_dev((298 * c + 516 * d + 128) >> 8);
+                    const uint8_t R = clip8_dev((298 * c + 409 * e + 128) >> 8);
+                    const uint8_t G = clip8_dev((298 * c - 100 * d - 208 * e + 128) >> 8);
+                    const uint8_t Bl = clip8_dev((298 * c + 516 * d + 128) >> 8);
+                    if (ARGB) {
+                        uint8_t *o = orow + (size_t)row * p.rgb_pitch + 4 * (size_t)x;
+                        o[0] = Bl; o[1] = G; o[2] = R; o[3] = 0xFF;
+                    } else {
+                        uint8_t *o = orow + (size_t)row * p.rgb_pitch + 3 * (size_t)x;
+                        o[0] = R; o[1] = G; o[2] = Bl;
+                    }
                     if (p.fused) tp[(size_t)(y0 + row) * w + x] = (uint8_t)Y;
                 }
                 if (p.fused && rp < (uint32_t)ch && (x & 1) == 0 && (x >> 1) < (uint32_t)cw) {

@@ -233,6 +233,16 @@ int jmc_job_rgb(jmc_job *j, int width, int height, int pitch, int rgb_pitch, int
     return JMC_OK;
 }
 
+int jmc_job_argb(jmc_job *j, int width, int height, int pitch, int argb_pitch)
+{
+    int r = jmc_job_nvdec(j, width, height, pitch, 1);
+    if (r) return r;
+    if (argb_pitch < 4 * width) { jmc_set_error("jmc_job_argb: argb_pitch < 4*width"); return JMC_ERR_INVALID; }
+    j->op = JMC_OP_NV12_TO_ARGB32;
+    j->rgb_pitch = argb_pitch;
+    return JMC_OK;
+}
+
 int64_t jmc_job_algorithmic_bytes(const jmc_job *j)
 {
     if (!j) return 0;
@@ -245,6 +255,7 @@ int64_t jmc_job_algorithmic_bytes(const jmc_job *j)
     }
     switch (j->op) {
     case JMC_OP_NV12_TO_RGB24: return luma + w * ((h + 1) >> 1) + 3 * luma;          /* reads every chroma row it uses */
+    case JMC_OP_NV12_TO_ARGB32: return luma + w * ((h + 1) >> 1) + 4 * luma;
     case JMC_OP_NV12_TO_I420_RGB24: return luma + w * ((h + 1) >> 1) + yuv + 3 * luma;
     default: return 2 * yuv;
     }
@@ -334,7 +345,11 @@ struct jmc_pipeline {
     uint64_t h2d, d2h;
 };
 
-static bool op_is_decode_side(int op) { return op == JMC_OP_NV12_TO_NV12 || op == JMC_OP_NV12_TO_I420 || op == JMC_OP_NV12_TO_RGB24 || op == JMC_OP_NV12_TO_I420_RGB24; }
+static bool op_is_decode_side(int op)
+{
+    return op == JMC_OP_NV12_TO_NV12 || op == JMC_OP_NV12_TO_I420 || op == JMC_OP_NV12_TO_RGB24 || op == JMC_OP_NV12_TO_I420_RGB24 ||
+           op == JMC_OP_NV12_TO_ARGB32;
+}
 
 extern "C" {
 
@@ -350,7 +365,7 @@ int jmc_pipeline_create(jmc_ctx *c, const jmc_job *shape, size_t surf_bytes, int
     p->ctx = c; p->shape = *shape; p->depth = depth; p->next = 0; p->h2d = p->d2h = 0;
     switch (shape->op) {
     case JMC_OP_NV12_TO_NV12: case JMC_OP_NV12_TO_I420: p->in_bytes = surf_bytes; p->out_bytes = tight; p->out2_bytes = 0; break;
-    case JMC_OP_NV12_TO_RGB24: p->in_bytes = surf_bytes; p->out_bytes = rgb; p->out2_bytes = 0; break;
+    case JMC_OP_NV12_TO_RGB24: case JMC_OP_NV12_TO_ARGB32: p->in_bytes = surf_bytes; p->out_bytes = rgb; p->out2_bytes = 0; break;
     case JMC_OP_NV12_TO_I420_RGB24: p->in_bytes = surf_bytes; p->out_bytes = tight; p->out2_bytes = rgb; break;
     case JMC_OP_NV12_TO_SURF: case JMC_OP_I420_TO_SURF: p->in_bytes = tight; p->out_bytes = surf_bytes; p->out2_bytes = 0; break;
     default: delete p; jmc_set_error("jmc_pipeline_create: unknown op"); return JMC_ERR_INVALID;
@@ -435,7 +450,7 @@ int jmc_pipeline_submit(jmc_pipeline *p, const void *host_in, const void *dev_in
     j.surf.list = j.tight.list = j.rgb.list = nullptr;
     if (dec) {
         j.surf.base = (void *)src; j.surf.stride = p->in_bytes;
-        if (j.op == JMC_OP_NV12_TO_RGB24) { j.rgb.base = s.d_out; j.rgb.stride = p->out_bytes; }
+        if (j.op == JMC_OP_NV12_TO_RGB24 || j.op == JMC_OP_NV12_TO_ARGB32) { j.rgb.base = s.d_out; j.rgb.stride = p->out_bytes; }
         else { j.tight.base = s.d_out; j.tight.stride = p->out_bytes; }
         if (j.op == JMC_OP_NV12_TO_I420_RGB24) { j.rgb.base = s.d_out2; j.rgb.stride = p->out2_bytes; }
     } else {

@@ -28,6 +28,7 @@ class JMC_OP(enum.IntEnum):
     I420_TO_SURF = 3
     NV12_TO_RGB24 = 4
     NV12_TO_I420_RGB24 = 5
+    NV12_TO_ARGB32 = 6
 
 
 JOB_ALIGNED16 = 1
@@ -96,6 +97,7 @@ _SIGS = {
     "jmc_job_intelenc": (C.c_int, [C.POINTER(Job)] + [C.c_int] * 7),
     "jmc_job_nvenc": (C.c_int, [C.POINTER(Job)] + [C.c_int] * 4),
     "jmc_job_rgb": (C.c_int, [C.POINTER(Job)] + [C.c_int] * 5),
+    "jmc_job_argb": (C.c_int, [C.POINTER(Job)] + [C.c_int] * 4),
     "jmc_tight_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "jmc_job_algorithmic_bytes": (C.c_int64, [C.POINTER(Job)]),
     "jmc_convert": (C.c_int, [C.c_void_p, C.POINTER(Job), C.c_void_p]),
@@ -299,6 +301,11 @@ class Ctx:
     def job_rgb(self, w, h, pitch, rgb_pitch, fused=False) -> Job:
         j = Job()
         _ck(self.L.jmc_job_rgb(C.byref(j), w, h, pitch, rgb_pitch, 1 if fused else 0), "jmc_job_rgb")
+        return j
+
+    def job_argb(self, w, h, pitch, argb_pitch) -> Job:
+        j = Job()
+        _ck(self.L.jmc_job_argb(C.byref(j), w, h, pitch, argb_pitch), "jmc_job_argb")
         return j
 
     def algorithmic_bytes(self, job: Job) -> int:

@@ -55,6 +55,8 @@ class _Port:
         L.jmo_nvenc_upload.restype = C.c_int
         L.jmo_nv12_to_rgb24.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         L.jmo_nv12_to_rgb24.restype = C.c_int
+        L.jmo_nv12_to_argb32.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
+        L.jmo_nv12_to_argb32.restype = C.c_int
         L.jmo_nvdec_run.argtypes = [_u8p, C.c_size_t, C.c_int, _u8p, C.c_size_t, C.c_int] + [C.c_int] * 6
         L.jmo_nvdec_run.restype = C.c_double
         self.L = L
@@ -194,3 +196,7 @@ def ref_nvenc_convert(in_buf, fmt, w, h, surf, stride):
 
 def nv12_to_rgb24(surf, pitch, w, h, rgb, rgb_pitch):
     return port().impl.L.jmo_nv12_to_rgb24(_ptr(surf), pitch, w, h, _ptr(rgb), rgb_pitch)
+
+
+def nv12_to_argb32(surf, pitch, w, h, argb, argb_pitch):
+    return port().impl.L.jmo_nv12_to_argb32(_ptr(surf), pitch, w, h, _ptr(argb), argb_pitch)

@@ -171,6 +171,30 @@ int jmo_nv12_to_rgb24(const uint8_t *surf, int pitch, int width, int height,
     return 0;
 }
 
+/* builder-defined spec, see jm_oracle.h (PARITY UNPINNED) */
+int jmo_nv12_to_argb32(const uint8_t *surf, int pitch, int width, int height,
+                       uint8_t *argb, int argb_pitch)
+{
+    const int cw = width >> 1, ch = height >> 1;
+    if (cw < 1 || ch < 1) return -1;
+    const uint8_t *uvp = surf + (size_t)pitch * height;
+    for (int y = 0; y < height; y++) {
+        int cy = y >> 1; if (cy > ch - 1) cy = ch - 1;
+        const uint8_t *yr = surf + (size_t)y * pitch;
+        const uint8_t *cr = uvp + (size_t)cy * pitch;
+        uint8_t *o = argb + (size_t)y * argb_pitch;
+        for (int x = 0; x < width; x++) {
+            int cx = x >> 1; if (cx > cw - 1) cx = cw - 1;
+            const int c = yr[x] - 16, d = cr[2 * cx] - 128, e = cr[2 * cx + 1] - 128;
+            o[4 * x + 0] = clip8((298 * c + 516 * d + 128) >> 8);               /* B */
+            o[4 * x + 1] = clip8((298 * c - 100 * d - 208 * e + 128) >> 8);     /* G */
+            o[4 * x + 2] = clip8((298 * c + 409 * e + 128) >> 8);               /* R */
+            o[4 * x + 3] = 0xFF;                                                 /* A */
+        }
+    }
+    return 0;
+}
+
 /* ---- "port" CPU baseline loop ---- */
 typedef struct {
     const uint8_t *surf_base; size_t surf_stride; int n_surf;

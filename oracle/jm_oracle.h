@@ -70,6 +70,12 @@ int jmo_nvenc_upload(const uint8_t *in_buf, int fmt, int width, int height,
 int jmo_nv12_to_rgb24(const uint8_t *surf, int pitch, int width, int height,
                       uint8_t *rgb, int rgb_pitch);
 
+/* Builder-defined (PARITY UNPINNED): the same integer BT.601 as jmo_nv12_to_rgb24, written as packed
+ * ARGB8888 words, i.e. bytes B,G,R,0xFF per pixel -- the layout the reference's disabled
+ * NV12ToARGB_drvapi hook targets (nv_dec/nv_dec.cpp:244-265).  argb_pitch >= 4*w. */
+int jmo_nv12_to_argb32(const uint8_t *surf, int pitch, int width, int height,
+                       uint8_t *argb, int argb_pitch);
+
 /* "port" CPU baseline: frames calls of jmo_nvdec_output_frame, frame f reading surface
  * f % n_surf and writing slot f % n_out, round-robin over nthreads.  Returns seconds or -1. */
 double jmo_nvdec_run(const uint8_t *surf_base, size_t surf_stride, int n_surf,

@@ -85,8 +85,17 @@ def rgb_cases():
     return out
 
 
+def argb_cases():
+    out = []
+    for (w, h, p) in RGB_SIZES:
+        kinds = ["random"] + (["gradient", "const16", "const235", "const255"] if w * h <= 64 * 64 else [])
+        for k in kinds:
+            out.append(dict(op="argb32", w=w, h=h, pitch=p, kind=k))
+    return out
+
+
 def all_cases():
-    return nvdec_cases() + inteldec_cases() + intelenc_cases() + nvenc_cases() + rgb_cases()
+    return nvdec_cases() + inteldec_cases() + intelenc_cases() + nvenc_cases() + rgb_cases() + argb_cases()
 
 
 def case_id(c: dict) -> str:
@@ -191,7 +200,15 @@ def run_rgb(_chk, c):
     return r, rgb_pitch * c["h"], out
 
 
-RUNNERS = {"nvdec": run_nvdec, "inteldec": run_inteldec, "intelenc": run_intelenc,
+def run_argb(_chk, c):
+    import oracle
+    pitch4 = c["w"] * 4
+    out = np.full(pitch4 * c["h"] + SLACK, synth.OUT_FILL, np.uint8)
+    r = oracle.nv12_to_argb32(rgb_input(c), c["pitch"], c["w"], c["h"], out, pitch4)
+    return r, pitch4 * c["h"], out
+
+
+RUNNERS = {"argb32": run_argb, "nvdec": run_nvdec, "inteldec": run_inteldec, "intelenc": run_intelenc,
            "nvenc": run_nvenc, "rgb24": run_rgb}
 # ops for which the unmodified reference has CPU code that oracle/_ref executes
 REF_OPS = ("nvdec", "inteldec", "intelenc", "nvenc")

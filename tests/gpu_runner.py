@@ -97,7 +97,20 @@ def gpu_rgb(ctx, c, fused=False):
     return (out, tight) if fused else out
 
 
-GPU_RUNNERS = {"nvdec": gpu_nvdec, "inteldec": gpu_inteldec, "intelenc": gpu_intelenc, "nvenc": gpu_nvenc, "rgb24": gpu_rgb}
+def gpu_argb(ctx, c):
+    s = K.rgb_input(c)
+    w, h = c["w"], c["h"]
+    cap = 4 * w * h + K.SLACK
+    ds, dout = ctx.upload(s), _dev_filled(ctx, cap, synth.OUT_FILL)
+    j = ctx.job_argb(w, h, c["pitch"], 4 * w)
+    j.n_frames, j.surf.base, j.rgb.base = 1, ds, dout
+    ctx.convert(j)
+    out = _download(ctx, dout, cap)
+    ctx.free(ds), ctx.free(dout)
+    return out
+
+
+GPU_RUNNERS = {"argb32": gpu_argb, "nvdec": gpu_nvdec, "inteldec": gpu_inteldec, "intelenc": gpu_intelenc, "nvenc": gpu_nvenc, "rgb24": gpu_rgb}
 
 
 def run_case_gpu(ctx, c):

@@ -149,7 +149,7 @@ def test_nvenc_api_upload(J, ctx, fmt, geom):
 # --------------------------------------------------------------------------------------------
 # host-delivery pipeline
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("op", ["i420", "nv12", "rgb", "fused", "pack"])
+@pytest.mark.parametrize("op", ["i420", "nv12", "rgb", "fused", "pack", "argb"])
 def test_pipeline_batches(J, ctx, op):
     w, h, pitch, batch, nb = 640, 360, 768, 5, 7
     surf_bytes, tight_bytes, rgb_bytes = pitch * h * 3 // 2, w * h * 3 // 2, 3 * w * h
@@ -157,6 +157,9 @@ def test_pipeline_batches(J, ctx, op):
     if op == "pack":
         shape = ctx.job_nvenc(w, h, pitch, 0x10)
         in_bytes, out_bytes = tight_bytes, surf_bytes
+    elif op == "argb":
+        shape = ctx.job_argb(w, h, pitch, 4 * w)
+        in_bytes, out_bytes = surf_bytes, 4 * w * h
     elif op in ("rgb", "fused"):
         shape = ctx.job_rgb(w, h, pitch, 3 * w, op == "fused")
         in_bytes, out_bytes = surf_bytes, (rgb_bytes if op == "rgb" else tight_bytes)
@@ -190,6 +193,9 @@ def test_pipeline_batches(J, ctx, op):
         elif op == "rgb":
             want = np.empty(out_bytes, np.uint8)
             oracle.nv12_to_rgb24(frames[i], pitch, w, h, want, 3 * w)
+        elif op == "argb":
+            want = np.empty(out_bytes, np.uint8)
+            oracle.nv12_to_argb32(frames[i], pitch, w, h, want, 4 * w)
         else:
             want = np.empty(out_bytes, np.uint8)
             chk.nvdec_output_frame(frames[i], pitch, w, h, 0 if op == "nv12" else 1, want, out_bytes)

@@ -102,7 +102,7 @@ struct RgbRun { RgbParams p; uint32_t grid; };
 template <class C> static void launch_rgb(void *arg)
 {
     RgbRun *r = (RgbRun *)arg;
-    rgb_kernel<C><<<r->grid, C::THREADS>>>(r->p);
+    rgb_kernel<C, false><<<r->grid, C::THREADS>>>(r->p);
 }
 
 template <int T, int B, int L, int S> struct RCfg { static constexpr int THREADS = T, BLOCKS_PER_SM = B, LDP = L, STP = S; };
