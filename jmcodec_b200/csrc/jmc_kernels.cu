@@ -21,6 +21,20 @@ static FrameSet to_set(const jmc_frames &f)
 
 static bool frames_ok(const jmc_frames &f) { return f.base != nullptr || f.list != nullptr; }
 
+/* fast_div(): m = ceil(2^sh / d), sh = 31 + ceil(log2 d) */
+static FastDiv make_fastdiv(uint32_t d)
+{
+    FastDiv f;
+    if (d == 0) d = 1;
+    uint32_t s = 0;
+    while ((1ull << s) < d) s++;
+    f.d = d;
+    f.sh = 31 + s;
+    f.m = (uint32_t)(((1ull << (31 + s)) + d - 1) / d);
+    f.pad_ = 0;
+    return f;
+}
+
 static Part make_part(int kind, uint32_t rows, uint32_t row_elems, int64_t p_off, int32_t pitch, int64_t a_off, int64_t b_off)
 {
     Part p;
@@ -34,14 +48,7 @@ static Part make_part(int kind, uint32_t rows, uint32_t row_elems, int64_t p_off
     p.pad_ = 0;
     p.a_off = a_off;
     p.b_off = b_off;
-    /* fast_div(): m = ceil(2^sh / d), sh = 31 + ceil(log2 d) */
-    const uint32_t d = row_elems ? row_elems : 1;
-    uint32_t s = 0;
-    while ((1ull << s) < d) s++;
-    p.rdiv.d = d;
-    p.rdiv.sh = 31 + s;
-    p.rdiv.m = (uint32_t)(((1ull << (31 + s)) + d - 1) / d);
-    p.rdiv.pad_ = 0;
+    p.rdiv = make_fastdiv(row_elems);
     return p;
 }
 
@@ -133,12 +140,23 @@ static int launch_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, in
         const Part &pt = pp.part[i];
         r.part[i] = pt;
         r.segs[i] = r.tasks[i] = 0;
+        r.rpt[i] = 1;
+        r.rstride[i] = ROWS_SEG;
+        r.cdiv[i] = make_fastdiv(ROWS_SEG / 16);
         if (pt.kind == PART_NONE) continue;
         const uint32_t row_bytes = pt.kind == PART_COPY ? pt.row_elems : 2 * pt.row_elems;      /* surface bytes per row */
         if (((uint64_t)pt.p_off | (uint32_t)pt.p_pitch) & 15) return 1;
         if ((uint32_t)pt.p_pitch < ((row_bytes + 15) & ~15u)) return 1;
         r.segs[i] = (row_bytes + ROWS_SEG - 1) / ROWS_SEG;
-        const uint64_t t = (uint64_t)pt.rows * r.segs[i];
+        /* short rows: several whole rows per warp task, so that each lane still has up to four loads in flight */
+        const uint32_t align = pt.kind == PART_COPY ? 16u : 32u;
+        const uint32_t rs = (row_bytes + align - 1) & ~(align - 1);
+        if (r.segs[i] == 1 && 2 * rs <= (uint32_t)ROWS_SEG && !getenv_flag("JMC_ROWS_SINGLE")) {
+            r.rpt[i] = std::min<uint32_t>(ROWS_SEG / rs, ROWS_MAX_RPT);
+            r.rstride[i] = rs;
+            r.cdiv[i] = make_fastdiv(rs / 16);
+        }
+        const uint64_t t = r.rpt[i] > 1 ? ((uint64_t)pt.rows + r.rpt[i] - 1) / r.rpt[i] : (uint64_t)pt.rows * r.segs[i];
         if (t > 0x3fffffffull) return 1;
         r.tasks[i] = (uint32_t)t;
         per_frame += t;
@@ -148,13 +166,18 @@ static int launch_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, in
     if (total > 0x7fffffffull) return 1;
     r.total_tasks = (uint32_t)total;
     const uint32_t grid = (r.total_tasks + ROWS_THREADS / 32 - 1) / (ROWS_THREADS / 32);
+    const bool multi = r.rpt[0] > 1 || r.rpt[1] > 1;
+#define JMC_ROWS(TT, K1)                                                                      \
+    do {                                                                                      \
+        if (multi) rows_kernel<TT, K1, true><<<grid, ROWS_THREADS, 0, stream>>>(r);           \
+        else rows_kernel<TT, K1, false><<<grid, ROWS_THREADS, 0, stream>>>(r);                \
+    } while (0)
     if (pp.to_tight) {
-        if (k1 == PART_SPLIT) rows_kernel<true, PART_SPLIT><<<grid, ROWS_THREADS, 0, stream>>>(r);
-        else rows_kernel<true, PART_COPY><<<grid, ROWS_THREADS, 0, stream>>>(r);
+        if (k1 == PART_SPLIT) JMC_ROWS(true, PART_SPLIT); else JMC_ROWS(true, PART_COPY);
     } else {
-        if (k1 == PART_MERGE) rows_kernel<false, PART_MERGE><<<grid, ROWS_THREADS, 0, stream>>>(r);
-        else rows_kernel<false, PART_COPY><<<grid, ROWS_THREADS, 0, stream>>>(r);
+        if (k1 == PART_MERGE) JMC_ROWS(false, PART_MERGE); else JMC_ROWS(false, PART_COPY);
     }
+#undef JMC_ROWS
     JMC_CUDA(cudaGetLastError());
     ctx->launches++;
     return JMC_OK;
@@ -209,7 +232,7 @@ static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
         int r = launch_bulk(ctx, p, k1, stream);
         if (r != 1) return r;                        /* 1: geometry does not fit the bulk kernel, use LDG/STG */
     }
-    if (!wide && !getenv_flag("JMC_NO_ROWS") && narrow_vectors(j, p)) {
+    if (!wide && !getenv_flag("JMC_NO_ROWS") && (narrow_vectors(j, p) || getenv_flag("JMC_ROWS_ALWAYS"))) {
         int r = launch_rows(ctx, j, p, k1, stream);
         if (r != 1) return r;                        /* 1: surface side not 16-byte friendly, use the any-alignment kernel */
     }

@@ -544,79 +544,133 @@ template <int NW> __device__ __forceinline__ void store_prefix(uint8_t *dst, con
  * (row, 2 KB segment): 16-byte loads/stores on the surface side, a pass through warp-private shared
  * memory, and on the tight side 16-byte accesses to the ALIGNED body of the segment, re-aligned by a
  * funnel shift (classic unaligned memcpy), with byte accesses only for the <16-byte head and tail. */
+/* CTAs per SM the register allocation is sized for, decode / encode direction (A/B: tools/variants.sh,
+ * profiles/r1_odd_sizes_minb.txt: 10 beats 8 and 12 on the decode side) */
+#ifndef JMC_ROWS_MINB_DEC
+#define JMC_ROWS_MINB_DEC 10
+#endif
+#ifndef JMC_ROWS_MINB_ENC
+#define JMC_ROWS_MINB_ENC 8
+#endif
 constexpr int ROWS_THREADS = 128;
 constexpr int ROWS_SEG = 2048;                       /* surface bytes per warp task */
+constexpr int ROWS_MAX_RPT = 8;                      /* rows per warp task, upper bound (bounds the serial per-row store loop) */
 constexpr int ROWS_SMEM_A = ROWS_SEG + 32, ROWS_SMEM_B = ROWS_SEG / 2 + 32;
 
 struct RowsParams {
     FrameSet pitched, tight;
     uint32_t n_frames;
-    uint32_t tasks[2];        /* warp tasks per frame of part 0 / part 1 (rows * segments) */
-    uint32_t segs[2];         /* segments per row */
+    uint32_t tasks[2];        /* warp tasks per frame of part 0 / part 1 */
+    uint32_t segs[2];         /* segments per row (rows longer than ROWS_SEG) */
+    uint32_t rpt[2];          /* rows per task (short rows: several rows share one warp task; 1 when segs > 1) */
+    uint32_t rstride[2];      /* shared-memory stride of a staged row, surface bytes (multiple of 16; 32 for chroma pairs) */
+    FastDiv cdiv[2];          /* division by rstride / 16 */
     uint32_t total_tasks;
     Part part[2];
 };
 
-/* smem[0..nbytes) -> dst (any alignment) */
+/* words ws..ws+4 of the eight words of two consecutive 16-byte chunks (ws warp-uniform), funnel-shifted by sh bits */
+__device__ __forceinline__ uint4 shift_pair(const uint4 &P, const uint4 &Q, uint32_t ws, uint32_t sh)
+{
+    uint32_t x0, x1, x2, x3, x4;
+    switch (ws) {
+    case 0: x0 = P.x; x1 = P.y; x2 = P.z; x3 = P.w; x4 = Q.x; break;
+    case 1: x0 = P.y; x1 = P.z; x2 = P.w; x3 = Q.x; x4 = Q.y; break;
+    case 2: x0 = P.z; x1 = P.w; x2 = Q.x; x3 = Q.y; x4 = Q.z; break;
+    default: x0 = P.w; x1 = Q.x; x2 = Q.y; x3 = Q.z; x4 = Q.w; break;
+    }
+    uint4 o;
+    o.x = __funnelshift_r(x0, x1, sh); o.y = __funnelshift_r(x1, x2, sh);
+    o.z = __funnelshift_r(x2, x3, sh); o.w = __funnelshift_r(x3, x4, sh);
+    return o;
+}
+
+/* smem[0..nbytes) -> dst (any alignment).  sm is 16-byte aligned and readable up to the next multiple of 16
+ * past nbytes + 16 (the staging buffers carry 32 spare bytes).  Shared memory is read as whole 16-byte
+ * chunks (conflict-free LDS.128), never as strided words. */
 __device__ __forceinline__ void warp_store_shifted(uint8_t *dst, const uint8_t *sm, uint32_t nbytes, uint32_t lane)
 {
     const uint32_t head = min(nbytes, (16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u);
     const uint32_t body = (nbytes - head) & ~15u;
     if (lane < head) dst[lane] = sm[lane];
-    const uint32_t sh = 8 * (head & 3);
-    const uint32_t *w32 = (const uint32_t *)sm + (head >> 2);
-    for (uint32_t j = lane; j < body / 16; j += 32) {
-        const uint32_t *q = w32 + 4 * j;
-        const uint32_t a = q[0], b = q[1], c = q[2], d = q[3], e = q[4];
-        uint4 o;
-        o.x = __funnelshift_r(a, b, sh); o.y = __funnelshift_r(b, c, sh);
-        o.z = __funnelshift_r(c, d, sh); o.w = __funnelshift_r(d, e, sh);
-        *(uint4 *)(dst + head + 16 * (size_t)j) = o;
+    const uint32_t sh = 8 * (head & 3), ws = head >> 2;
+    const uint4 *s16 = (const uint4 *)sm;
+    if (head == 0) {
+        for (uint32_t j = lane; j < body / 16; j += 32) *(uint4 *)(dst + 16 * (size_t)j) = s16[j];
+    } else {
+        for (uint32_t j = lane; j < body / 16; j += 32) {
+            const uint4 P = s16[j], Q = s16[j + 1];
+            *(uint4 *)(dst + head + 16 * (size_t)j) = shift_pair(P, Q, ws, sh);
+        }
     }
     const uint32_t t0 = head + body;
     if (lane < nbytes - t0) dst[t0 + lane] = sm[t0 + lane];
 }
 
-/* src (any alignment) -> smem[0..nbytes); never reads outside [src, src + nbytes) */
+/* src (any alignment) -> smem[0..nbytes), nbytes <= 512*K.  Global memory is read as ALIGNED 16-byte
+ * chunks, one load per lane and chunk, ALL issued before the first use; the neighbour chunk each output
+ * needs comes from the next lane by shuffle (lane 31 takes lane 0's next chunk).  The first aligned chunk
+ * starts up to 15 bytes before src: that is the end of the previous row / plane / frame, or - for the
+ * first byte of a buffer - still inside the allocation (device allocations are at least 256-byte
+ * aligned); nothing is ever read past src + nbytes. */
+template <int K> struct ShiftedLoad {
+    uint4 P[K + 1];
+    uint32_t s, nfull, nout, t0, t1;
+
+    /* phase 1: every global load of the row */
+    __device__ __forceinline__ void issue(const uint8_t *src, uint32_t nbytes, uint32_t lane)
+    {
+        s = (uint32_t)(uintptr_t)src & 15u;
+        const uint8_t *al = src - s;
+        nfull = (nbytes + s) / 16;                           /* aligned chunks 0..nfull-1 end at or before src + nbytes */
+        nout = s ? (nfull ? nfull - 1 : 0) : nfull;          /* output chunk j = bytes s.. of aligned chunks (j, j+1) */
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const uint32_t j = k * 32 + lane;
+            P[k] = make_uint4(0, 0, 0, 0);
+            if (j < nfull) P[k] = __ldg((const uint4 *)(al + 16 * (size_t)j));
+        }
+        P[K] = make_uint4(0, 0, 0, 0);
+        const uint32_t i0 = nout * 16 + lane, i1 = i0 + 32;  /* the < 48 bytes after the last full output chunk */
+        t0 = t1 = 0;
+        if (i0 < nbytes) t0 = __ldg(src + i0);
+        if (i1 < nbytes) t1 = __ldg(src + i1);
+    }
+    /* phase 2: re-align and store to shared memory */
+    __device__ __forceinline__ void commit(uint8_t *sm, uint32_t nbytes, uint32_t lane) const
+    {
+        if (s == 0) {
+#pragma unroll
+            for (int k = 0; k < K; k++) { const uint32_t j = k * 32 + lane; if (j < nout) *(uint4 *)(sm + 16 * j) = P[k]; }
+        } else {
+            const uint32_t sh = 8 * (s & 3), ws = s >> 2, nxt = (lane + 1) & 31;
+#pragma unroll
+            for (int k = 0; k < K; k++) {
+                if (k * 32 >= (int)nout) break;              /* warp-uniform */
+                const uint32_t j = k * 32 + lane;
+                const uint4 R = lane == 0 ? P[k + 1] : P[k]; /* lane l reads lane l+1's chunk j+1; lane 31 reads lane 0's next one */
+                uint4 Q;
+                Q.x = __shfl_sync(0xffffffffu, R.x, nxt); Q.y = __shfl_sync(0xffffffffu, R.y, nxt);
+                Q.z = __shfl_sync(0xffffffffu, R.z, nxt); Q.w = __shfl_sync(0xffffffffu, R.w, nxt);
+                if (j < nout) *(uint4 *)(sm + 16 * j) = shift_pair(P[k], Q, ws, sh);
+            }
+        }
+        const uint32_t i0 = nout * 16 + lane, i1 = i0 + 32;
+        if (i0 < nbytes) sm[i0] = (uint8_t)t0;
+        if (i1 < nbytes) sm[i1] = (uint8_t)t1;
+    }
+};
+
+template <int K>
 __device__ __forceinline__ void warp_load_shifted(uint8_t *sm, const uint8_t *src, uint32_t nbytes, uint32_t lane)
 {
-    const uint32_t s = (uint32_t)(uintptr_t)src & 15u;
-    const uint32_t nchunks = nbytes / 16;                       /* full 16-byte chunks of smem */
-    if (s == 0) {
-        for (uint32_t j = lane; j < nchunks; j += 32) *(uint4 *)(sm + 16 * j) = __ldg((const uint4 *)(src + 16 * (size_t)j));
-    } else {
-        /* smem chunk j = src[16j, 16j+16) = bytes s.. of the aligned pair (A, A+16), A = src - s + 16j.
-         * j = 0 would read s bytes before src, the last chunk 16-s bytes after the end: those two go bytewise. */
-        const uint8_t *al = src - s;
-        const uint32_t sh = 8 * (s & 3), ws = s >> 2;
-        for (uint32_t j = lane; j < nchunks; j += 32) {
-            if (j == 0 || 16 * j + 32 > nbytes + s) continue;    /* handled below */
-            const uint4 A = __ldg((const uint4 *)(al + 16 * (size_t)j)), B = __ldg((const uint4 *)(al + 16 * (size_t)j + 16));
-            const uint32_t v[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
-            uint32_t x0, x1, x2, x3, x4;
-            switch (ws) {                                        /* warp-uniform */
-            case 0: x0 = v[0]; x1 = v[1]; x2 = v[2]; x3 = v[3]; x4 = v[4]; break;
-            case 1: x0 = v[1]; x1 = v[2]; x2 = v[3]; x3 = v[4]; x4 = v[5]; break;
-            case 2: x0 = v[2]; x1 = v[3]; x2 = v[4]; x3 = v[5]; x4 = v[6]; break;
-            default: x0 = v[3]; x1 = v[4]; x2 = v[5]; x3 = v[6]; x4 = v[7]; break;
-            }
-            uint4 o;
-            o.x = __funnelshift_r(x0, x1, sh); o.y = __funnelshift_r(x1, x2, sh);
-            o.z = __funnelshift_r(x2, x3, sh); o.w = __funnelshift_r(x3, x4, sh);
-            *(uint4 *)(sm + 16 * j) = o;
-        }
-        /* first chunk and the (at most two) last chunks whose aligned pair would cross the end */
-        if (lane < 16 && nchunks > 0) sm[lane] = src[lane];
-        const uint32_t jf = nbytes + s >= 32 ? (nbytes + s - 32) / 16 + 1 : 1;
-        for (uint32_t j = max(jf, 1u); j < nchunks; j++)
-            if (lane < 16) sm[16 * j + lane] = src[16 * (size_t)j + lane];
-    }
-    const uint32_t t0 = nchunks * 16;
-    if (lane < nbytes - t0) sm[t0 + lane] = src[t0 + lane];
+    ShiftedLoad<K> l;
+    l.issue(src, nbytes, lane);
+    l.commit(sm, nbytes, lane);
 }
 
-template <bool TO_TIGHT, int KIND1>
-__global__ void __launch_bounds__(ROWS_THREADS, 8) rows_kernel(const __grid_constant__ RowsParams p)
+template <bool TO_TIGHT, int KIND1, bool MULTI>
+__global__ void __launch_bounds__(ROWS_THREADS, TO_TIGHT ? JMC_ROWS_MINB_DEC : JMC_ROWS_MINB_ENC) rows_kernel(const __grid_constant__ RowsParams p)
 {
     constexpr int WARPS = ROWS_THREADS / 32;
     __shared__ __align__(16) uint8_t sA[WARPS][ROWS_SMEM_A];
@@ -632,10 +686,26 @@ __global__ void __launch_bounds__(ROWS_THREADS, 8) rows_kernel(const __grid_cons
     if (second) r -= p.tasks[0];
     const Part &pt = second ? p.part[1] : p.part[0];
     const uint32_t segs = second ? p.segs[1] : p.segs[0];
-    const uint32_t row = r / segs, seg = r - row * segs;
+    /* MULTI: at least one part packs several rows into a task; otherwise the row arithmetic folds away */
+    const uint32_t rpt = MULTI ? (second ? p.rpt[1] : p.rpt[0]) : 1u;
+    const uint32_t rs = MULTI ? (second ? p.rstride[1] : p.rstride[0]) : (uint32_t)ROWS_SEG;
+    const FastDiv &cdiv = second ? p.cdiv[1] : p.cdiv[0];
+    /* a task is either one 2 KB segment of one row (segs >= 1, rpt == 1) or rpt whole rows (segs == 1) */
+    uint32_t row, seg;
+    if (rpt > 1) { row = r * rpt; seg = 0; } else { row = r / segs; seg = r - row * segs; }
+    const uint32_t nr = min(rpt, pt.rows - row);
+    const size_t pitch = (size_t)(uint32_t)pt.p_pitch;
     uint8_t *A = sA[wib], *B = sB[wib], *Cc = sC[wib];
-    uint8_t *prow = frame_ptr(p.pitched, f) + pt.p_off + (size_t)row * (uint32_t)pt.p_pitch + (size_t)seg * ROWS_SEG;
+    uint8_t *prow = frame_ptr(p.pitched, f) + pt.p_off + (size_t)row * pitch + (size_t)seg * ROWS_SEG;
     uint8_t *tp = frame_ptr(p.tight, f);
+    /* surface side: slot s = 16 bytes at offset cc of staged row ri; shared-memory address A + 16 s */
+    uint32_t ri[4], cc[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t s = k * 32 + lane;
+        ri[k] = MULTI ? fast_div(s, cdiv) : 0u;
+        cc[k] = 16 * s - ri[k] * rs;
+    }
 
     if (!second || KIND1 == PART_COPY) {
         const uint32_t nbytes = min((uint32_t)ROWS_SEG, pt.row_elems - seg * ROWS_SEG);
@@ -643,37 +713,42 @@ __global__ void __launch_bounds__(ROWS_THREADS, 8) rows_kernel(const __grid_cons
         if (TO_TIGHT) {
             uint4 v[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { const uint32_t c = (k * 32 + lane) * 16; if (c < nbytes) v[k] = ld16<1>(prow + c); }
+            for (int k = 0; k < 4; k++) if (ri[k] < nr && cc[k] < nbytes) v[k] = ld16<1>(prow + ri[k] * pitch + cc[k]);
 #pragma unroll
-            for (int k = 0; k < 4; k++) { const uint32_t c = (k * 32 + lane) * 16; if (c < nbytes) *(uint4 *)(A + c) = v[k]; }
+            for (int k = 0; k < 4; k++) if (ri[k] < nr && cc[k] < nbytes) *(uint4 *)(A + 16 * (k * 32 + lane)) = v[k];
             __syncwarp();
-            warp_store_shifted(trow, A, nbytes, lane);
+            for (uint32_t i = 0; i < nr; i++) warp_store_shifted(trow + (size_t)i * pt.row_elems, A + i * rs, nbytes, lane);
         } else {
-            warp_load_shifted(A, trow, nbytes, lane);
+            for (uint32_t i = 0; i < nr; i++) warp_load_shifted<4>(A + i * rs, trow + (size_t)i * pt.row_elems, nbytes, lane);
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t c = (k * 32 + lane) * 16;
-                if (c + 16 <= nbytes) *(uint4 *)(prow + c) = *(const uint4 *)(A + c);
-                else if (c < nbytes) { const uint4 t = *(const uint4 *)(A + c); const uint32_t wd[4] = {t.x, t.y, t.z, t.w}; store_prefix<4>(prow + c, wd, nbytes - c); }
+                if (ri[k] >= nr) continue;
+                uint8_t *d = prow + ri[k] * pitch + cc[k];
+                const uint8_t *sm = A + 16 * (k * 32 + lane);
+                if (cc[k] + 16 <= nbytes) *(uint4 *)d = *(const uint4 *)sm;
+                else if (cc[k] < nbytes) { const uint4 t = *(const uint4 *)sm; const uint32_t wd[4] = {t.x, t.y, t.z, t.w}; store_prefix<4>(d, wd, nbytes - cc[k]); }
             }
         }
     } else {
-        /* chroma: elements are pairs; a segment is ROWS_SEG interleaved bytes = ROWS_SEG/2 pairs */
+        /* chroma: elements are pairs; a segment is ROWS_SEG interleaved bytes = ROWS_SEG/2 pairs; staged rows
+         * are rs interleaved bytes apart in A (rs a multiple of 32) and rs/2 apart in B (U) and Cc (V) */
         const uint32_t npairs = min((uint32_t)ROWS_SEG / 2, pt.row_elems - seg * (ROWS_SEG / 2));
+        const uint32_t nbytes = 2 * npairs;
+        const uint32_t span = rpt > 1 ? nr * rs : nbytes;                  /* staged interleaved bytes of the task */
         uint8_t *tu = tp + pt.a_off + (size_t)row * pt.row_elems + (size_t)seg * (ROWS_SEG / 2);
         uint8_t *tv = tp + pt.b_off + (size_t)row * pt.row_elems + (size_t)seg * (ROWS_SEG / 2);
         if (KIND1 == PART_SPLIT) {
             uint4 v[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) { const uint32_t c = (k * 32 + lane) * 16; if (c < 2 * npairs) v[k] = ld16<1>(prow + c); }
+            for (int k = 0; k < 4; k++) if (ri[k] < nr && cc[k] < nbytes) v[k] = ld16<1>(prow + ri[k] * pitch + cc[k]);
 #pragma unroll
-            for (int k = 0; k < 4; k++) { const uint32_t c = (k * 32 + lane) * 16; if (c < 2 * npairs) *(uint4 *)(A + c) = v[k]; }
+            for (int k = 0; k < 4; k++) if (ri[k] < nr && cc[k] < nbytes) *(uint4 *)(A + 16 * (k * 32 + lane)) = v[k];
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const uint32_t c = k * 32 + lane;                          /* 32-byte chunk -> 16 U + 16 V */
-                if (32 * c < 2 * npairs) {
+                if (32 * c < span) {
                     const uint4 a = *(const uint4 *)(A + 32 * c), b = *(const uint4 *)(A + 32 * c + 16);
                     uint4 u, w;
                     u.x = __byte_perm(a.x, a.y, 0x6420); w.x = __byte_perm(a.x, a.y, 0x7531);
@@ -685,16 +760,23 @@ __global__ void __launch_bounds__(ROWS_THREADS, 8) rows_kernel(const __grid_cons
                 }
             }
             __syncwarp();
-            warp_store_shifted(tu, B, npairs, lane);
-            warp_store_shifted(tv, Cc, npairs, lane);
+            for (uint32_t i = 0; i < nr; i++) {
+                warp_store_shifted(tu + (size_t)i * pt.row_elems, B + i * (rs / 2), npairs, lane);
+                warp_store_shifted(tv + (size_t)i * pt.row_elems, Cc + i * (rs / 2), npairs, lane);
+            }
         } else {
-            warp_load_shifted(B, tu, npairs, lane);
-            warp_load_shifted(Cc, tv, npairs, lane);
+            for (uint32_t i = 0; i < nr; i++) {
+                ShiftedLoad<2> lu, lv;                                      /* U and V loads in flight together */
+                lu.issue(tu + (size_t)i * pt.row_elems, npairs, lane);
+                lv.issue(tv + (size_t)i * pt.row_elems, npairs, lane);
+                lu.commit(B + i * (rs / 2), npairs, lane);
+                lv.commit(Cc + i * (rs / 2), npairs, lane);
+            }
             __syncwarp();
 #pragma unroll
             for (int k = 0; k < 2; k++) {
                 const uint32_t c = k * 32 + lane;
-                if (16 * c < npairs) {
+                if (32 * c < span) {
                     const uint4 u = *(const uint4 *)(B + 16 * c), w = *(const uint4 *)(Cc + 16 * c);
                     uint4 a, b;
                     a.x = __byte_perm(u.x, w.x, 0x5140); a.y = __byte_perm(u.x, w.x, 0x7362);
@@ -706,12 +788,13 @@ __global__ void __launch_bounds__(ROWS_THREADS, 8) rows_kernel(const __grid_cons
                 }
             }
             __syncwarp();
-            const uint32_t nbytes = 2 * npairs;
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t c = (k * 32 + lane) * 16;
-                if (c + 16 <= nbytes) *(uint4 *)(prow + c) = *(const uint4 *)(A + c);
-                else if (c < nbytes) { const uint4 t = *(const uint4 *)(A + c); const uint32_t wd[4] = {t.x, t.y, t.z, t.w}; store_prefix<4>(prow + c, wd, nbytes - c); }
+                if (ri[k] >= nr) continue;
+                uint8_t *d = prow + ri[k] * pitch + cc[k];
+                const uint8_t *sm = A + 16 * (k * 32 + lane);
+                if (cc[k] + 16 <= nbytes) *(uint4 *)d = *(const uint4 *)sm;
+                else if (cc[k] < nbytes) { const uint4 t = *(const uint4 *)sm; const uint32_t wd[4] = {t.x, t.y, t.z, t.w}; store_prefix<4>(d, wd, nbytes - cc[k]); }
             }
         }
     }

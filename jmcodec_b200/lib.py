@@ -13,7 +13,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libjmcodec_b200.so")
+_SO = os.environ.get("JMCODEC_B200_LIB") or os.path.join(_HERE, "libjmcodec_b200.so")   # override: developer A/B builds
 _lib = None
 
 

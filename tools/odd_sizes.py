@@ -9,9 +9,13 @@ for name, spec in {
     "1366x768 p1536": ("i420", 1366, 768, 1536, 300), "854x480 p1024": ("i420", 854, 480, 1024, 600),
     "1918x1078 p2048": ("i420", 1918, 1078, 2048, 300), "1919x1079 p2048": ("i420", 1919, 1079, 2048, 300),
     "720x480 p768": ("i420", 720, 480, 768, 800), "1280x720 p1280": ("i420", 1280, 720, 1280, 600),
-    "pack 1080x1920 p1088": ("pack", 1080, 1920, 1088, 150), "rgb 1080x1920 p1088": ("rgb", 1080, 1920, 1088, 150),
+    "pack 1080x1920 p1088": ("pack", 1080, 1920, 1088, 150), "pack 1366x768 p1536": ("pack", 1366, 768, 1536, 300),
+    "pack 854x480 p1024": ("pack", 854, 480, 1024, 600), "pack 1919x1079 p2048": ("pack", 1919, 1079, 2048, 300),
+    "nv12 1366x768 p1536": ("nv12", 1366, 768, 1536, 300), "rgb 1080x1920 p1088": ("rgb", 1080, 1920, 1088, 150),
     "rgb 1366x768 p1536": ("rgb", 1366, 768, 1536, 300),
 }.items():
+    if len(sys.argv) > 1 and not any(a in name for a in sys.argv[1:]):
+        continue
     bench.WORKLOADS["_x"] = spec
     r = bench.device_only(ctx, "_x", 0, 10, 3)
     print(f"{name:28s} {r['frames_per_s']:12.0f} fps {r['gbs']:8.1f} GB/s  {r['gbs']/peak:.3f} of peak")
