@@ -585,26 +585,33 @@ __device__ __forceinline__ uint4 shift_pair(const uint4 &P, const uint4 &Q, uint
     return o;
 }
 
-/* smem[0..nbytes) -> dst (any alignment).  sm is 16-byte aligned and readable up to the next multiple of 16
- * past nbytes + 16 (the staging buffers carry 32 spare bytes).  Shared memory is read as whole 16-byte
- * chunks (conflict-free LDS.128), never as strided words. */
-__device__ __forceinline__ void warp_store_shifted(uint8_t *dst, const uint8_t *sm, uint32_t nbytes, uint32_t lane)
+/* A staged buffer of nbytes -> dst (any alignment).  chunk(c) returns the shared-memory address of the
+ * buffer's 16-byte chunk c (16-byte aligned; chunks up to nbytes/16 + 1 must be readable - the staging
+ * buffers carry spare bytes).  Shared memory is read as whole chunks (conflict-free LDS.128), never as
+ * strided words; global memory gets 16-byte stores on the aligned body, bytes on the < 16-byte head/tail. */
+template <class ChunkMap>
+__device__ __forceinline__ void warp_store_shifted_map(uint8_t *dst, ChunkMap chunk, uint32_t nbytes, uint32_t lane)
 {
     const uint32_t head = min(nbytes, (16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u);
     const uint32_t body = (nbytes - head) & ~15u;
-    if (lane < head) dst[lane] = sm[lane];
+    if (lane < head) dst[lane] = ((const uint8_t *)chunk(0))[lane];
     const uint32_t sh = 8 * (head & 3), ws = head >> 2;
-    const uint4 *s16 = (const uint4 *)sm;
     if (head == 0) {
-        for (uint32_t j = lane; j < body / 16; j += 32) *(uint4 *)(dst + 16 * (size_t)j) = s16[j];
+        for (uint32_t j = lane; j < body / 16; j += 32) *(uint4 *)(dst + 16 * (size_t)j) = *chunk(j);
     } else {
         for (uint32_t j = lane; j < body / 16; j += 32) {
-            const uint4 P = s16[j], Q = s16[j + 1];
+            const uint4 P = *chunk(j), Q = *chunk(j + 1);
             *(uint4 *)(dst + head + 16 * (size_t)j) = shift_pair(P, Q, ws, sh);
         }
     }
-    const uint32_t t0 = head + body;
-    if (lane < nbytes - t0) dst[t0 + lane] = sm[t0 + lane];
+    const uint32_t t = head + body + lane;
+    if (t < nbytes) dst[t] = ((const uint8_t *)chunk(t >> 4))[t & 15];
+}
+
+/* contiguous staging buffer sm[0..nbytes), 16-byte aligned, readable 32 bytes past nbytes */
+__device__ __forceinline__ void warp_store_shifted(uint8_t *dst, const uint8_t *sm, uint32_t nbytes, uint32_t lane)
+{
+    warp_store_shifted_map(dst, [sm](uint32_t c) { return (const uint4 *)sm + c; }, nbytes, lane);
 }
 
 /* src (any alignment) -> smem[0..nbytes), nbytes <= 512*K.  Global memory is read as ALIGNED 16-byte
@@ -983,11 +990,8 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
                             const uint32_t c = k * 32 + lane;                     /* 16-byte chunk: lane c/4, part c%4 */
                             if (16 * c < nb) st16<C::STP>(g + 16 * c, *(const uint4 *)(st + (c >> 2) * 80 + (c & 3) * 16));
                         }
-                    } else if (((uint32_t)(uintptr_t)g & 3) == 0) {
-                        for (uint32_t c = lane; 4 * c < nb; c += 32)
-                            *(uint32_t *)(g + 4 * c) = *(const uint32_t *)(st + (c >> 4) * 80 + (c & 15) * 4);
-                    } else {
-                        for (uint32_t c = lane; c < nb; c += 32) g[c] = st[(c >> 6) * 80 + (c & 63)];
+                    } else {                                                      /* 8-byte aligned rows (w % 4 == 2) or any other pitch */
+                        warp_store_shifted_map(g, [st](uint32_t c) { return (const uint4 *)(st + (c >> 2) * 80 + (c & 3) * 16); }, nb, lane);
                     }
                     continue;
                 }
@@ -1003,13 +1007,12 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
                 __syncwarp();
                 uint8_t *g = orow + (size_t)row * p.rgb_pitch + (size_t)seg * (32 * 48);
                 const uint32_t nbytes = 3 * seg_px;                               /* a multiple of 6 */
-                switch (vec_width((uint64_t)(uintptr_t)g | nbytes)) {
-                case 16: warp_flush<16, C::STP>(g, st, nbytes, lane); break;
-                case 8:  warp_flush<8, C::STP>(g, st, nbytes, lane); break;
-                case 4:  warp_flush<4, C::STP>(g, st, nbytes, lane); break;
-                case 2:  warp_flush<2, C::STP>(g, st, nbytes, lane); break;
-                default: warp_flush<1, C::STP>(g, st, nbytes, lane); break;
-                }
+                /* aligned rows: straight 16-byte stores; any other alignment (1080- or 1366-wide video): 16-byte
+                 * stores to the aligned body, re-aligned from shared memory by a funnel shift */
+                const uint32_t gb = (uint32_t)(uintptr_t)g | nbytes;
+                if ((gb & 15) == 0) warp_flush<16, C::STP>(g, st, nbytes, lane);
+                else if ((gb & 7) == 0) warp_flush<8, C::STP>(g, st, nbytes, lane);      /* 1080-wide: measured 0.76 vs 0.74 shifted */
+                else warp_store_shifted(g, st, nbytes, lane);
             }
         } else {
             /* odd widths, unaligned or too-tight surfaces: one pixel per lane per step, byte accesses */
