@@ -946,15 +946,41 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
                 uv = ld16<C::LDP>(crow + px0);
                 if (two) yb = ld16<C::LDP>(yrow + p.pitch + px0);
             }
-            if (p.fused && npx) {
-                const uint32_t y_a[4] = {ya.x, ya.y, ya.z, ya.w}, y_b[4] = {yb.x, yb.y, yb.z, yb.w};
-                store_prefix<4>(tp + (size_t)y0 * w + px0, y_a, npx);
-                if (two) store_prefix<4>(tp + (size_t)(y0 + 1) * w + px0, y_b, npx);
-                if (rp < (uint32_t)ch) {
-                    const uint32_t u[2] = {__byte_perm(uv.x, uv.y, 0x6420), __byte_perm(uv.z, uv.w, 0x6420)};
-                    const uint32_t v[2] = {__byte_perm(uv.x, uv.y, 0x7531), __byte_perm(uv.z, uv.w, 0x7531)};
-                    store_prefix<2>(tp + p.u_off + (size_t)rp * cw + (px0 >> 1), u, npx >> 1);
-                    store_prefix<2>(tp + p.v_off + (size_t)rp * cw + (px0 >> 1), v, npx >> 1);
+            uint8_t *st = stage[wib];
+            if (p.fused) {
+                uint8_t *ty = tp + (size_t)y0 * w + seg * 512;
+                uint8_t *tu = tp + p.u_off + (size_t)rp * cw + seg * 256, *tv = tp + p.v_off + (size_t)rp * cw + seg * 256;
+                const uint32_t u[2] = {__byte_perm(uv.x, uv.y, 0x6420), __byte_perm(uv.z, uv.w, 0x6420)};
+                const uint32_t v[2] = {__byte_perm(uv.x, uv.y, 0x7531), __byte_perm(uv.z, uv.w, 0x7531)};
+                const uint64_t tbits = (uint64_t)(uintptr_t)ty | (uint64_t)(uintptr_t)tu | (uint64_t)(uintptr_t)tv | (uint32_t)w | (uint32_t)cw;
+                if ((tbits & 7) == 0) {                                   /* every lane's 16 luma / 8 chroma bytes land aligned */
+                    if (npx) {
+                        const uint32_t y_a[4] = {ya.x, ya.y, ya.z, ya.w}, y_b[4] = {yb.x, yb.y, yb.z, yb.w};
+                        store_prefix<4>(ty + 16 * lane, y_a, npx);
+                        if (two) store_prefix<4>(ty + w + 16 * lane, y_b, npx);
+                        if (rp < (uint32_t)ch) { store_prefix<2>(tu + 8 * lane, u, npx >> 1); store_prefix<2>(tv + 8 * lane, v, npx >> 1); }
+                    }
+                } else {
+                    /* tight rows on odd addresses (1366-wide, ...): stage each row in the spare 960 bytes behind the
+                     * RGB staging area and write it with 16-byte stores re-aligned by a funnel shift */
+                    uint8_t *sy = st + 1600, *sv = st + 1600 + 288;
+                    *(uint4 *)(sy + 16 * lane) = ya;
+                    __syncwarp();
+                    warp_store_shifted(ty, sy, seg_px, lane);
+                    __syncwarp();
+                    if (two) {
+                        *(uint4 *)(sy + 16 * lane) = yb;
+                        __syncwarp();
+                        warp_store_shifted(ty + w, sy, seg_px, lane);
+                        __syncwarp();
+                    }
+                    if (rp < (uint32_t)ch) {
+                        *(uint2 *)(sy + 8 * lane) = make_uint2(u[0], u[1]);
+                        *(uint2 *)(sv + 8 * lane) = make_uint2(v[0], v[1]);
+                        __syncwarp();
+                        warp_store_shifted(tu, sy, seg_px >> 1, lane);
+                        warp_store_shifted(tv, sv, seg_px >> 1, lane);
+                    }
                 }
             }
             /* chroma terms of the 8 pairs this thread owns */
@@ -966,13 +992,12 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
                 cg[2 * j] = dp2a_lo(COEF_GUV, uvw[j], RGB_CG); cg[2 * j + 1] = dp2a_hi(COEF_GUV, uvw[j], RGB_CG);
                 cb[2 * j] = dp2a_lo(COEF_BU, uvw[j], RGB_CB);  cb[2 * j + 1] = dp2a_hi(COEF_BU, uvw[j], RGB_CB);
             }
-            uint8_t *st = stage[wib];
 #pragma unroll
             for (int row = 0; row < 2; row++) {
                 if (row == 1 && !two) break;
                 const uint4 yy = row ? yb : ya;
                 const uint32_t yw[4] = {yy.x, yy.y, yy.z, yy.w};
-                if (ARGB) {
+                if constexpr (ARGB) {
                     __syncwarp();
                     uint4 *s4 = (uint4 *)(st + lane * 80);                        /* 80-byte stride: conflict-free 16-byte stores */
 #pragma unroll
@@ -993,26 +1018,26 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
                     } else {                                                      /* 8-byte aligned rows (w % 4 == 2) or any other pitch */
                         warp_store_shifted_map(g, [st](uint32_t c) { return (const uint4 *)(st + (c >> 2) * 80 + (c & 3) * 16); }, nb, lane);
                     }
-                    continue;
-                }
-                uint32_t o[12];
+                } else {
+                    uint32_t o[12];
 #pragma unroll
-                for (int j = 0; j < 4; j++)
-                    rgb4(yw[j], cr[2 * j], cg[2 * j], cb[2 * j], cr[2 * j + 1], cg[2 * j + 1], cb[2 * j + 1], o + 3 * j);
-                __syncwarp();
-                uint4 *s4 = (uint4 *)(st + lane * 48);
-                s4[0] = make_uint4(o[0], o[1], o[2], o[3]);
-                s4[1] = make_uint4(o[4], o[5], o[6], o[7]);
-                s4[2] = make_uint4(o[8], o[9], o[10], o[11]);
-                __syncwarp();
-                uint8_t *g = orow + (size_t)row * p.rgb_pitch + (size_t)seg * (32 * 48);
-                const uint32_t nbytes = 3 * seg_px;                               /* a multiple of 6 */
-                /* aligned rows: straight 16-byte stores; any other alignment (1080- or 1366-wide video): 16-byte
-                 * stores to the aligned body, re-aligned from shared memory by a funnel shift */
-                const uint32_t gb = (uint32_t)(uintptr_t)g | nbytes;
-                if ((gb & 15) == 0) warp_flush<16, C::STP>(g, st, nbytes, lane);
-                else if ((gb & 7) == 0) warp_flush<8, C::STP>(g, st, nbytes, lane);      /* 1080-wide: measured 0.76 vs 0.74 shifted */
-                else warp_store_shifted(g, st, nbytes, lane);
+                    for (int j = 0; j < 4; j++)
+                        rgb4(yw[j], cr[2 * j], cg[2 * j], cb[2 * j], cr[2 * j + 1], cg[2 * j + 1], cb[2 * j + 1], o + 3 * j);
+                    __syncwarp();
+                    uint4 *s4 = (uint4 *)(st + lane * 48);
+                    s4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+                    s4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+                    s4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+                    __syncwarp();
+                    uint8_t *g = orow + (size_t)row * p.rgb_pitch + (size_t)seg * (32 * 48);
+                    const uint32_t nbytes = 3 * seg_px;                               /* a multiple of 6 */
+                    /* aligned rows: straight 16-byte stores; any other alignment (1080- or 1366-wide video): 16-byte
+                     * stores to the aligned body, re-aligned from shared memory by a funnel shift */
+                    const uint32_t gb = (uint32_t)(uintptr_t)g | nbytes;
+                    if ((gb & 15) == 0) warp_flush<16, C::STP>(g, st, nbytes, lane);
+                    else if ((gb & 7) == 0) warp_flush<8, C::STP>(g, st, nbytes, lane);      /* 1080-wide: measured 0.82 vs 0.74 shifted */
+                    else warp_store_shifted(g, st, nbytes, lane);
+                }
             }
         } else {
             /* odd widths, unaligned or too-tight surfaces: one pixel per lane per step, byte accesses */
