@@ -334,6 +334,36 @@ def dropin_api_fps(J, ctx, device, w=1920, h=1080, pitch=2048, frames=200):
     res["device_surface_pinned_out_fps"] = round(frames * 5 / (time.perf_counter() - t0), 1)
     dec.free_host(pinned)
     dec.deinit()
+    # (c) the reference's scaling model: one handle per stream, one host thread per handle
+    import threading
+    nthr = 4
+    decs = []
+    for _ in range(nthr):
+        d = J.NvDec(device)
+        d.init(J.NvDec.CODEC_RAW_NV12, 1)
+        decs.append((d, d.alloc_host(need)))
+    start, counts = threading.Barrier(nthr + 1), [0] * nthr
+
+    def stream(i):
+        d, buf = decs[i]
+        for k in range(10):
+            d.decode_frame(dpk[k % 4]); d.output_frame(buf, need)
+        start.wait()
+        for k in range(frames * 2):
+            d.decode_frame(dpk[(k + i) % 4]); d.output_frame(buf, need)
+        counts[i] = frames * 2
+
+    thr = [threading.Thread(target=stream, args=(i,)) for i in range(nthr)]
+    for t in thr:
+        t.start()
+    start.wait()
+    t0 = time.perf_counter()
+    for t in thr:
+        t.join()
+    res["device_surface_pinned_out_4_handles_fps"] = round(sum(counts) / (time.perf_counter() - t0), 1)
+    for d, buf in decs:
+        d.free_host(buf)
+        d.deinit()
     for d in dptrs:
         ctx.free(d)
     return res

@@ -183,6 +183,65 @@ static int launch_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, in
     return JMC_OK;
 }
 
+/* The same geometries through the bulk-copy engine (bulk_rows_kernel / bulk_rows_pack_kernel).  Same
+ * preconditions as launch_rows(); returns 1 when they do not hold or the tile does not fit. */
+static int launch_bulk_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, int k1, cudaStream_t stream)
+{
+    if (j->surf.list) { if (!(j->flags & JMC_JOB_ALIGNED16)) return 1; }
+    else if (((uint64_t)(uintptr_t)j->surf.base | (uint64_t)j->surf.stride) & 15) return 1;
+    BulkRowsParams b;
+    b.pitched = pp.pitched;
+    b.tight = pp.tight;
+    b.n_frames = pp.n_frames;
+    uint32_t per_row = 0, widest = 16;                 /* shared memory per staged row (worst part); surface bytes per row */
+    for (int i = 0; i < 2; i++) {
+        const Part &pt = pp.part[i];
+        b.part[i] = pt;
+        b.rstride[i] = b.ldbytes[i] = 16;
+        if (pt.kind == PART_NONE) continue;
+        const uint32_t row_bytes = pt.kind == PART_COPY ? pt.row_elems : 2 * pt.row_elems;
+        if (((uint64_t)pt.p_off | (uint32_t)pt.p_pitch) & 15) return 1;
+        b.ldbytes[i] = (row_bytes + 15) & ~15u;
+        if ((uint32_t)pt.p_pitch < b.ldbytes[i]) return 1;
+        b.rstride[i] = pt.kind == PART_COPY ? b.ldbytes[i] : ((row_bytes + 31) & ~31u);
+        widest = std::max(widest, b.rstride[i]);
+        /* decode: the staged surface rows (+ the two planar halves of a chroma row); encode: the tight run(s) */
+        per_row = std::max(per_row, pp.to_tight ? (pt.kind == PART_COPY ? b.rstride[i] : 2 * b.rstride[i]) : row_bytes);
+    }
+    if (per_row == 0) return JMC_OK;
+    /* ~12 KB of surface data per tile, a multiple of the four warps that store the rows */
+    uint32_t rows = std::min<uint32_t>(32, std::max<uint32_t>(4, (12288 / widest) & ~3u));
+    const size_t slack = 192;                          /* spare chunks behind each staging area, run alignment */
+    while (rows > 1 && (size_t)rows * per_row + slack > 96 * 1024) rows >>= 1;
+    if ((size_t)rows * per_row + slack > 96 * 1024) return 1;
+    b.rows_per_tile = rows;
+    b.tiles[0] = pp.part[0].kind == PART_NONE ? 0 : (pp.part[0].rows + rows - 1) / rows;
+    b.tiles[1] = pp.part[1].kind == PART_NONE ? 0 : (pp.part[1].rows + rows - 1) / rows;
+    const uint64_t total = (uint64_t)(b.tiles[0] + b.tiles[1]) * b.n_frames;
+    if (total == 0) return JMC_OK;
+    if (total > 0x7fffffffull) return 1;
+    const size_t smem = (size_t)rows * per_row + slack;
+    const uint32_t grid = (uint32_t)total;
+#define JMC_BROWS(KERNEL)                                                                                         \
+    do {                                                                                                          \
+        static bool attr_done[64];                                                                                \
+        if (ctx->device < 64 && !attr_done[ctx->device]) {                                                        \
+            JMC_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));       \
+            attr_done[ctx->device] = true;                                                                        \
+        }                                                                                                         \
+        KERNEL<<<grid, BROWS_THREADS, smem, stream>>>(b);                                                         \
+    } while (0)
+    if (pp.to_tight) {
+        if (k1 == PART_SPLIT) JMC_BROWS(bulk_rows_kernel<PART_SPLIT>); else JMC_BROWS(bulk_rows_kernel<PART_COPY>);
+    } else {
+        if (k1 == PART_MERGE) JMC_BROWS(bulk_rows_pack_kernel<PART_MERGE>); else JMC_BROWS(bulk_rows_pack_kernel<PART_COPY>);
+    }
+#undef JMC_BROWS
+    JMC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return JMC_OK;
+}
+
 /* Can the host prove that every access of this job is 16-byte aligned?  (1080p, 4K, 720p ... are.) */
 static bool all_wide(const jmc_job *j, const PlaneParams &p)
 {
@@ -232,9 +291,16 @@ static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
         int r = launch_bulk(ctx, p, k1, stream);
         if (r != 1) return r;                        /* 1: geometry does not fit the bulk kernel, use LDG/STG */
     }
-    if (!wide && !getenv_flag("JMC_NO_ROWS") && (narrow_vectors(j, p) || getenv_flag("JMC_ROWS_ALWAYS"))) {
-        int r = launch_rows(ctx, j, p, k1, stream);
-        if (r != 1) return r;                        /* 1: surface side not 16-byte friendly, use the any-alignment kernel */
+    if (!wide && !getenv_flag("JMC_NO_ROWS")) {
+        /* width not a multiple of 16 on an aligned surface: bulk-loaded row tiles, both directions */
+        if (!getenv_flag("JMC_NO_BULK")) {
+            int r = launch_bulk_rows(ctx, j, p, k1, stream);
+            if (r != 1) return r;                    /* 1: surface side not 16-byte friendly or tile too large */
+        }
+        if (narrow_vectors(j, p) || getenv_flag("JMC_ROWS_ALWAYS")) {
+            int r = launch_rows(ctx, j, p, k1, stream);
+            if (r != 1) return r;                    /* 1: surface side not 16-byte friendly, use the any-alignment kernel */
+        }
     }
 #define JMC_LAUNCH(TT, K1)                                                                               \
     do {                                                                                                 \

@@ -808,6 +808,198 @@ __global__ void __launch_bounds__(ROWS_THREADS, TO_TIGHT ? JMC_ROWS_MINB_DEC : J
 }
 
 /* ========================================================================================== */
+/* Bulk-loaded rows: decode direction, aligned surface, any width                              */
+/* ========================================================================================== */
+/* The surface side of a width that is not a multiple of 16 is still bulk-copy friendly (aligned rows,
+ * over-readable to the next multiple of 16 inside the pitch), so the copy engine loads a tile of rows
+ * into shared memory - every byte of the tile in flight at once, no registers, no LDG issue slots - and
+ * the four warps only do the re-aligned 16-byte stores of warp_store_shifted(), one tight row at a time
+ * (chroma: after a shared -> shared prmt de-interleave).  rows_kernel's load half was what held 1366-
+ * and 854-wide frames at 0.84-0.89 of peak: one row per warp leaves too few bytes in flight. */
+constexpr int BROWS_THREADS = 128;
+
+struct BulkRowsParams {
+    FrameSet pitched, tight;
+    uint32_t n_frames;
+    uint32_t rows_per_tile;
+    uint32_t tiles[2];        /* tiles per frame of part 0 / part 1 */
+    uint32_t rstride[2];      /* shared-memory stride of a staged row (surface bytes; multiple of 16, of 32 for chroma pairs) */
+    uint32_t ldbytes[2];      /* bytes per bulk row load: row bytes rounded up to 16 */
+    Part part[2];
+};
+
+template <int KIND1>
+__global__ void __launch_bounds__(BROWS_THREADS) bulk_rows_kernel(const __grid_constant__ BulkRowsParams p)
+{
+    extern __shared__ __align__(128) uint8_t bulk_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t tpf = p.tiles[0] + p.tiles[1];
+    const uint32_t f = blockIdx.x / tpf;
+    uint32_t r = blockIdx.x - f * tpf;
+    const bool second = r >= p.tiles[0];
+    if (second) r -= p.tiles[0];
+    const Part &pt = second ? p.part[1] : p.part[0];
+    const uint32_t rs = second ? p.rstride[1] : p.rstride[0];
+    const uint32_t ld = second ? p.ldbytes[1] : p.ldbytes[0];
+    const uint8_t *pp = frame_ptr(p.pitched, f) + pt.p_off;
+    uint8_t *tp = frame_ptr(p.tight, f);
+    const uint32_t r0 = r * p.rows_per_tile;
+    const uint32_t nr = min(p.rows_per_tile, pt.rows - r0);
+    const uint32_t re = pt.row_elems;
+    const size_t pitch = (size_t)(uint32_t)pt.p_pitch;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *A = bulk_smem;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, nr * ld);
+        for (uint32_t i = 0; i < nr; i++) bulk_g2s(A + (size_t)i * rs, pp + (size_t)(r0 + i) * pitch, ld, &bar);
+    }
+    mbar_wait(&bar, 0);
+
+    if (!second || KIND1 == PART_COPY) {
+        uint8_t *t = tp + pt.a_off + (size_t)r0 * re;
+        for (uint32_t i = warp; i < nr; i += BROWS_THREADS / 32) warp_store_shifted(t + (size_t)i * re, A + (size_t)i * rs, re, lane);
+    } else {
+        /* chroma: re = pairs per row; staged rows are rs interleaved bytes apart, rs/2 apart in the planar halves */
+        uint8_t *B = A + (size_t)p.rows_per_tile * rs + 32;
+        uint8_t *Cc = B + (size_t)p.rows_per_tile * (rs / 2) + 32;
+        const uint32_t nvec = nr * rs / 32;                   /* 16 bytes of U and of V per step */
+        for (uint32_t v = threadIdx.x; v < nvec; v += BROWS_THREADS) {
+            const uint4 a = *(const uint4 *)(A + (size_t)v * 32), b = *(const uint4 *)(A + (size_t)v * 32 + 16);
+            uint4 u, w;
+            u.x = __byte_perm(a.x, a.y, 0x6420); w.x = __byte_perm(a.x, a.y, 0x7531);
+            u.y = __byte_perm(a.z, a.w, 0x6420); w.y = __byte_perm(a.z, a.w, 0x7531);
+            u.z = __byte_perm(b.x, b.y, 0x6420); w.z = __byte_perm(b.x, b.y, 0x7531);
+            u.w = __byte_perm(b.z, b.w, 0x6420); w.w = __byte_perm(b.z, b.w, 0x7531);
+            *(uint4 *)(B + (size_t)v * 16) = u;
+            *(uint4 *)(Cc + (size_t)v * 16) = w;
+        }
+        __syncthreads();
+        uint8_t *tu = tp + pt.a_off + (size_t)r0 * re, *tv = tp + pt.b_off + (size_t)r0 * re;
+        for (uint32_t i = warp; i < nr; i += BROWS_THREADS / 32) {
+            warp_store_shifted(tu + (size_t)i * re, B + (size_t)i * (rs / 2), re, lane);
+            warp_store_shifted(tv + (size_t)i * re, Cc + (size_t)i * (rs / 2), re, lane);
+        }
+    }
+}
+
+/* Encode direction of the same idea.  The tight rows of a tile are ONE contiguous run at an arbitrary
+ * address: its 16-byte-aligned interior is bulk-loaded into shared memory at the same alignment modulo
+ * 16 (nothing outside the run is read), the < 16-byte head and tail come in through two warps, and
+ * each surface row (16-byte aligned) is then assembled from two aligned shared-memory chunks with a
+ * per-row funnel shift - U and V re-aligned separately and interleaved in registers for the packed
+ * chroma plane.  Padding bytes are never written (the last chunk of a row is a prefix store). */
+struct StagedRun {
+    uint32_t a, head, body, len;      /* run byte i lives at S[a + i]; S + a + head is 16-byte aligned */
+};
+__device__ __forceinline__ StagedRun make_run(const uint8_t *src, uint32_t len)
+{
+    StagedRun r;
+    r.a = (uint32_t)(uintptr_t)src & 15u;
+    r.len = len;
+    r.head = min(len, (16u - r.a) & 15u);
+    r.body = (len - r.head) & ~15u;
+    return r;
+}
+/* warps 0 and 1 bring in the head and the tail (thread 0 has already issued the bulk load of the body) */
+__device__ __forceinline__ void run_edges(uint8_t *S, const uint8_t *src, const StagedRun &r, uint32_t lane, uint32_t warp)
+{
+    if (warp == 0 && lane < r.head) S[r.a + lane] = src[lane];
+    const uint32_t t = r.head + r.body + lane;
+    if (warp == 1 && t < r.len) S[r.a + t] = src[t];
+}
+/* 16 bytes of a staged run starting at byte offset off of S (any alignment) */
+__device__ __forceinline__ uint4 staged16(const uint8_t *S, uint32_t off)
+{
+    const uint4 *q = (const uint4 *)S + (off >> 4);
+    if ((off & 15) == 0) return q[0];
+    return shift_pair(q[0], q[1], (off & 15) >> 2, 8 * (off & 3));
+}
+
+template <int KIND1>
+__global__ void __launch_bounds__(BROWS_THREADS) bulk_rows_pack_kernel(const __grid_constant__ BulkRowsParams p)
+{
+    extern __shared__ __align__(128) uint8_t bulk_smem[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t tpf = p.tiles[0] + p.tiles[1];
+    const uint32_t f = blockIdx.x / tpf;
+    uint32_t r = blockIdx.x - f * tpf;
+    const bool second = r >= p.tiles[0];
+    if (second) r -= p.tiles[0];
+    const Part &pt = second ? p.part[1] : p.part[0];
+    uint8_t *pp = frame_ptr(p.pitched, f) + pt.p_off;
+    const uint8_t *tp = frame_ptr(p.tight, f);
+    const uint32_t r0 = r * p.rows_per_tile;
+    const uint32_t nr = min(p.rows_per_tile, pt.rows - r0);
+    const uint32_t re = pt.row_elems;
+    const size_t pitch = (size_t)(uint32_t)pt.p_pitch;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+
+    if (!second || KIND1 == PART_COPY) {
+        const uint8_t *src = tp + pt.a_off + (size_t)r0 * re;
+        const StagedRun run = make_run(src, nr * re);
+        uint8_t *S = bulk_smem;
+        if (threadIdx.x == 0 && run.body) {
+            mbar_expect_tx(&bar, run.body);
+            bulk_g2s(S + run.a + run.head, src + run.head, run.body, &bar);
+        }
+        run_edges(S, src, run, lane, warp);
+        __syncthreads();
+        if (run.body) mbar_wait(&bar, 0);
+        for (uint32_t i = warp; i < nr; i += BROWS_THREADS / 32) {
+            uint8_t *d = pp + (size_t)(r0 + i) * pitch;
+            const uint32_t off = run.a + i * re;
+            for (uint32_t c = 16 * lane; c < re; c += 512) {
+                const uint4 o = staged16(S, off + c);
+                if (c + 16 <= re) *(uint4 *)(d + c) = o;
+                else { const uint32_t wd[4] = {o.x, o.y, o.z, o.w}; store_prefix<4>(d + c, wd, re - c); }
+            }
+        }
+    } else {
+        /* MERGE: re = pairs per row; U run and V run staged separately */
+        const uint8_t *su = tp + pt.a_off + (size_t)r0 * re, *sv = tp + pt.b_off + (size_t)r0 * re;
+        const StagedRun ru = make_run(su, nr * re), rv = make_run(sv, nr * re);
+        uint8_t *Su = bulk_smem;
+        uint8_t *Sv = bulk_smem + (((size_t)p.rows_per_tile * re + 63) & ~(size_t)15);
+        if (threadIdx.x == 0 && (ru.body | rv.body)) {
+            mbar_expect_tx(&bar, ru.body + rv.body);
+            if (ru.body) bulk_g2s(Su + ru.a + ru.head, su + ru.head, ru.body, &bar);
+            if (rv.body) bulk_g2s(Sv + rv.a + rv.head, sv + rv.head, rv.body, &bar);
+        }
+        run_edges(Su, su, ru, lane, warp);
+        run_edges(Sv, sv, rv, lane, warp ^ 2);               /* warps 2 and 3 */
+        __syncthreads();
+        if (ru.body | rv.body) mbar_wait(&bar, 0);
+        const uint32_t nbytes = 2 * re;
+        for (uint32_t i = warp; i < nr; i += BROWS_THREADS / 32) {
+            uint8_t *d = pp + (size_t)(r0 + i) * pitch;
+            const uint32_t offu = ru.a + i * re, offv = rv.a + i * re;
+            for (uint32_t c = 16 * lane; c < re; c += 512) {          /* 16 pairs -> 32 interleaved bytes at 2c */
+                const uint4 u = staged16(Su, offu + c), w = staged16(Sv, offv + c);
+                uint32_t lo[4], hi[4];
+                lo[0] = __byte_perm(u.x, w.x, 0x5140); lo[1] = __byte_perm(u.x, w.x, 0x7362);
+                lo[2] = __byte_perm(u.y, w.y, 0x5140); lo[3] = __byte_perm(u.y, w.y, 0x7362);
+                hi[0] = __byte_perm(u.z, w.z, 0x5140); hi[1] = __byte_perm(u.z, w.z, 0x7362);
+                hi[2] = __byte_perm(u.w, w.w, 0x5140); hi[3] = __byte_perm(u.w, w.w, 0x7362);
+                const uint32_t rem = nbytes - 2 * c;                  /* > 0 */
+                if (rem >= 32) {
+                    *(uint4 *)(d + 2 * c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    *(uint4 *)(d + 2 * c + 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                } else if (rem >= 16) {
+                    *(uint4 *)(d + 2 * c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    if (rem > 16) store_prefix<4>(d + 2 * c + 16, hi, rem - 16);
+                } else {
+                    store_prefix<4>(d + 2 * c, lo, rem);
+                }
+            }
+        }
+    }
+}
+
+/* ========================================================================================== */
 /* NV12 -> RGB24 (+ optional I420)                                                            */
 /* ========================================================================================== */
 struct RgbParams {

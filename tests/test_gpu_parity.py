@@ -266,15 +266,21 @@ def test_rgb_ldg_stg_kernel_still_matches(ctx, c, fused, monkeypatch):
     assert K.sha(rgb) == GOLD[K.case_id(c)]["sha256"]
 
 
+@pytest.mark.parametrize("kernels", ["bulk_rows", "ldg_rows", "ldg_rows_always"])
 @pytest.mark.parametrize("seed", range(4))
-def test_random_widths_on_aligned_surfaces(ctx, seed):
-    """The row-staged kernel: decoder-style surfaces (16-byte aligned, pitch a multiple of 16) with
-    arbitrary widths/heights and arbitrarily skewed tight buffers, all four YUV ops, vs the oracle."""
+def test_random_widths_on_aligned_surfaces(ctx, seed, kernels, monkeypatch):
+    """The row kernels (bulk-loaded tiles by default; JMC_NO_BULK=1: the warp-per-row LDG kernel): decoder-style
+    surfaces (16-byte aligned, pitch a multiple of 16) with arbitrary widths/heights (several tiles deep) and
+    arbitrarily skewed tight buffers, all four YUV ops, vs the oracle."""
+    if kernels != "bulk_rows":
+        monkeypatch.setenv("JMC_NO_BULK", "1")
+    if kernels == "ldg_rows_always":
+        monkeypatch.setenv("JMC_ROWS_ALWAYS", "1")
     chk = oracle.best()
     rng = np.random.default_rng(3000 + seed)
-    for _ in range(30):
+    for it in range(30):
         w = int(rng.integers(1, 2600))
-        h = int(rng.integers(1, 24))
+        h = int(rng.integers(1, 24)) if it % 3 else int(rng.integers(24, 150))
         pitch = ((w + 15) & ~15) + 16 * int(rng.integers(0, 5))
         kt = int(rng.integers(0, 16))
         surf = synth.nv12_surface(w, h, pitch, 23, w * 31 + h)

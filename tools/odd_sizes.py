@@ -13,9 +13,9 @@ for name, spec in {
     "pack 854x480 p1024": ("pack", 854, 480, 1024, 600), "pack 1919x1079 p2048": ("pack", 1919, 1079, 2048, 300),
     "nv12 1366x768 p1536": ("nv12", 1366, 768, 1536, 300), "rgb 1080x1920 p1088": ("rgb", 1080, 1920, 1088, 150),
     "rgb 1366x768 p1536": ("rgb", 1366, 768, 1536, 300), "argb 1366x768 p1536": ("argb", 1366, 768, 1536, 300),
-    "fused 1366x768 p1536": ("fused", 1366, 768, 1536, 300),
+    "fused 1366x768 p1536": ("fused", 1366, 768, 1536, 300), "argb 3840x2160 p4096": ("argb", 3840, 2160, 4096, 64),
 }.items():
-    if len(sys.argv) > 1 and not any(a in name for a in sys.argv[1:]):
+    if len(sys.argv) > 1 and not any((a[1:] == name) if a.startswith('=') else (a in name) for a in sys.argv[1:]):
         continue
     bench.WORKLOADS["_x"] = spec
     r = bench.device_only(ctx, "_x", 0, 10, 3)
