@@ -346,20 +346,29 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     if (total == 0) return JMC_OK;
     if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }
     p.total_tasks = (uint32_t)total;
-    /* bulk-copy-engine variant: everything 16-byte aligned, chroma rows 16-byte multiples (w % 32 == 0),
-     * 10*w bytes of shared memory */
+    /* bulk-copy-engine variants: 10 bytes of shared memory per pixel of a segment */
     {
         uint64_t bits = (uint64_t)j->surf_y_off | (uint64_t)j->surf_uv_off | (uint32_t)j->pitch | (uint32_t)j->rgb_pitch | (uint32_t)j->width;
         if (fused) bits |= (uint32_t)(j->width >> 1);            /* U / V rows are bulk-stored too */
         const jmc_frames *sets[3] = { &j->surf, &j->rgb, fused ? &j->tight : nullptr };
-        bool ok = !getenv_flag("JMC_NO_BULK") && !argb;          /* ARGB32 runs on the vector kernel */
-        for (int i = 0; i < 3 && ok; i++) {
+        const bool ok = !getenv_flag("JMC_NO_BULK") && !argb;    /* ARGB32 runs on the vector kernel */
+        bool known = true;                                       /* pointer lists: aligned only if the caller says so */
+        for (int i = 0; i < 3; i++) {
             if (!sets[i]) continue;
-            if (sets[i]->list) ok = (j->flags & JMC_JOB_ALIGNED16) != 0;
+            if (sets[i]->list) known = known && (j->flags & JMC_JOB_ALIGNED16) != 0;
             else bits |= (uint64_t)(uintptr_t)sets[i]->base | (uint64_t)sets[i]->stride;
         }
         if (fused) bits |= (uint64_t)j->tight_u_off | (uint64_t)j->tight_v_off;
-        if (ok && (bits & 15) == 0) {
+        /* !aligned: only the surface has to be 16-byte friendly (any even width; rows over-readable to the next
+         * multiple of 16 inside the pitch) - RGB / tight rows at any address are written with re-aligned stores */
+        const bool aligned = known && (bits & 15) == 0;
+        bool surf_ok = (j->width & 1) == 0 && j->pitch >= ((j->width + 15) & ~15) &&
+                       (((uint64_t)j->surf_y_off | (uint64_t)j->surf_uv_off | (uint32_t)j->pitch) & 15) == 0;
+        if (j->surf.list) surf_ok = surf_ok && (j->flags & JMC_JOB_ALIGNED16) != 0;
+        else surf_ok = surf_ok && (((uint64_t)(uintptr_t)j->surf.base | (uint64_t)j->surf.stride) & 15) == 0;
+        /* measured (profiles/r1_odd_sizes_rgb_bulk.txt): with unaligned rows the bulk-loaded variant wins for the
+         * fused op (1366-wide: 0.88 vs 0.79 of peak) but not for RGB alone (0.77 vs 0.82; 1080-wide 0.68 vs 0.82) */
+        if (ok && (aligned || (surf_ok && (fused || getenv_flag("JMC_RGB_BULK_ALWAYS"))))) {
             RgbBulkParams b;
             b.surf = p.surf; b.tight = p.tight; b.rgb = p.rgb;
             b.n_frames = p.n_frames; b.width = p.width; b.height = p.height; b.pitch = p.pitch;
@@ -373,13 +382,19 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
             b.seg_w = ((((uint32_t)j->width + b.segs - 1) / b.segs) + 31) & ~31u;
             b.segs = ((uint32_t)j->width + b.seg_w - 1) / b.seg_w;
             const uint64_t ctas = (uint64_t)b.row_pairs * b.segs * b.n_frames;
-            if (ctas <= 0x7fffffffull) {
-                static bool attr_done[64];
-                if (ctx->device < 64 && !attr_done[ctx->device]) {
-                    JMC_CUDA(cudaFuncSetAttribute(rgb_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                    attr_done[ctx->device] = true;
-                }
-                rgb_bulk_kernel<<<(uint32_t)ctas, RGB_BULK_THREADS, (size_t)b.seg_w * 10, stream>>>(b);
+            const size_t smem = (size_t)b.seg_w * 10 + 64;           /* + spare chunks read by the re-aligning stores */
+            if (ctas <= 0x7fffffffull && smem <= 100 * 1024) {
+#define JMC_RGB_BULK(AL)                                                                                          \
+    do {                                                                                                          \
+        static bool attr_done[64];                                                                                \
+        if (ctx->device < 64 && !attr_done[ctx->device]) {                                                        \
+            JMC_CUDA(cudaFuncSetAttribute(rgb_bulk_kernel<AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
+            attr_done[ctx->device] = true;                                                                        \
+        }                                                                                                         \
+        rgb_bulk_kernel<AL><<<(uint32_t)ctas, RGB_BULK_THREADS, smem, stream>>>(b);                               \
+    } while (0)
+                if (aligned) JMC_RGB_BULK(true); else JMC_RGB_BULK(false);
+#undef JMC_RGB_BULK
                 JMC_CUDA(cudaGetLastError());
                 ctx->launches++;
                 return JMC_OK;

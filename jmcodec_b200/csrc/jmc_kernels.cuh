@@ -1284,6 +1284,10 @@ struct RgbBulkParams {
 
 constexpr int RGB_BULK_THREADS = 128;
 
+/* ALIGNED: every RGB / tight row is a 16-byte-aligned multiple of 16 bytes and leaves through the copy engine.
+ * !ALIGNED: only the surface is aligned (any even width): rows are loaded rounded up to 16 bytes (inside the
+ * pitch) and the four warps write the RGB / tight rows with re-aligned 16-byte stores (warp_store_shifted). */
+template <bool ALIGNED>
 __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid_constant__ RgbBulkParams p)
 {
     extern __shared__ __align__(128) uint8_t rs[];
@@ -1294,7 +1298,8 @@ __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid
     const uint32_t rp = t / p.segs, seg = t - rp * p.segs;
     const uint32_t W = (uint32_t)p.width, h = (uint32_t)p.height, cw = W >> 1, ch = h >> 1;
     const uint32_t x0 = seg * p.seg_w;                     /* first pixel of this segment */
-    const uint32_t w = min(p.seg_w, W - x0);               /* pixels in this segment (multiple of 16) */
+    const uint32_t w = min(p.seg_w, W - x0);               /* pixels in this segment (ALIGNED: a multiple of 16; else even) */
+    const uint32_t lw = ALIGNED ? w : ((w + 15) & ~15u);   /* bytes loaded per row */
     const uint32_t y0 = rp * 2;
     const bool two = y0 + 1 < h;
     const uint32_t cy = min(rp, ch - 1);
@@ -1308,16 +1313,16 @@ __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid
     uint8_t *s_v = s_u + (sw >> 1);
     if (threadIdx.x == 0) {
         mbar_init(&bar, 1);
-        mbar_expect_tx(&bar, (two ? 3u : 2u) * w);
+        mbar_expect_tx(&bar, (two ? 3u : 2u) * lw);
         const uint8_t *yrow = sp + p.y_off + (size_t)y0 * p.pitch + x0;
-        bulk_g2s(s_y, yrow, w, &bar);
-        if (two) bulk_g2s(s_y + sw, yrow + p.pitch, w, &bar);
-        bulk_g2s(s_uv, sp + p.uv_off + (size_t)cy * p.pitch + x0, w, &bar);
+        bulk_g2s(s_y, yrow, lw, &bar);
+        if (two) bulk_g2s(s_y + sw, yrow + p.pitch, lw, &bar);
+        bulk_g2s(s_uv, sp + p.uv_off + (size_t)cy * p.pitch + x0, lw, &bar);
     }
     __syncthreads();
     mbar_wait(&bar, 0);
     const bool do_uv = p.fused && rp < ch;
-    for (uint32_t unit = threadIdx.x; unit < (w >> 4); unit += RGB_BULK_THREADS) {
+    for (uint32_t unit = threadIdx.x; unit < (lw >> 4); unit += RGB_BULK_THREADS) {
         const uint4 uv = *(const uint4 *)(s_uv + unit * 16);
         const uint32_t uvw[4] = {uv.x, uv.y, uv.z, uv.w};
         int cr[8], cg[8], cb[8];
@@ -1349,21 +1354,40 @@ __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid
             d[2] = make_uint4(o[8], o[9], o[10], o[11]);
         }
     }
-    fence_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        bulk_s2g(rgbp, s_rgb, 3 * w);
-        if (two) bulk_s2g(rgbp + p.rgb_pitch, s_rgb + 3 * (size_t)sw, 3 * w);
-        if (p.fused) {
-            uint8_t *tp = frame_ptr(p.tight, f);
-            bulk_s2g(tp + (size_t)y0 * W + x0, s_y, w);
-            if (two) bulk_s2g(tp + (size_t)(y0 + 1) * W + x0, s_y + sw, w);
-            if (do_uv) {
-                bulk_s2g(tp + p.u_off + (size_t)rp * cw + (x0 >> 1), s_u, w >> 1);
-                bulk_s2g(tp + p.v_off + (size_t)rp * cw + (x0 >> 1), s_v, w >> 1);
+    if (ALIGNED) {
+        fence_async_smem();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            bulk_s2g(rgbp, s_rgb, 3 * w);
+            if (two) bulk_s2g(rgbp + p.rgb_pitch, s_rgb + 3 * (size_t)sw, 3 * w);
+            if (p.fused) {
+                uint8_t *tp = frame_ptr(p.tight, f);
+                bulk_s2g(tp + (size_t)y0 * W + x0, s_y, w);
+                if (two) bulk_s2g(tp + (size_t)(y0 + 1) * W + x0, s_y + sw, w);
+                if (do_uv) {
+                    bulk_s2g(tp + p.u_off + (size_t)rp * cw + (x0 >> 1), s_u, w >> 1);
+                    bulk_s2g(tp + p.v_off + (size_t)rp * cw + (x0 >> 1), s_v, w >> 1);
+                }
             }
+            bulk_commit_wait_read();
         }
-        bulk_commit_wait_read();
+    } else {
+        __syncthreads();
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t row = warp & 1;                                 /* warps 0,2: first row; 1,3: second row */
+        if (p.fused) {
+            if (warp < 2) {
+                if (row == 0 || two) warp_store_shifted(rgbp + (size_t)row * p.rgb_pitch, s_rgb + (size_t)row * 3 * sw, 3 * w, lane);
+            } else {
+                uint8_t *tp = frame_ptr(p.tight, f);
+                if (row == 0 || two) warp_store_shifted(tp + (size_t)(y0 + row) * W + x0, s_y + (size_t)row * sw, w, lane);
+                if (do_uv) warp_store_shifted(tp + (row ? p.v_off : p.u_off) + (size_t)rp * cw + (x0 >> 1), row ? s_v : s_u, w >> 1, lane);
+            }
+        } else if (row == 0 || two) {
+            const uint32_t half = ((3 * w) >> 1) & ~15u;               /* each RGB row is shared by two warps */
+            const uint32_t b0 = warp < 2 ? 0u : half, b1 = warp < 2 ? half : 3 * w;
+            warp_store_shifted(rgbp + (size_t)row * p.rgb_pitch + b0, s_rgb + (size_t)row * 3 * sw + b0, b1 - b0, lane);
+        }
     }
 }
 

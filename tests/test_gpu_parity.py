@@ -266,6 +266,56 @@ def test_rgb_ldg_stg_kernel_still_matches(ctx, c, fused, monkeypatch):
     assert K.sha(rgb) == GOLD[K.case_id(c)]["sha256"]
 
 
+@pytest.mark.parametrize("c", [c for c in K.rgb_cases() if c["w"] % 2 == 0 and c["w"] % 16 != 0], ids=K.case_id)
+def test_rgb_bulk_loaded_kernel_with_unaligned_rows(ctx, c, monkeypatch):
+    """Even widths that are not multiples of 16: the fused op takes the bulk-loaded kernel with re-aligned stores;
+    JMC_RGB_BULK_ALWAYS=1 sends plain RGB24 through it too (normally the vector kernel, which is faster there)."""
+    monkeypatch.setenv("JMC_RGB_BULK_ALWAYS", "1")
+    assert K.sha(G.gpu_rgb(ctx, c)) == GOLD[K.case_id(c)]["sha256"]
+
+
+@pytest.mark.parametrize("always", [False, True])
+@pytest.mark.parametrize("seed", range(2))
+def test_random_widths_rgb_on_aligned_surfaces(ctx, seed, always, monkeypatch):
+    """RGB24, fused I420+RGB24 and ARGB32 on decoder-style surfaces with arbitrary widths and skewed output buffers."""
+    if always:
+        monkeypatch.setenv("JMC_RGB_BULK_ALWAYS", "1")
+    chk = oracle.best()
+    rng = np.random.default_rng(4000 + seed)
+    for it in range(24):
+        w = int(rng.integers(2, 2600))
+        if it % 4:
+            w &= ~1
+        h = int(rng.integers(2, 40))
+        pitch = ((w + 15) & ~15) + 16 * int(rng.integers(0, 3))
+        kt, kr = int(rng.integers(0, 16)), int(rng.integers(0, 16))
+        surf = synth.nv12_surface(w, h, pitch, 29, w * 7 + h)
+        dsurf = ctx.upload(surf)
+        for op in ("rgb", "fused", "argb"):
+            bpp = 4 if op == "argb" else 3
+            rcap, tcap = bpp * w * h + K.SLACK, w * h * 3 // 2 + K.SLACK
+            drgb, dt = ctx.alloc(rcap + 64), ctx.alloc(tcap + 64)
+            ctx.memset(drgb, synth.OUT_FILL, rcap + 64), ctx.memset(dt, synth.OUT_FILL, tcap + 64)
+            j = ctx.job_argb(w, h, pitch, 4 * w) if op == "argb" else ctx.job_rgb(w, h, pitch, 3 * w, op == "fused")
+            j.n_frames, j.surf.base, j.rgb.base = 1, dsurf, drgb + kr
+            if op == "fused":
+                j.tight.base = dt + kt
+            ctx.convert(j)
+            got = np.empty(rcap, np.uint8)
+            ctx.d2h(got, drgb + kr)
+            want = np.full(rcap, synth.OUT_FILL, np.uint8)
+            (oracle.nv12_to_argb32 if op == "argb" else oracle.nv12_to_rgb24)(surf, pitch, w, h, want, bpp * w)
+            assert np.array_equal(got, want), (op, w, h, pitch, kr)
+            if op == "fused":
+                gt = np.empty(tcap, np.uint8)
+                ctx.d2h(gt, dt + kt)
+                wt = np.full(tcap, synth.OUT_FILL, np.uint8)
+                chk.nvdec_output_frame(surf, pitch, w, h, 1, wt, tcap)
+                assert np.array_equal(gt, wt), (op, w, h, pitch, kt)
+            ctx.free(drgb), ctx.free(dt)
+        ctx.free(dsurf)
+
+
 @pytest.mark.parametrize("kernels", ["bulk_rows", "ldg_rows", "ldg_rows_always"])
 @pytest.mark.parametrize("seed", range(4))
 def test_random_widths_on_aligned_surfaces(ctx, seed, kernels, monkeypatch):
