@@ -103,10 +103,11 @@ static int launch_bulk(jmc_ctx *ctx, const PlaneParams &pp, int k1, cudaStream_t
     return JMC_OK;
 }
 
-/* Would the any-alignment kernel be reduced to <= 4-byte luma or <= 2-byte chroma accesses on this job?
- * (Then the row-staged kernel wins: measured 0.41-0.59 -> 0.69-0.87 of peak on 1366/854/1918/1919-wide
- * frames; with 8-byte luma / 4-byte chroma vectors - 1080-wide portrait, 720x480 - the plain kernel is
- * faster, 0.96 vs 0.67-0.74.)  Pointer lists are taken as 16-byte aligned only with JMC_JOB_ALIGNED16. */
+/* Only consulted with JMC_NO_BULK=1 (the LDG kernels): would the any-alignment kernel be reduced to <= 4-byte
+ * luma or <= 2-byte chroma accesses on this job?  Then the warp-per-row kernel wins (0.41-0.59 -> 0.84-0.98 of
+ * peak on 1366/854/1918/1919-wide frames); with 8-byte luma / 4-byte chroma vectors - 1080-wide portrait,
+ * 720x480 - the plain kernel is faster (0.96 vs 0.78-0.87).  Pointer lists count as aligned only with
+ * JMC_JOB_ALIGNED16. */
 static bool narrow_vectors(const jmc_job *j, const PlaneParams &p)
 {
     uint64_t common = 0;
@@ -124,9 +125,9 @@ static bool narrow_vectors(const jmc_job *j, const PlaneParams &p)
     return vy <= 4 || vc <= 2;
 }
 
-/* Row-staged kernel for widths that are not multiples of 16: needs only the SURFACE side aligned
- * (base, pitch, plane offsets multiples of 16; rows over-readable up to the next multiple of 16).
- * Returns 1 when that does not hold. */
+/* Warp-per-row LDG kernel for widths that are not multiples of 16 (the A/B partner of launch_bulk_rows):
+ * needs only the SURFACE side aligned (base, pitch, plane offsets multiples of 16; rows over-readable up
+ * to the next multiple of 16).  Returns 1 when that does not hold. */
 static int launch_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, int k1, cudaStream_t stream)
 {
     if (j->surf.list) { if (!(j->flags & JMC_JOB_ALIGNED16)) return 1; }

@@ -536,14 +536,16 @@ template <int NW> __device__ __forceinline__ void store_prefix(uint8_t *dst, con
 }
 
 /* ========================================================================================== */
-/* Row-staged plane kernel: full-width accesses for sizes that are NOT multiples of 16           */
+/* Row kernels: full-width accesses for sizes that are NOT multiples of 16                        */
 /* ========================================================================================== */
 /* Decoder/encoder surfaces are always 16-byte aligned with a 16-byte-multiple pitch, whatever the
  * picture width; only the tight side (rows of w or w/2 bytes back to back) lands on odd addresses
- * when w is not a multiple of 16/32 (1366, 854, 1080-wide portrait chroma, odd sizes).  One warp per
- * (row, 2 KB segment): 16-byte loads/stores on the surface side, a pass through warp-private shared
- * memory, and on the tight side 16-byte accesses to the ALIGNED body of the segment, re-aligned by a
- * funnel shift (classic unaligned memcpy), with byte accesses only for the <16-byte head and tail. */
+ * when w is not a multiple of 16/32 (1366, 854, 1080-wide portrait chroma, odd sizes).  Common idea of
+ * the kernels below: 16-byte accesses on the surface side, a pass through shared memory, and on the
+ * tight side 16-byte accesses to the ALIGNED body of each row, re-aligned by a funnel shift (classic
+ * unaligned memcpy), with byte accesses only for the <16-byte head and tail.
+ * rows_kernel (this one, JMC_NO_BULK=1): LDG/STG, one warp per (row, 2 KB segment) or per group of short
+ * rows.  bulk_rows_kernel / bulk_rows_pack_kernel (further down, the default): the copy engine loads. */
 /* CTAs per SM the register allocation is sized for, decode / encode direction (A/B: tools/variants.sh,
  * profiles/r1_odd_sizes_minb.txt: 10 beats 8 and 12 on the decode side) */
 #ifndef JMC_ROWS_MINB_DEC
