@@ -101,6 +101,17 @@ def test_algorithmic_bytes(lib):
     assert lib.jmc_job_algorithmic_bytes(C.byref(j)) == 37324800
     _, j = _job("jmc_job_rgb", 3840, 2160, 4096, 3 * 3840, 1)
     assert lib.jmc_job_algorithmic_bytes(C.byref(j)) == 49766400
+    _, j = _job("jmc_job_argb", 3840, 2160, 4096, 4 * 3840)                   # 1.5*w*h read + 4*w*h written
+    assert lib.jmc_job_algorithmic_bytes(C.byref(j)) == 45619200
+
+
+def test_job_argb_filler(lib):
+    w, h, p = 1366, 768, 1536
+    r, j = _job("jmc_job_argb", w, h, p, 4 * w)
+    assert r == 0 and j.op == J.JMC_OP.NV12_TO_ARGB32
+    assert (j.width, j.height, j.pitch, j.rgb_pitch) == (w, h, p, 4 * w)
+    assert (j.surf_y_off, j.surf_uv_off) == (0, p * h)                         # the nv_dec surface layout, nv_dec.cpp:765
+    assert _job("jmc_job_argb", w, h, p, 4 * w - 1)[0] == -1                   # rows must hold 4 bytes per pixel
 
 
 def _no_gpu():

@@ -91,3 +91,17 @@ def test_rgb_spec_known_points():
     assert px(145, 54, 34) == (0, 255, 1)        # BT.601 green: (386>>8)=1 by the integer formula
     assert px(41, 240, 110) == (0, 0, 255)       # BT.601 blue
     assert oracle.nv12_to_rgb24(np.zeros(4, np.uint8), 1, 1, 1, np.zeros(3, np.uint8), 3) == -1
+
+
+def test_argb_is_bgra_bytes_with_opaque_alpha():
+    """ARGB32 = NV_ENC_BUFFER_FORMAT_ARGB's memory order: a little-endian 0xAARRGGBB word, i.e. bytes B,G,R,A; the
+    colour values are those of the RGB24 spec, alpha is 0xFF."""
+    rng = np.random.default_rng(5)
+    w, h, p = 10, 6, 16
+    s = rng.integers(0, 256, p * h * 3 // 2, dtype=np.uint8)
+    rgb, argb = np.zeros(3 * w * h, np.uint8), np.zeros(4 * w * h, np.uint8)
+    assert oracle.nv12_to_rgb24(s, p, w, h, rgb, 3 * w) == 0
+    assert oracle.nv12_to_argb32(s, p, w, h, argb, 4 * w) == 0
+    a, r = argb.reshape(-1, 4), rgb.reshape(-1, 3)
+    assert (a[:, 3] == 255).all()
+    assert np.array_equal(a[:, 2], r[:, 0]) and np.array_equal(a[:, 1], r[:, 1]) and np.array_equal(a[:, 0], r[:, 2])
