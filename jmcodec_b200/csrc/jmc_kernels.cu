@@ -3,6 +3,9 @@
  */
 #include <stdlib.h>
 
+#include <algorithm>
+#include <atomic>
+
 #include "jmc_internal.h"
 #include "jmc_kernels.cuh"
 
@@ -58,6 +61,17 @@ static bool getenv_flag(const char *name)
     return e && atoi(e) != 0;
 }
 
+/* Opt a kernel in to more than 48 KB of dynamic shared memory, once per (kernel, device); safe to race */
+#define JMC_SMEM_ONCE(BYTES, ...)                                                                                 \
+    do {                                                                                                          \
+        static std::atomic<bool> smem_done[64];                                                                   \
+        const bool tracked = ctx->device >= 0 && ctx->device < 64;                                                \
+        if (!tracked || !smem_done[ctx->device].load(std::memory_order_relaxed)) {                                \
+            JMC_CUDA(cudaFuncSetAttribute(__VA_ARGS__, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES));      \
+            if (tracked) smem_done[ctx->device].store(true, std::memory_order_relaxed);                           \
+        }                                                                                                         \
+    } while (0)
+
 /* Bulk-copy-engine kernel (cp.async.bulk): returns 1 when the geometry does not fit it. */
 static int launch_bulk(jmc_ctx *ctx, const PlaneParams &pp, int k1, cudaStream_t stream)
 {
@@ -85,11 +99,7 @@ static int launch_bulk(jmc_ctx *ctx, const PlaneParams &pp, int k1, cudaStream_t
     const uint32_t grid = (uint32_t)total;
 #define JMC_BULK(TT, K1)                                                                                          \
     do {                                                                                                          \
-        static bool attr_done[64];                                                                                \
-        if (ctx->device < 64 && !attr_done[ctx->device]) {                                                        \
-            JMC_CUDA(cudaFuncSetAttribute(bulk_planes_kernel<TT, K1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); \
-            attr_done[ctx->device] = true;                                                                        \
-        }                                                                                                         \
+        JMC_SMEM_ONCE(96 * 1024, bulk_planes_kernel<TT, K1>);                                                     \
         bulk_planes_kernel<TT, K1><<<grid, BULK_THREADS, smem, stream>>>(b);                                      \
     } while (0)
     if (pp.to_tight) {
@@ -225,11 +235,7 @@ static int launch_bulk_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &p
     const uint32_t grid = (uint32_t)total;
 #define JMC_BROWS(KERNEL)                                                                                         \
     do {                                                                                                          \
-        static bool attr_done[64];                                                                                \
-        if (ctx->device < 64 && !attr_done[ctx->device]) {                                                        \
-            JMC_CUDA(cudaFuncSetAttribute(KERNEL, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));       \
-            attr_done[ctx->device] = true;                                                                        \
-        }                                                                                                         \
+        JMC_SMEM_ONCE(96 * 1024, KERNEL);                                                                         \
         KERNEL<<<grid, BROWS_THREADS, smem, stream>>>(b);                                                         \
     } while (0)
     if (pp.to_tight) {
@@ -387,11 +393,7 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
             if (ctas <= 0x7fffffffull && smem <= 100 * 1024) {
 #define JMC_RGB_BULK(AL)                                                                                          \
     do {                                                                                                          \
-        static bool attr_done[64];                                                                                \
-        if (ctx->device < 64 && !attr_done[ctx->device]) {                                                        \
-            JMC_CUDA(cudaFuncSetAttribute(rgb_bulk_kernel<AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024)); \
-            attr_done[ctx->device] = true;                                                                        \
-        }                                                                                                         \
+        JMC_SMEM_ONCE(100 * 1024, rgb_bulk_kernel<AL>);                                                           \
         rgb_bulk_kernel<AL><<<(uint32_t)ctas, RGB_BULK_THREADS, smem, stream>>>(b);                               \
     } while (0)
                 if (aligned) JMC_RGB_BULK(true); else JMC_RGB_BULK(false);
