@@ -105,3 +105,49 @@ def test_argb_is_bgra_bytes_with_opaque_alpha():
     a, r = argb.reshape(-1, 4), rgb.reshape(-1, 3)
     assert (a[:, 3] == 255).all()
     assert np.array_equal(a[:, 2], r[:, 0]) and np.array_equal(a[:, 1], r[:, 1]) and np.array_equal(a[:, 0], r[:, 2])
+
+
+@pytest.mark.skipif(not oracle.have_ref(), reason="oracle/_ref/libjmref.so not built")
+@pytest.mark.parametrize("seed", range(4))
+def test_port_matches_compiled_reference_on_random_geometries(seed):
+    """Beyond the fixed case matrix: 60 random geometries per seed (odd sizes, crops, slack pitches) through every
+    reference function the port restates, compared byte for byte including the bytes neither may touch."""
+    rng = np.random.default_rng(7000 + seed)
+    P, R = oracle.port(), oracle.ref()
+    for _ in range(60):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 120))
+        pitch = w + int(rng.integers(0, 40))
+        surf = rng.integers(0, 256, pitch * (h * 3 // 2 + 2), dtype=np.uint8)
+        cap = w * h * 3 // 2 + 32
+        for fmt in (0, 1):                                                   # nv_dec.cpp:750-828
+            a, b = np.full(cap, 0xA5, np.uint8), np.full(cap, 0xA5, np.uint8)
+            assert P.nvdec_output_frame(surf, pitch, w, h, fmt, a, cap) == R.nvdec_output_frame(surf, pitch, w, h, fmt, b, cap)
+            assert np.array_equal(a, b), ("nvdec", w, h, pitch, fmt)
+        # intel_dec.cpp:244-332: a crop window inside a larger surface
+        rows = h + int(rng.integers(0, 8))
+        cw, ch = int(rng.integers(1, w + 1)), int(rng.integers(1, h + 1))
+        cx, cy = int(rng.integers(0, w - cw + 1)), int(rng.integers(0, h - ch + 1))
+        big = rng.integers(0, 256, pitch * (rows + rows // 2 + 2), dtype=np.uint8)
+        ccap = cw * ch * 3 // 2 + 32
+        for fmt in (0, 1):
+            a, b = np.full(ccap, 0xA5, np.uint8), np.full(ccap, 0xA5, np.uint8)
+            ra = P.inteldec_output_frame(big, pitch * rows, pitch, (cx, cy, cw, ch), fmt, a, ccap)
+            rb = R.inteldec_output_frame(big, pitch * rows, pitch, (cx, cy, cw, ch), fmt, b, ccap)
+            assert ra == rb and np.array_equal(a, b), ("inteldec", w, h, pitch, (cx, cy, cw, ch), fmt)
+        # intel_enc.cpp:251-387: tight NV12 / I420 into the crop window of a surface
+        yuv = rng.integers(0, 256, cw * ch * 3 // 2 + 8, dtype=np.uint8)
+        for i420 in (0, 1):
+            a = np.full(big.size, 0xCD, np.uint8)
+            b = a.copy()
+            ra = P.intelenc_input(yuv, i420, a, pitch * rows, pitch, (w, h), (cx, cy, cw, ch))
+            rb = R.intelenc_input(yuv, i420, b, pitch * rows, pitch, (w, h), (cx, cy, cw, ch))
+            assert ra == rb and np.array_equal(a, b), ("intelenc", w, h, pitch, (cx, cy, cw, ch), i420)
+        # nv_enc.cpp:1023-1103 through the fake CUDA driver
+        stride = ((w + 15) & ~15) + 16 * int(rng.integers(0, 3))
+        tight = rng.integers(0, 256, w * h * 3 // 2 + 8, dtype=np.uint8)
+        for fmt in (0x1, 0x10):
+            a = np.full(stride * (h * 3 // 2 + 2), 0xCD, np.uint8)
+            b = a.copy()
+            ra = oracle.nvenc_upload(tight, fmt, w, h, a, stride)
+            rb, _ = oracle.ref_nvenc_convert(tight, fmt, w, h, b, stride)
+            assert ra == rb and np.array_equal(a, b), ("nvenc", w, h, stride, hex(fmt))
