@@ -45,6 +45,7 @@ WORKLOADS = {
     "nv12_to_rgb24_4k_x64_pitch4096": ("rgb", 3840, 2160, 4096, 64),
     "nv12_to_i420_rgb24_4k_x64_pitch4096": ("fused", 3840, 2160, 4096, 64),
     "nv12_to_argb32_4k_x64_pitch4096": ("argb", 3840, 2160, 4096, 64),
+    "rgb24_to_nv12_4k_x64_pitch4096": ("rgb2nv12", 3840, 2160, 4096, 64),      # kernel table only (not a pipeline op)
 }
 DEFAULT_WORKLOAD = "nv12_to_i420_1080p_x300_pitch2048"
 N_DISTINCT = 32          # distinct synthetic surfaces, tiled over the batch
@@ -186,6 +187,8 @@ def make_inputs(op, w, h, pitch, rank):
     from jmcodec_b200 import synth
     if op == "pack":
         return [synth.i420_frame(w, h, rank, f) for f in range(N_DISTINCT)]
+    if op == "rgb2nv12":
+        return [synth.random_bytes(3 * w * h, synth.frame_key(rank, f) ^ 0x33CC33CC) for f in range(N_DISTINCT)]
     return [synth.nv12_surface(w, h, pitch, rank, f) for f in range(N_DISTINCT)]
 
 
@@ -252,6 +255,9 @@ def build_job(ctx, op, w, h, pitch, n, d_in, d_out, d_out2):
     elif op == "argb":
         j = ctx.job_argb(w, h, pitch, 4 * w)
         j.surf.base, j.surf.stride, j.rgb.base, j.rgb.stride = d_in, surf_bytes, d_out, 4 * w * h
+    elif op == "rgb2nv12":
+        j = ctx.job_rgb_to_nv12(w, h, 3 * w, pitch)
+        j.rgb.base, j.rgb.stride, j.surf.base, j.surf.stride = d_in, 3 * w * h, d_out, surf_bytes
     else:
         j = ctx.job_rgb(w, h, pitch, 3 * w, op == "fused")
         j.surf.base, j.surf.stride = d_in, surf_bytes
@@ -271,6 +277,8 @@ def io_bytes(op, w, h, pitch):
         return surf_bytes, rgb, 0
     if op == "argb":
         return surf_bytes, 4 * w * h, 0
+    if op == "rgb2nv12":
+        return rgb, surf_bytes, 0
     if op == "fused":
         return surf_bytes, tight_bytes, rgb
     return surf_bytes, tight_bytes, 0
@@ -288,7 +296,7 @@ def device_only(ctx, name, rank, iters, warmup):
         ctx.h2d(d_in + r * N_DISTINCT * in_b, host, cnt * in_b)
     d_out = ctx.alloc(out_b * n)
     d_out2 = ctx.alloc(out2_b * n) if out2_b else None
-    if op == "pack":
+    if op in ("pack", "rgb2nv12"):
         ctx.memset(d_out, 0, out_b * n)
     j = build_job(ctx, op, w, h, pitch, n, d_in, d_out, d_out2)
     for _ in range(warmup):
@@ -375,7 +383,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(k for k, v in WORKLOADS.items() if v[0] != "rgb2nv12"))
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel table and the CPU baseline")
     ap.add_argument("--e2e-sub", type=int, default=0, help="frames per pipeline batch in the e2e leg (default: auto)")
     ap.add_argument("--e2e-depth", type=int, default=3, help="pipeline slots in the e2e leg")

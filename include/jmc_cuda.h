@@ -84,7 +84,11 @@ typedef enum jmc_op {
     JMC_OP_NV12_TO_I420_RGB24 = 5, /* fused: one read of the surface, both outputs */
     /* what the reference's disabled NV12ToARGB_drvapi hook would have produced on the device
      * (nv_dec.cpp:244-265): packed 32-bit ARGB8888, i.e. bytes B,G,R,0xFF per pixel; same integer BT.601 */
-    JMC_OP_NV12_TO_ARGB32 = 6
+    JMC_OP_NV12_TO_ARGB32 = 6,
+    /* encode side from RGB ("RGB -> NV12 would complete a transcode loop"): packed R,G,B rows
+     * in job->rgb -> pitched NV12 surface in job->surf; builder-defined forward integer BT.601, chroma from the
+     * 2x2 block sums (see oracle/jm_oracle.h jmo_rgb24_to_nv12) */
+    JMC_OP_RGB24_TO_SURF = 7
 } jmc_op;
 
 /* Where frame f of a batch lives: base + f*stride, or list[f] (a DEVICE array of n_frames device
@@ -108,7 +112,7 @@ typedef struct jmc_job {
     jmc_frames tight;
     int64_t    tight_u_off;   /* I420 ops: U plane offset in the tight frame (w*h)              */
     int64_t    tight_v_off;   /* I420 ops: V plane offset (nv_dec: w*h+(w>>1)*(h>>1), :815)     */
-    /* packed RGB24 destination of the display ops */
+    /* packed RGB24 / ARGB32 destination of the display ops, RGB24 source of RGB24_TO_SURF */
     jmc_frames rgb;
     int32_t    rgb_pitch;     /* bytes per RGB row, >= 3*width (>= 4*width for ARGB32)          */
     uint32_t   flags;         /* JMC_JOB_*                                                      */
@@ -133,6 +137,9 @@ JMC_API int jmc_job_nvenc(jmc_job *job, int width, int height, int stride, int i
 JMC_API int jmc_job_rgb(jmc_job *job, int width, int height, int pitch, int rgb_pitch, int fused);
 /* NV12_TO_ARGB32 on an nv_dec-style surface; the ARGB frames go to job->rgb, row pitch argb_pitch >= 4*width. */
 JMC_API int jmc_job_argb(jmc_job *job, int width, int height, int pitch, int argb_pitch);
+/* RGB24_TO_SURF into an nv_enc-style surface (Y at 0, UV at stride*height, nv_enc.cpp:1069); the RGB frames are
+ * read from job->rgb, row pitch rgb_pitch >= 3*width.  Not a jmc_pipeline op. */
+JMC_API int jmc_job_rgb_to_nv12(jmc_job *job, int width, int height, int rgb_pitch, int stride);
 /* Bytes of one tight frame as the reference computes it: w*h*3/2 (nv_dec.cpp:773,824). */
 JMC_API int64_t jmc_tight_bytes(int width, int height);
 /* Algorithmic bytes (read + write, padding excluded) one frame of `job` moves: the roofline numerator. */

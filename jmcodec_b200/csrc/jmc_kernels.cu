@@ -414,6 +414,30 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     return JMC_OK;
 }
 
+static int launch_rgb_to_nv12(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
+{
+    if (!frames_ok(j->surf) || !frames_ok(j->rgb)) { jmc_set_error("jmc_convert: surf/rgb frame set is empty"); return JMC_ERR_INVALID; }
+    if (j->rgb_pitch < 3 * j->width) { jmc_set_error("jmc_convert: rgb_pitch %d < 3*width", j->rgb_pitch); return JMC_ERR_INVALID; }
+    Rgb2Params p;
+    p.rgb = to_set(j->rgb);
+    p.surf = to_set(j->surf);
+    p.n_frames = (uint32_t)j->n_frames;
+    p.width = j->width; p.height = j->height; p.pitch = j->pitch; p.rgb_pitch = j->rgb_pitch;
+    p.y_off = j->surf_y_off; p.uv_off = j->surf_uv_off;
+    p.row_pairs = ((uint32_t)j->height + 1) / 2;
+    p.segs_per_row = ((uint32_t)j->width + 511) / 512;
+    p.tasks_per_frame = p.row_pairs * p.segs_per_row;
+    const uint64_t total = (uint64_t)p.tasks_per_frame * p.n_frames;
+    if (total == 0) return JMC_OK;
+    if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }
+    p.total_tasks = (uint32_t)total;
+    constexpr uint32_t WARPS = RGB2_THREADS / 32;
+    rgb_to_nv12_kernel<<<(p.total_tasks + WARPS - 1) / WARPS, RGB2_THREADS, 0, stream>>>(p);
+    JMC_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return JMC_OK;
+}
+
 int jmc_launch_job(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
 {
     if (!ctx || !j) { jmc_set_error("jmc_convert: NULL ctx/job"); return JMC_ERR_INVALID; }
@@ -431,6 +455,8 @@ int jmc_launch_job(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     case JMC_OP_NV12_TO_I420_RGB24:
     case JMC_OP_NV12_TO_ARGB32:
         return launch_rgb(ctx, j, stream);
+    case JMC_OP_RGB24_TO_SURF:
+        return launch_rgb_to_nv12(ctx, j, stream);
     default:
         jmc_set_error("jmc_convert: unknown op %d", j->op);
         return JMC_ERR_INVALID;

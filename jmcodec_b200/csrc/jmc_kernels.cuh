@@ -1393,4 +1393,114 @@ __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid
     }
 }
 
+/* ========================================================================================== */
+/* RGB24 -> pitched NV12 (forward integer BT.601, chroma from 2x2 block sums)                  */
+/* ========================================================================================== */
+/* One warp per (row pair, 512-pixel segment).  The RGB rows sit at arbitrary addresses (3*w bytes per
+ * row), so they come in through ShiftedLoad (aligned 16-byte loads, all in flight together, re-aligned by
+ * shuffle + funnel shift into warp-private shared memory); each lane then owns 16 pixels x 2 rows = 2 x 48
+ * bytes.  A pixel is cut out of its three-word group with one prmt (the fourth byte meets a zero
+ * coefficient), Y is one dp4a per pixel, U and V four dp4a each per 2x2 block (dp4a is linear, so the
+ * block sum never has to be formed).  Surface rows get 16 bytes per lane; prefix stores at the row end
+ * keep the padding untouched. */
+struct Rgb2Params {
+    FrameSet rgb, surf;
+    uint32_t n_frames;
+    int32_t width, height, pitch, rgb_pitch;
+    int64_t y_off, uv_off;
+    uint32_t row_pairs, segs_per_row, tasks_per_frame, total_tasks;
+};
+
+constexpr uint32_t FWD_Y = 66u | (129u << 8) | (25u << 16);                 /* R,G,B -> Y, unsigned bytes */
+constexpr uint32_t FWD_U = 0xDAu | (0xB6u << 8) | (0x70u << 16);            /* -38, -74, 112 as signed bytes */
+constexpr uint32_t FWD_V = 0x70u | (0xA2u << 8) | (0xEEu << 16);            /* 112, -94, -18 */
+constexpr int FWD_Y_BIAS = 128 + 16 * 256, FWD_C_BIAS = 512 + 128 * 1024;
+
+__device__ __forceinline__ int dp4a_us(uint32_t a_u8x4, uint32_t b_s8x4, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a_u8x4), "r"(b_s8x4), "r"(c));
+    return d;
+}
+
+/* the four pixels (R,G,B,x) of a 12-byte group a,b,c */
+__device__ __forceinline__ void cut4(uint32_t a, uint32_t b, uint32_t c, uint32_t (&px)[4])
+{
+    px[0] = a;
+    px[1] = __byte_perm(a, b, 0x6543);
+    px[2] = __byte_perm(b, c, 0x5432);
+    px[3] = c >> 8;
+}
+
+constexpr int RGB2_THREADS = 128;
+constexpr int RGB2_ROW = 1536 + 32;                   /* staged bytes per RGB row segment + spare chunks */
+
+__global__ void __launch_bounds__(RGB2_THREADS, 8) rgb_to_nv12_kernel(const __grid_constant__ Rgb2Params p)
+{
+    constexpr int WARPS = RGB2_THREADS / 32;
+    __shared__ __align__(16) uint8_t stage[WARPS][2 * RGB2_ROW];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t task = blockIdx.x * WARPS + wib;
+    if (task >= p.total_tasks) return;
+    const uint32_t f = task / p.tasks_per_frame;
+    const uint32_t r = task - f * p.tasks_per_frame;
+    const uint32_t rp = r / p.segs_per_row, seg = r - rp * p.segs_per_row;
+    const uint32_t w = (uint32_t)p.width, h = (uint32_t)p.height, cw = w >> 1, ch = h >> 1;
+    const uint32_t y0 = 2 * rp, x0 = seg * 512;
+    const bool two = y0 + 1 < h, do_uv = rp < ch;
+    const uint32_t seg_px = min(512u, w - x0);
+    const uint8_t *src = frame_ptr(p.rgb, f) + (size_t)y0 * p.rgb_pitch + 3 * (size_t)x0;
+    uint8_t *sp = frame_ptr(p.surf, f);
+    uint8_t *A0 = stage[wib], *A1 = A0 + RGB2_ROW;
+    {
+        ShiftedLoad<3> l0, l1;
+        l0.issue(src, 3 * seg_px, lane);
+        if (two) l1.issue(src + p.rgb_pitch, 3 * seg_px, lane);
+        l0.commit(A0, 3 * seg_px, lane);
+        if (two) l1.commit(A1, 3 * seg_px, lane);
+    }
+    __syncwarp();
+    const uint32_t px0 = 16 * lane;
+    if (px0 >= seg_px) return;
+    const uint32_t npx = min(16u, seg_px - px0);
+    uint32_t ya[4], yb[4], uvw[4];
+    uint32_t r0[12], r1[12];                                                /* this lane's 16 pixels of both rows */
+#pragma unroll
+    for (int m = 0; m < 3; m++) {                                           /* 48-byte lane stride: conflict-free LDS.128 */
+        const uint4 a = *(const uint4 *)(A0 + 48 * lane + 16 * m);
+        const uint4 b = two ? *(const uint4 *)(A1 + 48 * lane + 16 * m) : make_uint4(0, 0, 0, 0);
+        r0[4 * m] = a.x; r0[4 * m + 1] = a.y; r0[4 * m + 2] = a.z; r0[4 * m + 3] = a.w;
+        r1[4 * m] = b.x; r1[4 * m + 1] = b.y; r1[4 * m + 2] = b.z; r1[4 * m + 3] = b.w;
+    }
+#pragma unroll
+    for (int g = 0; g < 4; g++) {                                           /* 4 pixels = 12 bytes per row */
+        uint32_t pa[4], pb[4];
+        cut4(r0[3 * g], r0[3 * g + 1], r0[3 * g + 2], pa);
+        cut4(r1[3 * g], r1[3 * g + 1], r1[3 * g + 2], pb);
+        uint32_t t[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[k] = __dp4a(pa[k], FWD_Y, (uint32_t)FWD_Y_BIAS);       /* Y in byte 1 */
+        ya[g] = __byte_perm(__byte_perm(t[0], t[1], 0x0051), __byte_perm(t[2], t[3], 0x0051), 0x5410);
+#pragma unroll
+        for (int k = 0; k < 4; k++) t[k] = __dp4a(pb[k], FWD_Y, (uint32_t)FWD_Y_BIAS);
+        yb[g] = __byte_perm(__byte_perm(t[0], t[1], 0x0051), __byte_perm(t[2], t[3], 0x0051), 0x5410);
+        uint32_t c[4];                                                      /* U0 V0 U1 V1 of the two 2x2 blocks */
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            const int u = dp4a_us(pa[2 * b], FWD_U, dp4a_us(pa[2 * b + 1], FWD_U, dp4a_us(pb[2 * b], FWD_U, dp4a_us(pb[2 * b + 1], FWD_U, FWD_C_BIAS))));
+            const int v = dp4a_us(pa[2 * b], FWD_V, dp4a_us(pa[2 * b + 1], FWD_V, dp4a_us(pb[2 * b], FWD_V, dp4a_us(pb[2 * b + 1], FWD_V, FWD_C_BIAS))));
+            c[2 * b] = (uint32_t)u >> 10;
+            c[2 * b + 1] = (uint32_t)v >> 10;
+        }
+        uvw[g] = __byte_perm(__byte_perm(c[0], c[1], 0x0040), __byte_perm(c[2], c[3], 0x0040), 0x5410);
+    }
+    uint8_t *yrow = sp + p.y_off + (size_t)y0 * p.pitch + x0 + px0;
+    store_prefix<4>(yrow, ya, npx);
+    if (two) store_prefix<4>(yrow + p.pitch, yb, npx);
+    if (do_uv) {
+        const uint32_t pair0 = (x0 + px0) >> 1;                             /* first chroma pair of this lane */
+        if (pair0 < cw) store_prefix<4>(sp + p.uv_off + (size_t)rp * p.pitch + x0 + px0, uvw, 2 * min(8u, cw - pair0));
+    }
+}
+
 } /* namespace jmc */

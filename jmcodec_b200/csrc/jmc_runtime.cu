@@ -243,6 +243,16 @@ int jmc_job_argb(jmc_job *j, int width, int height, int pitch, int argb_pitch)
     return JMC_OK;
 }
 
+int jmc_job_rgb_to_nv12(jmc_job *j, int width, int height, int rgb_pitch, int stride)
+{
+    int r = jmc_job_nvenc(j, width, height, stride, 0x1);        /* surface geometry of nv_enc.cpp:1029-1069 */
+    if (r) return r;
+    if (rgb_pitch < 3 * width) { jmc_set_error("jmc_job_rgb_to_nv12: rgb_pitch < 3*width"); return JMC_ERR_INVALID; }
+    j->op = JMC_OP_RGB24_TO_SURF;
+    j->rgb_pitch = rgb_pitch;
+    return JMC_OK;
+}
+
 int64_t jmc_job_algorithmic_bytes(const jmc_job *j)
 {
     if (!j) return 0;
@@ -256,6 +266,7 @@ int64_t jmc_job_algorithmic_bytes(const jmc_job *j)
     switch (j->op) {
     case JMC_OP_NV12_TO_RGB24: return luma + w * ((h + 1) >> 1) + 3 * luma;          /* reads every chroma row it uses */
     case JMC_OP_NV12_TO_ARGB32: return luma + w * ((h + 1) >> 1) + 4 * luma;
+    case JMC_OP_RGB24_TO_SURF: return 3 * luma + luma + 2 * (w >> 1) * (h >> 1);
     case JMC_OP_NV12_TO_I420_RGB24: return luma + w * ((h + 1) >> 1) + yuv + 3 * luma;
     default: return 2 * yuv;
     }

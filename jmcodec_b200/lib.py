@@ -29,6 +29,7 @@ class JMC_OP(enum.IntEnum):
     NV12_TO_RGB24 = 4
     NV12_TO_I420_RGB24 = 5
     NV12_TO_ARGB32 = 6
+    RGB24_TO_SURF = 7
 
 
 JOB_ALIGNED16 = 1
@@ -98,6 +99,7 @@ _SIGS = {
     "jmc_job_nvenc": (C.c_int, [C.POINTER(Job)] + [C.c_int] * 4),
     "jmc_job_rgb": (C.c_int, [C.POINTER(Job)] + [C.c_int] * 5),
     "jmc_job_argb": (C.c_int, [C.POINTER(Job)] + [C.c_int] * 4),
+    "jmc_job_rgb_to_nv12": (C.c_int, [C.POINTER(Job)] + [C.c_int] * 4),
     "jmc_tight_bytes": (C.c_int64, [C.c_int, C.c_int]),
     "jmc_job_algorithmic_bytes": (C.c_int64, [C.POINTER(Job)]),
     "jmc_convert": (C.c_int, [C.c_void_p, C.POINTER(Job), C.c_void_p]),
@@ -306,6 +308,11 @@ class Ctx:
     def job_argb(self, w, h, pitch, argb_pitch) -> Job:
         j = Job()
         _ck(self.L.jmc_job_argb(C.byref(j), w, h, pitch, argb_pitch), "jmc_job_argb")
+        return j
+
+    def job_rgb_to_nv12(self, w, h, rgb_pitch, stride) -> Job:
+        j = Job()
+        _ck(self.L.jmc_job_rgb_to_nv12(C.byref(j), w, h, rgb_pitch, stride), "jmc_job_rgb_to_nv12")
         return j
 
     def algorithmic_bytes(self, job: Job) -> int:

@@ -57,6 +57,8 @@ class _Port:
         L.jmo_nv12_to_rgb24.restype = C.c_int
         L.jmo_nv12_to_argb32.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
         L.jmo_nv12_to_argb32.restype = C.c_int
+        L.jmo_rgb24_to_nv12.argtypes = [_u8p, C.c_int, C.c_int, C.c_int, _u8p, C.c_int]
+        L.jmo_rgb24_to_nv12.restype = C.c_int
         L.jmo_nvdec_run.argtypes = [_u8p, C.c_size_t, C.c_int, _u8p, C.c_size_t, C.c_int] + [C.c_int] * 6
         L.jmo_nvdec_run.restype = C.c_double
         self.L = L
@@ -200,3 +202,7 @@ def nv12_to_rgb24(surf, pitch, w, h, rgb, rgb_pitch):
 
 def nv12_to_argb32(surf, pitch, w, h, argb, argb_pitch):
     return port().impl.L.jmo_nv12_to_argb32(_ptr(surf), pitch, w, h, _ptr(argb), argb_pitch)
+
+
+def rgb24_to_nv12(rgb, rgb_pitch, w, h, surf, pitch):
+    return port().impl.L.jmo_rgb24_to_nv12(_ptr(rgb), rgb_pitch, w, h, _ptr(surf), pitch)

@@ -195,6 +195,35 @@ int jmo_nv12_to_argb32(const uint8_t *surf, int pitch, int width, int height,
     return 0;
 }
 
+/* builder-defined spec, see jm_oracle.h (PARITY UNPINNED) */
+int jmo_rgb24_to_nv12(const uint8_t *rgb, int rgb_pitch, int width, int height,
+                      uint8_t *surf, int pitch)
+{
+    const int cw = width >> 1, ch = height >> 1;
+    if (width < 1 || height < 1) return -1;
+    for (int y = 0; y < height; y++) {
+        const uint8_t *p = rgb + (size_t)y * rgb_pitch;
+        uint8_t *yr = surf + (size_t)y * pitch;
+        for (int x = 0; x < width; x++)
+            yr[x] = (uint8_t)((66 * p[3 * x] + 129 * p[3 * x + 1] + 25 * p[3 * x + 2] + 128 + 16 * 256) >> 8);
+    }
+    uint8_t *uvp = surf + (size_t)pitch * height;
+    for (int cy = 0; cy < ch; cy++) {
+        const uint8_t *p0 = rgb + (size_t)(2 * cy) * rgb_pitch, *p1 = p0 + rgb_pitch;
+        uint8_t *o = uvp + (size_t)cy * pitch;
+        for (int cx = 0; cx < cw; cx++) {
+            const int a = 6 * cx;                                   /* pixels 2cx, 2cx+1 of both rows */
+            const int r = p0[a] + p0[a + 3] + p1[a] + p1[a + 3];
+            const int g = p0[a + 1] + p0[a + 4] + p1[a + 1] + p1[a + 4];
+            const int b = p0[a + 2] + p0[a + 5] + p1[a + 2] + p1[a + 5];
+            /* + 128*1024 keeps the sum positive, so >> is a floor whatever the compiler does with negatives */
+            o[2 * cx] = (uint8_t)((-38 * r - 74 * g + 112 * b + 512 + 128 * 1024) >> 10);
+            o[2 * cx + 1] = (uint8_t)((112 * r - 94 * g - 18 * b + 512 + 128 * 1024) >> 10);
+        }
+    }
+    return 0;
+}
+
 /* ---- "port" CPU baseline loop ---- */
 typedef struct {
     const uint8_t *surf_base; size_t surf_stride; int n_surf;

@@ -76,6 +76,17 @@ int jmo_nv12_to_rgb24(const uint8_t *surf, int pitch, int width, int height,
 int jmo_nv12_to_argb32(const uint8_t *surf, int pitch, int width, int height,
                        uint8_t *argb, int argb_pitch);
 
+/* Builder-defined (PARITY UNPINNED; SURVEY 8f rank 4 "RGB -> NV12 would complete a transcode loop"): the
+ * forward BT.601 limited-range integer transform, the counterpart of jmo_nv12_to_rgb24:
+ *   Y = ((66R + 129G + 25B + 128) >> 8) + 16                      per pixel
+ *   U = floor((-38Rs - 74Gs + 112Bs + 512) / 1024) + 128          Rs,Gs,Bs = sums over the 2x2 block
+ *   V = floor((112Rs - 94Gs - 18Bs + 512) / 1024) + 128
+ * into an nv_enc-style pitched NV12 surface (Y at 0, UV at pitch*height, nv_enc.cpp:1069); chroma has
+ * (w>>1) x (h>>1) samples, an odd last column / row contributes luma only; padding is not written.
+ * Returns -1 if w<1 or h<1, else 0. */
+int jmo_rgb24_to_nv12(const uint8_t *rgb, int rgb_pitch, int width, int height,
+                      uint8_t *surf, int pitch);
+
 /* "port" CPU baseline: frames calls of jmo_nvdec_output_frame, frame f reading surface
  * f % n_surf and writing slot f % n_out, round-robin over nthreads.  Returns seconds or -1. */
 double jmo_nvdec_run(const uint8_t *surf_base, size_t surf_stride, int n_surf,

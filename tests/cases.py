@@ -94,8 +94,19 @@ def argb_cases():
     return out
 
 
+def rgb2nv12_cases():
+    """RGB24 -> pitched NV12 (builder-defined forward BT.601): rgb_pitch = 3*w + skew, surface pitch p."""
+    out = []
+    for (w, h, p) in RGB_SIZES + [(1366, 768, 1536), (1, 1, 16), (2, 1, 16), (1, 2, 16)]:
+        for skew in ((0, 5) if w * h <= 64 * 64 else (0,)):
+            kinds = ["random"] + (["const0", "const255", "primaries"] if w * h <= 64 * 64 and skew == 0 else [])
+            for k in kinds:
+                out.append(dict(op="rgb2nv12", w=w, h=h, pitch=p, skew=skew, kind=k))
+    return out
+
+
 def all_cases():
-    return nvdec_cases() + inteldec_cases() + intelenc_cases() + nvenc_cases() + rgb_cases() + argb_cases()
+    return nvdec_cases() + inteldec_cases() + intelenc_cases() + nvenc_cases() + rgb_cases() + argb_cases() + rgb2nv12_cases()
 
 
 def case_id(c: dict) -> str:
@@ -208,7 +219,34 @@ def run_argb(_chk, c):
     return r, pitch4 * c["h"], out
 
 
-RUNNERS = {"argb32": run_argb, "nvdec": run_nvdec, "inteldec": run_inteldec, "intelenc": run_intelenc,
+def rgb2nv12_input(c):
+    """Tight-ish RGB24 rows: 3*w bytes of pixels then `skew` pad bytes per row."""
+    w, h, rp = c["w"], c["h"], 3 * c["w"] + c["skew"]
+    if c["kind"] == "random":
+        a = synth.random_bytes(rp * h, synth.frame_key(9, w * 131 + h) ^ 0x0F0F0F0F)
+    elif c["kind"] == "primaries":
+        pal = np.array([[255, 0, 0], [0, 255, 0], [0, 0, 255], [255, 255, 0], [0, 255, 255], [255, 0, 255], [255, 255, 255], [0, 0, 0]], np.uint8)
+        a = np.full((h, rp), synth.PAD_BYTE, np.uint8)
+        for y in range(h):
+            a[y, :3 * w] = pal[(np.arange(w) // 2 + y // 2) % 8].reshape(-1)
+        a = a.reshape(-1)
+    else:
+        a = np.full(rp * h, int(c["kind"][5:]), np.uint8)
+    return a
+
+
+def rgb2nv12_surface_bytes(c):
+    return c["pitch"] * (c["h"] + (c["h"] >> 1) + 1)
+
+
+def run_rgb2nv12(_chk, c):
+    import oracle
+    surf = np.full(rgb2nv12_surface_bytes(c), synth.PAD_BYTE, np.uint8)
+    r = oracle.rgb24_to_nv12(rgb2nv12_input(c), 3 * c["w"] + c["skew"], c["w"], c["h"], surf, c["pitch"])
+    return r, surf.size, surf
+
+
+RUNNERS = {"rgb2nv12": run_rgb2nv12, "argb32": run_argb, "nvdec": run_nvdec, "inteldec": run_inteldec, "intelenc": run_intelenc,
            "nvenc": run_nvenc, "rgb24": run_rgb}
 # ops for which the unmodified reference has CPU code that oracle/_ref executes
 REF_OPS = ("nvdec", "inteldec", "intelenc", "nvenc")

@@ -38,7 +38,7 @@ def main():
         r, n, out = K.run_case(ref if from_ref else port, c)
         e = {"ret": int(r), "out_len": int(n), "nbytes": int(out.size), "sha256": K.sha(out),
              "source": "reference" if from_ref else "port"}
-        if c["op"] in ("rgb24", "argb32"):
+        if c["op"] in ("rgb24", "argb32", "rgb2nv12"):
             e["parity"] = "unpinned"
         if out.size <= 512:
             e["hex"] = out.tobytes().hex()

@@ -110,7 +110,20 @@ def gpu_argb(ctx, c):
     return out
 
 
-GPU_RUNNERS = {"argb32": gpu_argb, "nvdec": gpu_nvdec, "inteldec": gpu_inteldec, "intelenc": gpu_intelenc, "nvenc": gpu_nvenc, "rgb24": gpu_rgb}
+def gpu_rgb2nv12(ctx, c):
+    rgb = K.rgb2nv12_input(c)
+    w, h = c["w"], c["h"]
+    nsurf = K.rgb2nv12_surface_bytes(c)
+    drgb, dsurf = ctx.upload(rgb), _dev_filled(ctx, nsurf, synth.PAD_BYTE)
+    j = ctx.job_rgb_to_nv12(w, h, 3 * w + c["skew"], c["pitch"])
+    j.n_frames, j.rgb.base, j.surf.base = 1, drgb, dsurf
+    ctx.convert(j)
+    out = _download(ctx, dsurf, nsurf)
+    ctx.free(drgb), ctx.free(dsurf)
+    return out
+
+
+GPU_RUNNERS = {"rgb2nv12": gpu_rgb2nv12, "argb32": gpu_argb, "nvdec": gpu_nvdec, "inteldec": gpu_inteldec, "intelenc": gpu_intelenc, "nvenc": gpu_nvenc, "rgb24": gpu_rgb}
 
 
 def run_case_gpu(ctx, c):

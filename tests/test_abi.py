@@ -105,6 +105,17 @@ def test_algorithmic_bytes(lib):
     assert lib.jmc_job_algorithmic_bytes(C.byref(j)) == 45619200
 
 
+def test_job_rgb_to_nv12_filler(lib):
+    w, h, s_ = 1366, 768, 1536
+    r, j = _job("jmc_job_rgb_to_nv12", w, h, 3 * w, s_)
+    assert r == 0 and j.op == J.JMC_OP.RGB24_TO_SURF
+    assert (j.width, j.height, j.pitch, j.rgb_pitch) == (w, h, s_, 3 * w)
+    assert (j.surf_y_off, j.surf_uv_off) == (0, s_ * h)                        # nv_enc.cpp:1069
+    assert lib.jmc_job_algorithmic_bytes(C.byref(j)) == 3 * w * h + w * h + 2 * (w >> 1) * (h >> 1)
+    assert _job("jmc_job_rgb_to_nv12", w, h, 3 * w - 1, s_)[0] == -1
+    assert _job("jmc_job_rgb_to_nv12", w, h, 3 * w, w - 1)[0] == -1
+
+
 def test_job_argb_filler(lib):
     w, h, p = 1366, 768, 1536
     r, j = _job("jmc_job_argb", w, h, p, 4 * w)

@@ -316,6 +316,43 @@ def test_random_widths_rgb_on_aligned_surfaces(ctx, seed, always, monkeypatch):
         ctx.free(dsurf)
 
 
+@pytest.mark.parametrize("seed", range(3))
+def test_rgb24_to_nv12_random_geometries(ctx, seed):
+    """Forward transform: random sizes, RGB rows at any address / pitch, surfaces aligned or not, batched (stride and
+    pointer-list modes), against the oracle including every byte that must stay untouched."""
+    rng = np.random.default_rng(5000 + seed)
+    for it in range(16):
+        w, h = int(rng.integers(1, 1400)), int(rng.integers(1, 30))
+        n = int(rng.integers(1, 4))
+        rp = 3 * w + int(rng.integers(0, 9))
+        pitch = (((w + 15) & ~15) + 16 * int(rng.integers(0, 3))) if it % 3 else w + int(rng.integers(0, 7))
+        kr, ks = int(rng.integers(0, 16)), (0 if it % 3 else int(rng.integers(0, 16)))
+        rgb_bytes, surf_bytes = rp * h + 7, pitch * (h + (h >> 1) + 1)
+        rgbs = [rng.integers(0, 256, rgb_bytes, dtype=np.uint8) for _ in range(n)]
+        drgb, dsurf = ctx.alloc(n * rgb_bytes + 64), ctx.alloc(n * surf_bytes + 64)
+        ctx.h2d(drgb + kr, np.concatenate(rgbs))
+        ctx.memset(dsurf, synth.PAD_BYTE, n * surf_bytes + 64)
+        j = ctx.job_rgb_to_nv12(w, h, rp, pitch)
+        j.n_frames = n
+        dl = None
+        if it % 2:
+            j.rgb.base, j.rgb.stride, j.surf.base, j.surf.stride = drgb + kr, rgb_bytes, dsurf + ks, surf_bytes
+        else:
+            dl = (G.device_ptr_array(ctx, [drgb + kr + f * rgb_bytes for f in range(n)]),
+                  G.device_ptr_array(ctx, [dsurf + ks + f * surf_bytes for f in range(n)]))
+            j.rgb.list, j.surf.list = dl
+        ctx.convert(j)
+        got = np.empty(n * surf_bytes, np.uint8)
+        ctx.d2h(got, dsurf + ks)
+        for f in range(n):
+            want = np.full(surf_bytes, synth.PAD_BYTE, np.uint8)
+            assert oracle.rgb24_to_nv12(rgbs[f], rp, w, h, want, pitch) == 0
+            assert np.array_equal(got[f * surf_bytes:(f + 1) * surf_bytes], want), (w, h, rp, pitch, kr, ks, f)
+        ctx.free(drgb), ctx.free(dsurf)
+        if dl:
+            ctx.free(dl[0]), ctx.free(dl[1])
+
+
 @pytest.mark.parametrize("kernels", ["bulk_rows", "ldg_rows", "ldg_rows_always"])
 @pytest.mark.parametrize("seed", range(4))
 def test_random_widths_on_aligned_surfaces(ctx, seed, kernels, monkeypatch):

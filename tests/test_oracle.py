@@ -151,3 +151,27 @@ def test_port_matches_compiled_reference_on_random_geometries(seed):
             ra = oracle.nvenc_upload(tight, fmt, w, h, a, stride)
             rb, _ = oracle.ref_nvenc_convert(tight, fmt, w, h, b, stride)
             assert ra == rb and np.array_equal(a, b), ("nvenc", w, h, stride, hex(fmt))
+
+
+def test_forward_bt601_known_points():
+    """Builder-defined forward transform (parity unpinned): the textbook limited-range values of the primaries, and
+    chroma taken from the 2x2 block SUM (one red pixel in a black block moves U,V a quarter of the way)."""
+    def blk(px):                         # px: four (r,g,b) of one 2x2 block, row-major
+        rgb = np.array(px, np.uint8).reshape(2, 6)
+        s = np.zeros(2 * 2 + 2, np.uint8)
+        assert oracle.rgb24_to_nv12(rgb.reshape(-1), 6, 2, 2, s, 2) == 0
+        return [int(x) for x in s]
+    assert blk([(0, 0, 0)] * 4) == [16, 16, 16, 16, 128, 128]
+    assert blk([(255, 255, 255)] * 4) == [235, 235, 235, 235, 128, 128]
+    assert blk([(255, 0, 0)] * 4) == [82, 82, 82, 82, 90, 240]
+    assert blk([(0, 255, 0)] * 4) == [144, 144, 144, 144, 54, 34]
+    assert blk([(0, 0, 255)] * 4) == [41, 41, 41, 41, 240, 110]
+    one_red = blk([(255, 0, 0), (0, 0, 0), (0, 0, 0), (0, 0, 0)])
+    assert one_red[:4] == [82, 16, 16, 16] and one_red[4:] == [(-38 * 255 + 512 + 131072) >> 10, (112 * 255 + 512 + 131072) >> 10]
+    # odd sizes: the last column / row has luma only, padding and the missing chroma stay untouched
+    s = np.full(16 * 5, 0xCD, np.uint8)                    # 3 luma rows + 1 chroma row (h>>1) + one spare row
+    assert oracle.rgb24_to_nv12(np.full(27, 255, np.uint8), 9, 3, 3, s, 16) == 0
+    assert [int(x) for x in s[32:36]] == [235, 235, 235, 0xCD]           # third luma row: 3 pixels, then padding
+    assert [int(x) for x in s[48:52]] == [128, 128, 0xCD, 0xCD]          # one chroma pair (w>>1), then padding
+    assert (s[64:] == 0xCD).all()                                        # no second chroma row (h>>1 == 1)
+    assert oracle.rgb24_to_nv12(np.zeros(3, np.uint8), 3, 0, 1, s, 16) == -1

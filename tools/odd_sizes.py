@@ -14,6 +14,8 @@ for name, spec in {
     "nv12 1366x768 p1536": ("nv12", 1366, 768, 1536, 300), "rgb 1080x1920 p1088": ("rgb", 1080, 1920, 1088, 150),
     "rgb 1366x768 p1536": ("rgb", 1366, 768, 1536, 300), "argb 1366x768 p1536": ("argb", 1366, 768, 1536, 300),
     "fused 1366x768 p1536": ("fused", 1366, 768, 1536, 300), "argb 3840x2160 p4096": ("argb", 3840, 2160, 4096, 64),
+    "rgb2nv12 3840x2160 p4096": ("rgb2nv12", 3840, 2160, 4096, 64), "rgb2nv12 1920x1080 p2048": ("rgb2nv12", 1920, 1080, 2048, 200),
+    "rgb2nv12 1366x768 p1536": ("rgb2nv12", 1366, 768, 1536, 300),
 }.items():
     if len(sys.argv) > 1 and not any((a[1:] == name) if a.startswith('=') else (a in name) for a in sys.argv[1:]):
         continue
