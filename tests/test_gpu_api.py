@@ -426,6 +426,44 @@ def test_full_size_rgb_batch_samples(ctx):
         ctx.free(d)
 
 
+def test_full_size_transcode_loop_property(ctx):
+    """16 x 4K: NV12 -> RGB24 -> NV12 on the device.  The chain is lossy in general, but for grey frames in the legal
+    range (Y 16..235, U = V = 128) it must return chroma exactly and luma within 1 (a property of the two integer
+    transforms, checked on the oracle for every Y); sampled frames of the second hop are compared with the oracle."""
+    w, h, pitch, n = 3840, 2160, 4096, 16
+    surf_bytes, rgb_bytes = pitch * h * 3 // 2, 3 * w * h
+    rng = np.random.default_rng(77)
+    base = []
+    for f in range(2):
+        s = np.full((h * 3 // 2, pitch), synth.PAD_BYTE, np.uint8)
+        s[:h, :w] = rng.integers(16, 236, (h, w), dtype=np.uint8)
+        s[h:, :w] = 128
+        base.append(s.reshape(-1))
+    dsurf, drgb, dback = ctx.alloc(n * surf_bytes), ctx.alloc(n * rgb_bytes), ctx.alloc(n * surf_bytes)
+    for f in range(n):
+        ctx.h2d(dsurf + f * surf_bytes, base[f % 2])
+    ctx.memset(dback, synth.PAD_BYTE, n * surf_bytes)
+    j = ctx.job_rgb(w, h, pitch, 3 * w, False)
+    j.n_frames, j.surf.base, j.surf.stride, j.rgb.base, j.rgb.stride = n, dsurf, surf_bytes, drgb, rgb_bytes
+    ctx.convert(j)
+    k = ctx.job_rgb_to_nv12(w, h, 3 * w, pitch)
+    k.n_frames, k.rgb.base, k.rgb.stride, k.surf.base, k.surf.stride = n, drgb, rgb_bytes, dback, surf_bytes
+    ctx.convert(k)
+    back, rgb = np.empty(surf_bytes, np.uint8), np.empty(rgb_bytes, np.uint8)
+    want = np.empty(surf_bytes, np.uint8)
+    for f in (0, 1, 7, 15):
+        ctx.d2h(back, dback + f * surf_bytes)
+        a, b = back.reshape(-1, pitch), base[f % 2].reshape(-1, pitch)
+        assert np.abs(a[:h, :w].astype(np.int16) - b[:h, :w].astype(np.int16)).max() <= 1
+        assert (a[h:, :w] == 128).all() and (a[:, w:] == synth.PAD_BYTE).all()
+        ctx.d2h(rgb, drgb + f * rgb_bytes)
+        want[:] = synth.PAD_BYTE
+        assert oracle.rgb24_to_nv12(rgb, 3 * w, w, h, want, pitch) == 0
+        assert np.array_equal(back, want)
+    for d in (dsurf, drgb, dback):
+        ctx.free(d)
+
+
 def test_pipeline_argument_errors_and_depth_one(J, ctx):
     w, h, pitch, batch = 64, 32, 64, 4
     surf_bytes, tight_bytes = pitch * h * 3 // 2, w * h * 3 // 2
