@@ -53,28 +53,22 @@ typedef void *handle_nvenc;
 
 #define JM_NVENC_NUM_SURFACES 10             /* MAX_NV_ENC_FRAME_NUM, nv_enc/nv_enc.h:99 */
 
-typedef struct _nv_enc_param
-{
-	int			codec_id;	/* JM_NVENC_H264 / JM_NVENC_HEVC / JM_NVENC_CODEC_SURFACE_ONLY */
-	int			in_fmt;		/* NV_ENC_BUFFER_FORMAT */
-	int			preset;
-
-	int			src_width;
-	int			src_height;
-
-	int			dst_width;
-	int			dst_height;
-
-	int			fps;
-	int			bitrate_kb;
-	int			gop_len;
-	int			num_bframe;
-
-	int         is_external_alloc;	/* 1: CUDA surface path (the one implemented here) */
-
-	int			qp;
-
-}nv_enc_param;
+/* Field order and types are the ABI (nv_enc/jmnv_enc.h:23-53): thirteen ints. */
+typedef struct _nv_enc_param {
+    int codec_id;           /* JM_NVENC_H264 / JM_NVENC_HEVC / JM_NVENC_CODEC_SURFACE_ONLY */
+    int in_fmt;             /* an NV_ENC_BUFFER_FORMAT value: JM_NVENC_FMT_* below */
+    int preset;             /* index into the NVENC preset GUIDs; unused without an encoder */
+    int src_width;          /* size of the frames handed to jm_nvenc_enc_frame */
+    int src_height;
+    int dst_width;          /* encoded size; unused without an encoder */
+    int dst_height;
+    int fps;
+    int bitrate_kb;
+    int gop_len;
+    int num_bframe;
+    int is_external_alloc;  /* 1: CUDA surface path (the one implemented here) */
+    int qp;
+} nv_enc_param;
 
 JMDLL_FUNC handle_nvenc jm_nvenc_create_handle(void);
 JMDLL_FUNC int jm_nvenc_init(nv_enc_param *in_param, handle_nvenc handle);

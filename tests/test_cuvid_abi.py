@@ -23,6 +23,16 @@ def test_cuvid_min_matches_the_reference_sdk_headers():
 
 
 @pytest.mark.skipif(not os.path.isdir(REF_INC), reason="/root/reference is not mounted here")
+def test_drop_in_headers_declare_the_reference_signatures():
+    """include/jm_nv_dec.h and include/jmnv_enc.h against nv_dec/jm_nv_dec.h and nv_enc/jmnv_enc.h: every entry point
+    has the reference's function type, nv_enc_param the reference's layout (tests/abi_check/api_signatures.cpp)."""
+    cmd = ["g++", "-std=gnu++11", "-fsyntax-only", "-I/root/reference", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "abi_check", "api_signatures.cpp")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stderr[-3000:]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_INC), reason="/root/reference is not mounted here")
 def test_the_layout_check_can_fail(tmp_path):
     """Guard against a vacuous check: a deliberately wrong assertion must stop the compile."""
     src = open(os.path.join(ROOT, "tests", "abi_check", "cuvid_layout.cpp")).read()
