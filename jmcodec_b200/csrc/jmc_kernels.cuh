@@ -526,13 +526,25 @@ template <int NW> __device__ __forceinline__ void store_prefix(uint8_t *dst, con
         else { *(uint32_t *)dst = wd[0]; *(uint32_t *)(dst + 4) = wd[1]; }
         return;
     }
-    const uint32_t nfull = (a & 3) == 0 ? (nbytes >> 2) : 0;              /* leading bytes that can go out as words */
+    if ((a & 3) == 0) {
+        /* row ends on aligned surfaces: whole words, then the last 1-3 bytes of the word that follows them
+         * (a dozen instructions; the byte loop below costs ~50 issue slots even when it stores nothing) */
+        const uint32_t nfull = nbytes >> 2, rem = nbytes & 3;
+        uint32_t last = wd[0];
 #pragma unroll
-    for (int i = 0; i < NW; i++)
-        if ((uint32_t)i < nfull) *(uint32_t *)(dst + 4 * i) = wd[i];
+        for (int i = 0; i < NW; i++) {
+            if ((uint32_t)i < nfull) *(uint32_t *)(dst + 4 * i) = wd[i];
+            if ((uint32_t)i == nfull) last = wd[i];
+        }
+        uint8_t *q = dst + 4 * nfull;
+        if (rem & 2) *(uint16_t *)q = (uint16_t)last;
+        if (rem == 1) q[0] = (uint8_t)last;
+        if (rem == 3) q[2] = (uint8_t)(last >> 16);
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 4 * NW; i++)
-        if ((uint32_t)i >= 4 * nfull && (uint32_t)i < nbytes) dst[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
+        if ((uint32_t)i < nbytes) dst[i] = (uint8_t)(wd[i >> 2] >> (8 * (i & 3)));
 }
 
 /* ========================================================================================== */
@@ -571,20 +583,30 @@ struct RowsParams {
     Part part[2];
 };
 
-/* words ws..ws+4 of the eight words of two consecutive 16-byte chunks (ws warp-uniform), funnel-shifted by sh bits */
-__device__ __forceinline__ uint4 shift_pair(const uint4 &P, const uint4 &Q, uint32_t ws, uint32_t sh)
+/* bytes 4*WS + sh/8 .. +16 of the 32 bytes of two consecutive 16-byte chunks: words WS..WS+4, funnel-shifted.
+ * WS is a template parameter and the callers branch on it ONCE per row (warp-uniform), outside their chunk
+ * loops: as a run-time switch per chunk the compiler if-converts it into a dozen selects per 16 bytes, which
+ * made the odd-width RGB kernels issue-bound (ncu: +48 % instructions, profiles/README.md). */
+template <int WS> __device__ __forceinline__ uint4 shift_pair_ws(const uint4 &P, const uint4 &Q, uint32_t sh)
 {
-    uint32_t x0, x1, x2, x3, x4;
-    switch (ws) {
-    case 0: x0 = P.x; x1 = P.y; x2 = P.z; x3 = P.w; x4 = Q.x; break;
-    case 1: x0 = P.y; x1 = P.z; x2 = P.w; x3 = Q.x; x4 = Q.y; break;
-    case 2: x0 = P.z; x1 = P.w; x2 = Q.x; x3 = Q.y; x4 = Q.z; break;
-    default: x0 = P.w; x1 = Q.x; x2 = Q.y; x3 = Q.z; x4 = Q.w; break;
-    }
+    const uint32_t x0 = WS == 0 ? P.x : WS == 1 ? P.y : WS == 2 ? P.z : P.w;
+    const uint32_t x1 = WS == 0 ? P.y : WS == 1 ? P.z : WS == 2 ? P.w : Q.x;
+    const uint32_t x2 = WS == 0 ? P.z : WS == 1 ? P.w : WS == 2 ? Q.x : Q.y;
+    const uint32_t x3 = WS == 0 ? P.w : WS == 1 ? Q.x : WS == 2 ? Q.y : Q.z;
+    const uint32_t x4 = WS == 0 ? Q.x : WS == 1 ? Q.y : WS == 2 ? Q.z : Q.w;
     uint4 o;
     o.x = __funnelshift_r(x0, x1, sh); o.y = __funnelshift_r(x1, x2, sh);
     o.z = __funnelshift_r(x2, x3, sh); o.w = __funnelshift_r(x3, x4, sh);
     return o;
+}
+__device__ __forceinline__ uint4 shift_pair(const uint4 &P, const uint4 &Q, uint32_t ws, uint32_t sh)
+{
+    switch (ws) {
+    case 0: return shift_pair_ws<0>(P, Q, sh);
+    case 1: return shift_pair_ws<1>(P, Q, sh);
+    case 2: return shift_pair_ws<2>(P, Q, sh);
+    default: return shift_pair_ws<3>(P, Q, sh);
+    }
 }
 
 /* A staged buffer of nbytes -> dst (any alignment).  chunk(c) returns the shared-memory address of the
@@ -597,15 +619,23 @@ __device__ __forceinline__ void warp_store_shifted_map(uint8_t *dst, ChunkMap ch
     const uint32_t head = min(nbytes, (16u - ((uint32_t)(uintptr_t)dst & 15u)) & 15u);
     const uint32_t body = (nbytes - head) & ~15u;
     if (lane < head) dst[lane] = ((const uint8_t *)chunk(0))[lane];
-    const uint32_t sh = 8 * (head & 3), ws = head >> 2;
+    const uint32_t sh = 8 * (head & 3);
+#define JMC_SHIFTED_BODY(WS)                                                                                   \
+    for (uint32_t j = lane; j < body / 16; j += 32) {                                                          \
+        const uint4 P = *chunk(j), Q = *chunk(j + 1);                                                          \
+        *(uint4 *)(dst + head + 16 * (size_t)j) = shift_pair_ws<WS>(P, Q, sh);                                 \
+    }
     if (head == 0) {
         for (uint32_t j = lane; j < body / 16; j += 32) *(uint4 *)(dst + 16 * (size_t)j) = *chunk(j);
     } else {
-        for (uint32_t j = lane; j < body / 16; j += 32) {
-            const uint4 P = *chunk(j), Q = *chunk(j + 1);
-            *(uint4 *)(dst + head + 16 * (size_t)j) = shift_pair(P, Q, ws, sh);
+        switch (head >> 2) {                                                     /* warp-uniform, once per row */
+        case 0: JMC_SHIFTED_BODY(0) break;
+        case 1: JMC_SHIFTED_BODY(1) break;
+        case 2: JMC_SHIFTED_BODY(2) break;
+        default: JMC_SHIFTED_BODY(3) break;
         }
     }
+#undef JMC_SHIFTED_BODY
     const uint32_t t = head + body + lane;
     if (t < nbytes) dst[t] = ((const uint8_t *)chunk(t >> 4))[t & 15];
 }
@@ -645,6 +675,24 @@ template <int K> struct ShiftedLoad {
         if (i0 < nbytes) t0 = __ldg(src + i0);
         if (i1 < nbytes) t1 = __ldg(src + i1);
     }
+    template <int WS> __device__ __forceinline__ void commit_ws(uint8_t *sm, uint32_t lane) const
+    {
+        const uint32_t sh = 8 * (s & 3), nxt = (lane + 1) & 31;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            if (k * 32 >= (int)nout) break;                  /* warp-uniform */
+            const uint32_t j = k * 32 + lane;
+            /* lane l needs lane l+1's chunk; lane 31 needs lane 0's NEXT chunk.  Only the words that WS selects
+             * travel: words WS.. of the neighbour chunk are never used when they fall beyond word WS+4. */
+            const uint4 R = lane == 0 ? P[k + 1] : P[k];
+            uint4 Q = make_uint4(0, 0, 0, 0);
+            Q.x = __shfl_sync(0xffffffffu, R.x, nxt);
+            if (WS >= 1) Q.y = __shfl_sync(0xffffffffu, R.y, nxt);
+            if (WS >= 2) Q.z = __shfl_sync(0xffffffffu, R.z, nxt);
+            if (WS >= 3) Q.w = __shfl_sync(0xffffffffu, R.w, nxt);
+            if (j < nout) *(uint4 *)(sm + 16 * j) = shift_pair_ws<WS>(P[k], Q, sh);
+        }
+    }
     /* phase 2: re-align and store to shared memory */
     __device__ __forceinline__ void commit(uint8_t *sm, uint32_t nbytes, uint32_t lane) const
     {
@@ -652,16 +700,11 @@ template <int K> struct ShiftedLoad {
 #pragma unroll
             for (int k = 0; k < K; k++) { const uint32_t j = k * 32 + lane; if (j < nout) *(uint4 *)(sm + 16 * j) = P[k]; }
         } else {
-            const uint32_t sh = 8 * (s & 3), ws = s >> 2, nxt = (lane + 1) & 31;
-#pragma unroll
-            for (int k = 0; k < K; k++) {
-                if (k * 32 >= (int)nout) break;              /* warp-uniform */
-                const uint32_t j = k * 32 + lane;
-                const uint4 R = lane == 0 ? P[k + 1] : P[k]; /* lane l reads lane l+1's chunk j+1; lane 31 reads lane 0's next one */
-                uint4 Q;
-                Q.x = __shfl_sync(0xffffffffu, R.x, nxt); Q.y = __shfl_sync(0xffffffffu, R.y, nxt);
-                Q.z = __shfl_sync(0xffffffffu, R.z, nxt); Q.w = __shfl_sync(0xffffffffu, R.w, nxt);
-                if (j < nout) *(uint4 *)(sm + 16 * j) = shift_pair(P[k], Q, ws, sh);
+            switch (s >> 2) {                                /* warp-uniform, once per row */
+            case 0: commit_ws<0>(sm, lane); break;
+            case 1: commit_ws<1>(sm, lane); break;
+            case 2: commit_ws<2>(sm, lane); break;
+            default: commit_ws<3>(sm, lane); break;
             }
         }
         const uint32_t i0 = nout * 16 + lane, i1 = i0 + 32;
@@ -954,11 +997,23 @@ __global__ void __launch_bounds__(BROWS_THREADS) bulk_rows_pack_kernel(const __g
         for (uint32_t i = warp; i < nr; i += BROWS_THREADS / 32) {
             uint8_t *d = pp + (size_t)(r0 + i) * pitch;
             const uint32_t off = run.a + i * re;
-            for (uint32_t c = 16 * lane; c < re; c += 512) {
-                const uint4 o = staged16(S, off + c);
-                if (c + 16 <= re) *(uint4 *)(d + c) = o;
-                else { const uint32_t wd[4] = {o.x, o.y, o.z, o.w}; store_prefix<4>(d + c, wd, re - c); }
+            const uint4 *q0 = (const uint4 *)S + (off >> 4);                  /* the row starts off & 15 bytes into this chunk */
+            const uint32_t sh = 8 * (off & 3);
+#define JMC_PACK_ROW(EXPR)                                                                                     \
+            for (uint32_t c = 16 * lane; c < re; c += 512) {                                                   \
+                const uint4 *q = q0 + (c >> 4);                                                                \
+                const uint4 o = EXPR;                                                                          \
+                if (c + 16 <= re) *(uint4 *)(d + c) = o;                                                       \
+                else { const uint32_t wd[4] = {o.x, o.y, o.z, o.w}; store_prefix<4>(d + c, wd, re - c); }     \
             }
+            if ((off & 15) == 0) { JMC_PACK_ROW(q[0]) }
+            else switch ((off & 15) >> 2) {                                    /* warp-uniform, once per row */
+            case 0: JMC_PACK_ROW(shift_pair_ws<0>(q[0], q[1], sh)) break;
+            case 1: JMC_PACK_ROW(shift_pair_ws<1>(q[0], q[1], sh)) break;
+            case 2: JMC_PACK_ROW(shift_pair_ws<2>(q[0], q[1], sh)) break;
+            default: JMC_PACK_ROW(shift_pair_ws<3>(q[0], q[1], sh)) break;
+            }
+#undef JMC_PACK_ROW
         }
     } else {
         /* MERGE: re = pairs per row; U run and V run staged separately */

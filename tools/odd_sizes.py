@@ -13,7 +13,10 @@ for name, spec in {
     "pack 854x480 p1024": ("pack", 854, 480, 1024, 600), "pack 1919x1079 p2048": ("pack", 1919, 1079, 2048, 300),
     "nv12 1366x768 p1536": ("nv12", 1366, 768, 1536, 300), "rgb 1080x1920 p1088": ("rgb", 1080, 1920, 1088, 150),
     "rgb 1366x768 p1536": ("rgb", 1366, 768, 1536, 300), "argb 1366x768 p1536": ("argb", 1366, 768, 1536, 300),
-    "fused 1366x768 p1536": ("fused", 1366, 768, 1536, 300), "argb 3840x2160 p4096": ("argb", 3840, 2160, 4096, 64),
+    "fused 1366x768 p1536": ("fused", 1366, 768, 1536, 300),
+    "rgb 1376x768 p1536": ("rgb", 1376, 768, 1536, 300), "rgb 1536x768 p1536": ("rgb", 1536, 768, 1536, 300),
+    "argb 1376x768 p1536": ("argb", 1376, 768, 1536, 300), "argb 1536x768 p1536": ("argb", 1536, 768, 1536, 300),
+    "rgb2nv12 1376x768 p1536": ("rgb2nv12", 1376, 768, 1536, 300), "rgb2nv12 1536x768 p1536": ("rgb2nv12", 1536, 768, 1536, 300), "argb 3840x2160 p4096": ("argb", 3840, 2160, 4096, 64),
     "rgb2nv12 3840x2160 p4096": ("rgb2nv12", 3840, 2160, 4096, 64), "rgb2nv12 1920x1080 p2048": ("rgb2nv12", 1920, 1080, 2048, 200),
     "rgb2nv12 1366x768 p1536": ("rgb2nv12", 1366, 768, 1536, 300),
 }.items():
