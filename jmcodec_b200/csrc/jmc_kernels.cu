@@ -349,6 +349,8 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     p.segs_per_row = ((uint32_t)j->width + 511) / 512;
     p.row_pairs = ((uint32_t)j->height + 1) / 2;
     p.tasks_per_frame = p.segs_per_row * p.row_pairs;
+    p.tpf_div = make_fastdiv(p.tasks_per_frame);
+    p.seg_div = make_fastdiv(p.segs_per_row);
     const uint64_t total = (uint64_t)p.tasks_per_frame * p.n_frames;
     if (total == 0) return JMC_OK;
     if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }
@@ -427,6 +429,8 @@ static int launch_rgb_to_nv12(jmc_ctx *ctx, const jmc_job *j, cudaStream_t strea
     p.row_pairs = ((uint32_t)j->height + 1) / 2;
     p.segs_per_row = ((uint32_t)j->width + 511) / 512;
     p.tasks_per_frame = p.row_pairs * p.segs_per_row;
+    p.tpf_div = make_fastdiv(p.tasks_per_frame);
+    p.seg_div = make_fastdiv(p.segs_per_row);
     const uint64_t total = (uint64_t)p.tasks_per_frame * p.n_frames;
     if (total == 0) return JMC_OK;
     if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }

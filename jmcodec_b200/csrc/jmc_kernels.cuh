@@ -1071,6 +1071,7 @@ struct RgbParams {
     uint32_t segs_per_row;     /* ceil(width / 512): one warp covers 512 pixels of a row pair */
     uint32_t row_pairs;        /* ceil(height / 2) */
     uint32_t tasks_per_frame;  /* row_pairs * segs_per_row */
+    FastDiv tpf_div, seg_div;  /* division by tasks_per_frame / segs_per_row (a generic divide costs ~20 issue slots) */
     uint32_t total_tasks;
 };
 
@@ -1143,15 +1144,17 @@ struct RgbCfg {                           /* tools/sweep.cu: 128 x 8 CTAs/SM, on
 /* copy nbytes from warp-private shared memory to global, V bytes per lane per step */
 template <int V, int STP> __device__ __forceinline__ void warp_flush(uint8_t *g, const uint8_t *st, uint32_t nbytes, uint32_t lane)
 {
+    uint8_t *gl = g + lane * V;                       /* per-lane bases once, constant steps of 32*V */
+    const uint8_t *sl = st + lane * V;
 #pragma unroll
     for (int k = 0; k < 1536 / (32 * V); k++) {
-        const uint32_t c = (k * 32 + lane) * V;
-        if (c < nbytes) {
-            if (V == 16) st16<STP>(g + c, *(const uint4 *)(st + c));
-            else if (V == 8) st8<STP>(g + c, *(const uint2 *)(st + c));
-            else if (V == 4) *(uint32_t *)(g + c) = *(const uint32_t *)(st + c);
-            else if (V == 2) *(uint16_t *)(g + c) = *(const uint16_t *)(st + c);
-            else g[c] = st[c];
+        constexpr int STEP = 32 * V;
+        if (k * STEP + lane * V < nbytes) {
+            if (V == 16) st16<STP>(gl + k * STEP, *(const uint4 *)(sl + k * STEP));
+            else if (V == 8) st8<STP>(gl + k * STEP, *(const uint2 *)(sl + k * STEP));
+            else if (V == 4) *(uint32_t *)(gl + k * STEP) = *(const uint32_t *)(sl + k * STEP);
+            else if (V == 2) *(uint16_t *)(gl + k * STEP) = *(const uint16_t *)(sl + k * STEP);
+            else gl[k * STEP] = sl[k * STEP];
         }
     }
 }
@@ -1166,9 +1169,9 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
     const int w = p.width, h = p.height, cw = w >> 1, ch = h >> 1;
 
     for (uint32_t task = blockIdx.x * WARPS + wib; task < p.total_tasks; task += warps_total) {
-        const uint32_t f = task / p.tasks_per_frame;
+        const uint32_t f = fast_div(task, p.tpf_div);
         const uint32_t r = task - f * p.tasks_per_frame;
-        const uint32_t rp = r / p.segs_per_row, seg = r - rp * p.segs_per_row;
+        const uint32_t rp = fast_div(r, p.seg_div), seg = r - rp * p.segs_per_row;
         const uint8_t *sp = frame_ptr(p.surf, f);
         uint8_t *rgbp = frame_ptr(p.rgb, f);
         uint8_t *tp = p.fused ? frame_ptr(p.tight, f) : nullptr;
@@ -1259,11 +1262,12 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
                     uint8_t *g = orow + (size_t)row * p.rgb_pitch + (size_t)seg * (32 * 64);
                     const uint32_t nb = 4 * seg_px;                               /* a multiple of 8 */
                     if ((((uint32_t)(uintptr_t)g | nb) & 15) == 0) {
+                        /* 16-byte chunk c = 32k + lane lives at stage lane c/4, part c%4: per-lane bases once, constant steps */
+                        const uint8_t *sl = st + (lane >> 2) * 80 + (lane & 3) * 16;
+                        uint8_t *gl = g + 16 * lane;
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint32_t c = k * 32 + lane;                     /* 16-byte chunk: lane c/4, part c%4 */
-                            if (16 * c < nb) st16<C::STP>(g + 16 * c, *(const uint4 *)(st + (c >> 2) * 80 + (c & 3) * 16));
-                        }
+                        for (int k = 0; k < 4; k++)
+                            if (512 * k + 16 * lane < nb) st16<C::STP>(gl + 512 * k, *(const uint4 *)(sl + 640 * k));
                     } else {                                                      /* 8-byte aligned rows (w % 4 == 2) or any other pitch */
                         warp_store_shifted_map(g, [st](uint32_t c) { return (const uint4 *)(st + (c >> 2) * 80 + (c & 3) * 16); }, nb, lane);
                     }
@@ -1464,6 +1468,7 @@ struct Rgb2Params {
     int32_t width, height, pitch, rgb_pitch;
     int64_t y_off, uv_off;
     uint32_t row_pairs, segs_per_row, tasks_per_frame, total_tasks;
+    FastDiv tpf_div, seg_div;  /* division by tasks_per_frame / segs_per_row */
 };
 
 constexpr uint32_t FWD_Y = 66u | (129u << 8) | (25u << 16);                 /* R,G,B -> Y, unsigned bytes */
@@ -1497,9 +1502,9 @@ __global__ void __launch_bounds__(RGB2_THREADS, 8) rgb_to_nv12_kernel(const __gr
     const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const uint32_t task = blockIdx.x * WARPS + wib;
     if (task >= p.total_tasks) return;
-    const uint32_t f = task / p.tasks_per_frame;
+    const uint32_t f = fast_div(task, p.tpf_div);
     const uint32_t r = task - f * p.tasks_per_frame;
-    const uint32_t rp = r / p.segs_per_row, seg = r - rp * p.segs_per_row;
+    const uint32_t rp = fast_div(r, p.seg_div), seg = r - rp * p.segs_per_row;
     const uint32_t w = (uint32_t)p.width, h = (uint32_t)p.height, cw = w >> 1, ch = h >> 1;
     const uint32_t y0 = 2 * rp, x0 = seg * 512;
     const bool two = y0 + 1 < h, do_uv = rp < ch;
