@@ -377,7 +377,11 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
         else surf_ok = surf_ok && (((uint64_t)(uintptr_t)j->surf.base | (uint64_t)j->surf.stride) & 15) == 0;
         /* measured (profiles/r1_odd_sizes_rgb_bulk.txt): with unaligned rows the bulk-loaded variant wins for the
          * fused op (1366-wide: 0.88 vs 0.79 of peak) but not for RGB alone (0.77 vs 0.82; 1080-wide 0.68 vs 0.82) */
-        if (ok && (aligned || (surf_ok && (fused || getenv_flag("JMC_RGB_BULK_ALWAYS"))))) {
+        /* ... and for RGB alone on narrow frames the warp-per-task kernel is ahead even when everything is aligned
+         * (profiles/r1c_rgb_bulk_vs_vector.txt: 1536 wide 1.03 vs 0.99, 1376 wide 0.95 vs 0.92; from 1920 wide on the
+         * bulk kernel wins, 1.02 vs 1.00) */
+        const bool bulk_pays = fused || j->width >= 1664 || getenv_flag("JMC_RGB_BULK_ALWAYS");
+        if (ok && ((aligned && bulk_pays) || (surf_ok && (fused || getenv_flag("JMC_RGB_BULK_ALWAYS"))))) {
             RgbBulkParams b;
             b.surf = p.surf; b.tight = p.tight; b.rgb = p.rgb;
             b.n_frames = p.n_frames; b.width = p.width; b.height = p.height; b.pitch = p.pitch;

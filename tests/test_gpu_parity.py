@@ -266,10 +266,11 @@ def test_rgb_ldg_stg_kernel_still_matches(ctx, c, fused, monkeypatch):
     assert K.sha(rgb) == GOLD[K.case_id(c)]["sha256"]
 
 
-@pytest.mark.parametrize("c", [c for c in K.rgb_cases() if c["w"] % 2 == 0 and c["w"] % 16 != 0], ids=K.case_id)
-def test_rgb_bulk_loaded_kernel_with_unaligned_rows(ctx, c, monkeypatch):
-    """Even widths that are not multiples of 16: the fused op takes the bulk-loaded kernel with re-aligned stores;
-    JMC_RGB_BULK_ALWAYS=1 sends plain RGB24 through it too (normally the vector kernel, which is faster there)."""
+@pytest.mark.parametrize("c", [c for c in K.rgb_cases() if c["w"] % 2 == 0 and c["kind"] in ("random", "gradient")], ids=K.case_id)
+def test_rgb_bulk_loaded_kernel_everywhere_it_can_run(ctx, c, monkeypatch):
+    """The bulk-loaded RGB kernel is the default only where it is the fastest (fused op; RGB24 from 1664 pixels wide);
+    JMC_RGB_BULK_ALWAYS=1 sends every even width through it - aligned rows (copy-engine stores) and rows at odd
+    addresses (re-aligned stores) - and the bytes must not change."""
     monkeypatch.setenv("JMC_RGB_BULK_ALWAYS", "1")
     assert K.sha(G.gpu_rgb(ctx, c)) == GOLD[K.case_id(c)]["sha256"]
 
