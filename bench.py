@@ -45,7 +45,7 @@ WORKLOADS = {
     "nv12_to_rgb24_4k_x64_pitch4096": ("rgb", 3840, 2160, 4096, 64),
     "nv12_to_i420_rgb24_4k_x64_pitch4096": ("fused", 3840, 2160, 4096, 64),
     "nv12_to_argb32_4k_x64_pitch4096": ("argb", 3840, 2160, 4096, 64),
-    "rgb24_to_nv12_4k_x64_pitch4096": ("rgb2nv12", 3840, 2160, 4096, 64),      # kernel table only (not a pipeline op)
+    "rgb24_to_nv12_4k_x64_pitch4096": ("rgb2nv12", 3840, 2160, 4096, 64),      # kernel table only
 }
 DEFAULT_WORKLOAD = "nv12_to_i420_1080p_x300_pitch2048"
 N_DISTINCT = 32          # distinct synthetic surfaces, tiled over the batch

@@ -138,7 +138,7 @@ JMC_API int jmc_job_rgb(jmc_job *job, int width, int height, int pitch, int rgb_
 /* NV12_TO_ARGB32 on an nv_dec-style surface; the ARGB frames go to job->rgb, row pitch argb_pitch >= 4*width. */
 JMC_API int jmc_job_argb(jmc_job *job, int width, int height, int pitch, int argb_pitch);
 /* RGB24_TO_SURF into an nv_enc-style surface (Y at 0, UV at stride*height, nv_enc.cpp:1069); the RGB frames are
- * read from job->rgb, row pitch rgb_pitch >= 3*width.  Not a jmc_pipeline op. */
+ * read from job->rgb, row pitch rgb_pitch >= 3*width (a pipeline batch takes rgb_pitch*height bytes per frame). */
 JMC_API int jmc_job_rgb_to_nv12(jmc_job *job, int width, int height, int rgb_pitch, int stride);
 /* Bytes of one tight frame as the reference computes it: w*h*3/2 (nv_dec.cpp:773,824). */
 JMC_API int64_t jmc_tight_bytes(int width, int height);

@@ -379,6 +379,7 @@ int jmc_pipeline_create(jmc_ctx *c, const jmc_job *shape, size_t surf_bytes, int
     case JMC_OP_NV12_TO_RGB24: case JMC_OP_NV12_TO_ARGB32: p->in_bytes = surf_bytes; p->out_bytes = rgb; p->out2_bytes = 0; break;
     case JMC_OP_NV12_TO_I420_RGB24: p->in_bytes = surf_bytes; p->out_bytes = tight; p->out2_bytes = rgb; break;
     case JMC_OP_NV12_TO_SURF: case JMC_OP_I420_TO_SURF: p->in_bytes = tight; p->out_bytes = surf_bytes; p->out2_bytes = 0; break;
+    case JMC_OP_RGB24_TO_SURF: p->in_bytes = rgb; p->out_bytes = surf_bytes; p->out2_bytes = 0; break;
     default: delete p; jmc_set_error("jmc_pipeline_create: unknown op"); return JMC_ERR_INVALID;
     }
     if (surf_bytes == 0) { delete p; jmc_set_error("jmc_pipeline_create: surf_bytes == 0"); return JMC_ERR_INVALID; }
@@ -465,7 +466,8 @@ int jmc_pipeline_submit(jmc_pipeline *p, const void *host_in, const void *dev_in
         else { j.tight.base = s.d_out; j.tight.stride = p->out_bytes; }
         if (j.op == JMC_OP_NV12_TO_I420_RGB24) { j.rgb.base = s.d_out2; j.rgb.stride = p->out2_bytes; }
     } else {
-        j.tight.base = (void *)src; j.tight.stride = p->in_bytes;
+        if (j.op == JMC_OP_RGB24_TO_SURF) { j.rgb.base = (void *)src; j.rgb.stride = p->in_bytes; }
+        else { j.tight.base = (void *)src; j.tight.stride = p->in_bytes; }
         j.surf.base = s.d_out; j.surf.stride = p->out_bytes;
     }
     int r = jmc_launch_job(c, &j, c->stream[0]);

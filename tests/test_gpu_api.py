@@ -149,7 +149,7 @@ def test_nvenc_api_upload(J, ctx, fmt, geom):
 # --------------------------------------------------------------------------------------------
 # host-delivery pipeline
 # --------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("op", ["i420", "nv12", "rgb", "fused", "pack", "argb"])
+@pytest.mark.parametrize("op", ["i420", "nv12", "rgb", "fused", "pack", "argb", "rgb2nv12"])
 def test_pipeline_batches(J, ctx, op):
     w, h, pitch, batch, nb = 640, 360, 768, 5, 7
     surf_bytes, tight_bytes, rgb_bytes = pitch * h * 3 // 2, w * h * 3 // 2, 3 * w * h
@@ -157,6 +157,9 @@ def test_pipeline_batches(J, ctx, op):
     if op == "pack":
         shape = ctx.job_nvenc(w, h, pitch, 0x10)
         in_bytes, out_bytes = tight_bytes, surf_bytes
+    elif op == "rgb2nv12":
+        shape = ctx.job_rgb_to_nv12(w, h, 3 * w, pitch)
+        in_bytes, out_bytes = rgb_bytes, surf_bytes
     elif op == "argb":
         shape = ctx.job_argb(w, h, pitch, 4 * w)
         in_bytes, out_bytes = surf_bytes, 4 * w * h
@@ -173,7 +176,10 @@ def test_pipeline_batches(J, ctx, op):
     hout2 = ctx.alloc_host(nb * batch * rgb_bytes) if op == "fused" else None
     frames = []
     for i in range(nb * batch):
-        f = synth.i420_frame(w, h, 14, i) if op == "pack" else synth.nv12_surface(w, h, pitch, 14, i)
+        if op == "rgb2nv12":
+            f = synth.random_bytes(rgb_bytes, synth.frame_key(14, i) ^ 0x3C3C3C3C)
+        else:
+            f = synth.i420_frame(w, h, 14, i) if op == "pack" else synth.nv12_surface(w, h, pitch, 14, i)
         frames.append(f)
         hin.array[i * in_bytes:(i + 1) * in_bytes] = f
     for b in range(nb):
@@ -183,13 +189,16 @@ def test_pipeline_batches(J, ctx, op):
     pipe.drain()
     total = nb * batch - 2
     # decode-side uploads skip the pitch padding (2-D copy): only width of every pitch bytes cross PCIe
-    assert pipe.h2d_bytes == (total * in_bytes if op == "pack" else total * (h * 3 // 2) * w)
+    assert pipe.h2d_bytes == (total * in_bytes if op in ("pack", "rgb2nv12") else total * (h * 3 // 2) * w)
     assert pipe.d2h_bytes == total * (out_bytes + (rgb_bytes if op == "fused" else 0))
     for i in range(total):
         got = hout.array[i * out_bytes:(i + 1) * out_bytes]
         if op == "pack":
             want = np.zeros(out_bytes, np.uint8)
             oracle.nvenc_upload(frames[i], 0x10, w, h, want, pitch)
+        elif op == "rgb2nv12":
+            want = np.zeros(out_bytes, np.uint8)                     # pipeline surfaces start zeroed; padding stays 0
+            oracle.rgb24_to_nv12(frames[i], 3 * w, w, h, want, pitch)
         elif op == "rgb":
             want = np.empty(out_bytes, np.uint8)
             oracle.nv12_to_rgb24(frames[i], pitch, w, h, want, 3 * w)
