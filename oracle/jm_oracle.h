@@ -13,8 +13,8 @@
  * jmo_nvenc_upload restates nv_enc/nv_enc.cpp:1023-1103: PINNED against the reference's own
  * nvenc_convert_yuv_data_to_nv12() executed over a fake CUDA driver (oracle/ref_nvenc_driver.cpp);
  * only the InterleaveUV kernel body (PTX absent from the reference tree) is emulated there, from the
- * 8 launch arguments at nv_enc.cpp:1070.  jmo_nv12_to_rgb24 is a builder-defined
- * BT.601 spec: PARITY UNPINNED (the reference has no YUV->RGB code; SDL2 does it).
+ * 8 launch arguments at nv_enc.cpp:1070.  jmo_nv12_to_rgb24, jmo_nv12_to_argb32 and jmo_rgb24_to_nv12 are
+ * builder-defined BT.601 specs: PARITY UNPINNED (the reference has no YUV<->RGB code; SDL2 does it).
  *
  * All citations are relative to /root/reference.
  */
