@@ -99,6 +99,15 @@ typedef struct jmc_frames {
     void *const *list;
 } jmc_frames;
 
+/* Memory contract of a job.
+ *  - Surfaces are allocated as whole rows: every row of `pitch` bytes exists up to its end, as cudaMallocPitch /
+ *    cuMemAllocPitch (nv_enc.cpp:961-975) and decoder-mapped surfaces guarantee.  When a surface is 16-byte
+ *    aligned (base, pitch, plane offsets) the kernels may READ a source row up to the next multiple of 16 past
+ *    `width`, inside the pitch; padding is never written.
+ *  - Tight / RGB frames: exactly the bytes the reference writes are written.  Reads of a tight or RGB source may
+ *    start up to 15 bytes before a row (aligned 16-byte loads): that is the previous row or, for the first row,
+ *    still inside the device allocation (allocations are at least 256-byte aligned); nothing is read past the
+ *    last byte of a frame. */
 typedef struct jmc_job {
     int32_t    op;            /* jmc_op                                                         */
     int32_t    n_frames;      /* frames converted by this launch                                */
