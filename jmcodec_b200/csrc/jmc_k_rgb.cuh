@@ -276,6 +276,116 @@ __global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_kernel(const
 }
 
 
+/* ---- flattened variant: every lane slot busy whatever the width --------------------------------
+ * rgb_kernel gives a warp 512 pixels of ONE row pair, so a 1366-wide row pair costs 96 lane slots for 85.4
+ * sixteen-pixel units and a 1080-wide one 96 for 67.5 - and at that utilisation the kernel is issue-bound.
+ * Here the (row pair, unit) space of a frame is numbered through and a warp takes 32 CONSECUTIVE units, which
+ * may end one row pair and begin the next: loads are per lane anyway; the staged RGB bytes of a warp then form
+ * one run per row pair it touches (usually one or two), each flushed like rgb_kernel flushes its single run.
+ * Host guarantees: aligned surface, even width, rows over-readable to 16 bytes, not the fused op. */
+struct RgbFlatParams {
+    FrameSet surf, rgb;
+    uint32_t n_frames;
+    int32_t width, height, pitch;
+    int64_t y_off, uv_off;
+    int32_t rgb_pitch;
+    uint32_t units_per_row;    /* ceil(width / 16) */
+    uint32_t units_per_frame;  /* units_per_row * ceil(height / 2) */
+    uint32_t tasks_per_frame;  /* ceil(units_per_frame / 32) */
+    FastDiv tpf_div, unit_div; /* division by tasks_per_frame / units_per_row */
+    uint32_t total_tasks;
+};
+
+template <class C, bool ARGB>
+__global__ void __launch_bounds__(C::THREADS, C::BLOCKS_PER_SM) rgb_flat_kernel(const __grid_constant__ RgbFlatParams p)
+{
+    constexpr int WARPS = C::THREADS / 32;
+    constexpr uint32_t BPP = ARGB ? 4 : 3;
+    __shared__ __align__(16) uint8_t stage[WARPS][32 * 80 + 64];     /* RGB24: 48 B per lane; ARGB32: 64 B at an 80-byte stride */
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t task = blockIdx.x * WARPS + wib;
+    if (task >= p.total_tasks) return;
+    const uint32_t f = fast_div(task, p.tpf_div);
+    const uint32_t u0 = (task - f * p.tasks_per_frame) * 32;         /* first unit of this warp */
+    const uint32_t w = (uint32_t)p.width, h = (uint32_t)p.height, ch = h >> 1;
+    const uint32_t U = p.units_per_row, ulast = min(u0 + 31, p.units_per_frame - 1);
+    const bool valid = u0 + lane <= ulast;
+    const uint32_t u = valid ? u0 + lane : ulast;
+    const uint32_t rp = fast_div(u, p.unit_div), px0 = (u - rp * U) * 16;
+    const uint32_t y0 = 2 * rp;
+    const bool two = y0 + 1 < h;
+    const uint8_t *sp = frame_ptr(p.surf, f);
+    uint8_t *rgbp = frame_ptr(p.rgb, f);
+    const uint8_t *yrow = sp + p.y_off + (size_t)y0 * p.pitch + px0;
+    uint4 ya = make_uint4(0, 0, 0, 0), yb = ya, uv = ya;
+    if (valid) {
+        ya = ld16<C::LDP>(yrow);
+        uv = ld16<C::LDP>(sp + p.uv_off + (size_t)min(rp, ch - 1) * p.pitch + px0);
+        if (two) yb = ld16<C::LDP>(yrow + p.pitch);
+    }
+    int cr[8], cg[8], cb[8];
+    const uint32_t uvw[4] = {uv.x, uv.y, uv.z, uv.w};
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        cr[2 * j] = dp2a_lo(COEF_RV, uvw[j], RGB_CR);  cr[2 * j + 1] = dp2a_hi(COEF_RV, uvw[j], RGB_CR);
+        cg[2 * j] = dp2a_lo(COEF_GUV, uvw[j], RGB_CG); cg[2 * j + 1] = dp2a_hi(COEF_GUV, uvw[j], RGB_CG);
+        cb[2 * j] = dp2a_lo(COEF_BU, uvw[j], RGB_CB);  cb[2 * j + 1] = dp2a_hi(COEF_BU, uvw[j], RGB_CB);
+    }
+    uint8_t *st = stage[wib];
+    const uint32_t rp_a = fast_div(u0, p.unit_div), rp_b = fast_div(ulast, p.unit_div);   /* row pairs this warp touches */
+#pragma unroll
+    for (int row = 0; row < 2; row++) {
+        const uint4 yy = row ? yb : ya;
+        const uint32_t yw[4] = {yy.x, yy.y, yy.z, yy.w};
+        __syncwarp();
+        if constexpr (ARGB) {
+            uint4 *s4 = (uint4 *)(st + lane * 80);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                uint32_t o[4];
+                argb4(yw[j], cr[2 * j], cg[2 * j], cb[2 * j], cr[2 * j + 1], cg[2 * j + 1], cb[2 * j + 1], o);
+                s4[j] = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+        } else {
+            uint32_t o[12];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                rgb4(yw[j], cr[2 * j], cg[2 * j], cb[2 * j], cr[2 * j + 1], cg[2 * j + 1], cb[2 * j + 1], o + 3 * j);
+            uint4 *s4 = (uint4 *)(st + lane * 48);
+            s4[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            s4[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            s4[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        }
+        __syncwarp();
+        for (uint32_t r = rp_a; r <= rp_b; r++) {                        /* one run per row pair; all of it warp-uniform */
+            if (2 * r + row >= h) continue;                              /* odd height: the last row pair has one row */
+            const uint32_t ua = max(u0, r * U), ub = min(ulast + 1, (r + 1) * U);          /* units [ua, ub) of row pair r */
+            const uint32_t lo = ua - u0;                                 /* first lane of the run */
+            const uint32_t px_lo = (ua - r * U) * 16, px_hi = min(w, (ub - r * U) * 16);
+            const uint32_t nb = BPP * (px_hi - px_lo);
+            uint8_t *g = rgbp + (size_t)(2 * r + row) * p.rgb_pitch + (size_t)BPP * px_lo;
+            const uint32_t gb = (uint32_t)(uintptr_t)g | nb;
+            if constexpr (ARGB) {
+                if ((gb & 15) == 0) {
+                    const uint8_t *sl = st + (lo + (lane >> 2)) * 80 + (lane & 3) * 16;
+                    uint8_t *gl = g + 16 * lane;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (512 * k + 16 * lane < nb) st16<C::STP>(gl + 512 * k, *(const uint4 *)(sl + 640 * k));
+                } else {
+                    warp_store_shifted_map(g, [st, lo](uint32_t c) { return (const uint4 *)(st + (lo + (c >> 2)) * 80 + (c & 3) * 16); }, nb, lane);
+                }
+            } else {
+                const uint8_t *s0 = st + lo * 48;
+                if ((gb & 15) == 0) warp_flush<16, C::STP>(g, s0, nb, lane);
+                else if ((gb & 7) == 0) warp_flush<8, C::STP>(g, s0, nb, lane);
+                else warp_store_shifted(g, s0, nb, lane);
+            }
+        }
+    }
+}
+
+
 /* ---- bulk-copy-engine variant of the RGB kernel ------------------------------------------------
  * One CTA per (frame, row pair, column segment of <= 2048 pixels): three bulk loads (two luma rows,
  * one chroma row) into shared memory, threads convert shared -> shared (same dp2a / cvt.pack.sat

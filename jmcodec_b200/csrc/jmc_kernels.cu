@@ -411,6 +411,40 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
         }
     }
     constexpr uint32_t WARPS = RgbCfg::THREADS / 32;
+    /* flattened variant: when a row pair leaves more than ~1/7 of the lane slots of its warps idle and the surface
+     * allows 16-byte loads for every lane.  Measured (profiles/r1c_rgb_flat.txt): 1080 wide (71 % of the slots used)
+     * RGB24 0.84 -> 0.92, ARGB32 0.93 -> 1.02; 1280 wide (83 %) 0.96 -> 0.98; but 1366 / 1376 wide (90 %) lose
+     * 3-5 % to the extra runs per warp, and 4K (94 %) is a tie.  JMC_RGB_FLAT=0 / 1 forces it off / on (A/B). */
+    {
+        bool surf_ok = !fused && (j->width & 1) == 0 && j->pitch >= ((j->width + 15) & ~15) &&
+                       (((uint64_t)j->surf_y_off | (uint64_t)j->surf_uv_off | (uint32_t)j->pitch) & 15) == 0;
+        if (j->surf.list) surf_ok = surf_ok && (j->flags & JMC_JOB_ALIGNED16) != 0;
+        else surf_ok = surf_ok && (((uint64_t)(uintptr_t)j->surf.base | (uint64_t)j->surf.stride) & 15) == 0;
+        const char *force = getenv("JMC_RGB_FLAT");
+        const uint32_t units = ((uint32_t)j->width + 15) / 16, slots = 32 * ((units + 31) / 32);
+        const bool want = force ? atoi(force) != 0 : units * 100 < slots * 86;
+        if (surf_ok && want) {
+            RgbFlatParams q;
+            q.surf = p.surf; q.rgb = p.rgb; q.n_frames = p.n_frames;
+            q.width = p.width; q.height = p.height; q.pitch = p.pitch;
+            q.y_off = p.y_off; q.uv_off = p.uv_off; q.rgb_pitch = p.rgb_pitch;
+            q.units_per_row = ((uint32_t)j->width + 15) / 16;
+            q.units_per_frame = q.units_per_row * p.row_pairs;
+            q.tasks_per_frame = (q.units_per_frame + 31) / 32;
+            q.tpf_div = make_fastdiv(q.tasks_per_frame);
+            q.unit_div = make_fastdiv(q.units_per_row);
+            const uint64_t tasks = (uint64_t)q.tasks_per_frame * q.n_frames;
+            if (tasks <= 0x7fffffffull) {
+                q.total_tasks = (uint32_t)tasks;
+                const uint32_t g2 = (q.total_tasks + WARPS - 1) / WARPS;
+                if (argb) rgb_flat_kernel<RgbCfg, true><<<g2, RgbCfg::THREADS, 0, stream>>>(q);
+                else rgb_flat_kernel<RgbCfg, false><<<g2, RgbCfg::THREADS, 0, stream>>>(q);
+                JMC_CUDA(cudaGetLastError());
+                ctx->launches++;
+                return JMC_OK;
+            }
+        }
+    }
     const uint32_t blocks_needed = (p.total_tasks + WARPS - 1) / WARPS;
     const uint32_t grid = blocks_needed;             /* one warp per (row pair, 512-pixel segment) task */
     if (argb) rgb_kernel<RgbCfg, true><<<grid, RgbCfg::THREADS, 0, stream>>>(p);

@@ -275,12 +275,17 @@ def test_rgb_bulk_loaded_kernel_everywhere_it_can_run(ctx, c, monkeypatch):
     assert K.sha(G.gpu_rgb(ctx, c)) == GOLD[K.case_id(c)]["sha256"]
 
 
+@pytest.mark.parametrize("flat", ["default", "0", "1"])
 @pytest.mark.parametrize("always", [False, True])
 @pytest.mark.parametrize("seed", range(2))
-def test_random_widths_rgb_on_aligned_surfaces(ctx, seed, always, monkeypatch):
-    """RGB24, fused I420+RGB24 and ARGB32 on decoder-style surfaces with arbitrary widths and skewed output buffers."""
+def test_random_widths_rgb_on_aligned_surfaces(ctx, seed, always, flat, monkeypatch):
+    """RGB24, fused I420+RGB24 and ARGB32 on decoder-style surfaces with arbitrary widths and skewed output buffers;
+    every kernel that can serve them: bulk-loaded (JMC_RGB_BULK_ALWAYS), flattened (JMC_RGB_FLAT=1, the default when
+    the width is not a multiple of 512) and the warp-per-segment kernel (JMC_RGB_FLAT=0)."""
     if always:
         monkeypatch.setenv("JMC_RGB_BULK_ALWAYS", "1")
+    if flat != "default":
+        monkeypatch.setenv("JMC_RGB_FLAT", flat)
     chk = oracle.best()
     rng = np.random.default_rng(4000 + seed)
     for it in range(24):

@@ -17,6 +17,7 @@ for name, spec in {
     "rgb 1376x768 p1536": ("rgb", 1376, 768, 1536, 300), "rgb 1536x768 p1536": ("rgb", 1536, 768, 1536, 300),
     "argb 1376x768 p1536": ("argb", 1376, 768, 1536, 300), "argb 1536x768 p1536": ("argb", 1536, 768, 1536, 300),
     "rgb2nv12 1376x768 p1536": ("rgb2nv12", 1376, 768, 1536, 300), "rgb2nv12 1536x768 p1536": ("rgb2nv12", 1536, 768, 1536, 300), "argb 3840x2160 p4096": ("argb", 3840, 2160, 4096, 64),
+    "argb 1080x1920 p1088": ("argb", 1080, 1920, 1088, 150), "rgb 1280x720 p1280": ("rgb", 1280, 720, 1280, 400),
     "rgb 3840x2160 p4096": ("rgb", 3840, 2160, 4096, 64), "fused 3840x2160 p4096": ("fused", 3840, 2160, 4096, 64),
     "rgb 1920x1080 p2048": ("rgb", 1920, 1080, 2048, 200), "fused 1920x1080 p2048": ("fused", 1920, 1080, 2048, 200),
     "rgb2nv12 3840x2160 p4096": ("rgb2nv12", 3840, 2160, 4096, 64), "rgb2nv12 1920x1080 p2048": ("rgb2nv12", 1920, 1080, 2048, 200),
