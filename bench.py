@@ -312,69 +312,19 @@ def device_only(ctx, name, rank, iters, warmup):
     return res
 
 
-def dropin_api_fps(J, ctx, device, w=1920, h=1080, pitch=2048, frames=200):
-    """Frames/s of the per-frame drop-in API, called as test_nv_dec.cpp:215-218 calls it
-    (jm_nvdec_decode_frame then jm_nvdec_output_frame, one frame at a time, one handle, one thread)."""
-    from jmcodec_b200 import synth
-    need = w * h * 3 // 2
-    surfs = [synth.nv12_surface(w, h, pitch, 7, f) for f in range(4)]
-    res = {}
-    # (a) the reference's calling convention: pageable packet in, pageable frame out
-    dec = J.NvDec(device)
-    dec.init(J.NvDec.CODEC_RAW_NV12, 1)
-    pkts = [J.NvDec.raw_packet(s, w, h, pitch) for s in surfs]
-    out = np.empty(need, np.uint8)
-    for i in range(10):
-        dec.decode_frame(pkts[i % 4]); dec.output_frame(out, need)
-    t0 = time.perf_counter()
-    for i in range(frames):
-        dec.decode_frame(pkts[i % 4]); dec.output_frame(out, need)
-    res["host_packet_pageable_out_fps"] = round(frames / (time.perf_counter() - t0), 1)
-    # (b) what an NVDEC front-end yields: device-resident surface in, pinned frame out
-    dptrs = [ctx.upload(s) for s in surfs]
-    dpk = [J.NvDec.raw_packet(None, w, h, pitch, device_ptr=d) for d in dptrs]
-    pinned = dec.alloc_host(need)
-    for i in range(10):
-        dec.decode_frame(dpk[i % 4]); dec.output_frame(pinned, need)
-    t0 = time.perf_counter()
-    for i in range(frames * 5):
-        dec.decode_frame(dpk[i % 4]); dec.output_frame(pinned, need)
-    res["device_surface_pinned_out_fps"] = round(frames * 5 / (time.perf_counter() - t0), 1)
-    dec.free_host(pinned)
-    dec.deinit()
-    # (c) the reference's scaling model: one handle per stream, one host thread per handle
-    import threading
-    nthr = 4
-    decs = []
-    for _ in range(nthr):
-        d = J.NvDec(device)
-        d.init(J.NvDec.CODEC_RAW_NV12, 1)
-        decs.append((d, d.alloc_host(need)))
-    start, counts = threading.Barrier(nthr + 1), [0] * nthr
-
-    def stream(i):
-        d, buf = decs[i]
-        for k in range(10):
-            d.decode_frame(dpk[k % 4]); d.output_frame(buf, need)
-        start.wait()
-        for k in range(frames * 2):
-            d.decode_frame(dpk[(k + i) % 4]); d.output_frame(buf, need)
-        counts[i] = frames * 2
-
-    thr = [threading.Thread(target=stream, args=(i,)) for i in range(nthr)]
-    for t in thr:
-        t.start()
-    start.wait()
-    t0 = time.perf_counter()
-    for t in thr:
-        t.join()
-    res["device_surface_pinned_out_4_handles_fps"] = round(sum(counts) / (time.perf_counter() - t0), 1)
-    for d, buf in decs:
-        d.free_host(buf)
-        d.deinit()
-    for d in dptrs:
-        ctx.free(d)
-    return res
+def dropin_api_fps(device, w=1920, h=1080, pitch=2048, frames=400):
+    """Frames/s of the per-frame drop-in API, called as test_nv_dec.cpp:215-218 calls it (jm_nvdec_decode_frame
+    then jm_nvdec_output_frame, one frame at a time, one handle per thread), measured by tools/jm_dropin -- plain
+    C++ on the C-ABI, so that no Python sits in the timed loop.  Keys: see the VARIANTS table of tools/jm_dropin.cpp."""
+    import subprocess
+    exe = os.path.join(ROOT, "tools", "jm_dropin")
+    if not os.path.exists(exe):
+        raise RuntimeError("tools/jm_dropin is not built (python -c 'import __graft_entry__ as g; g.build()')")
+    p = subprocess.run([exe, "--device", str(device), "--frames", str(frames), "--width", str(w), "--height", str(h),
+                        "--pitch", str(pitch)], capture_output=True, text=True, timeout=600)
+    if p.returncode != 0:
+        raise RuntimeError("tools/jm_dropin failed: " + p.stderr[-300:])
+    return json.loads(p.stdout)
 
 
 def main():
@@ -574,7 +524,7 @@ def main():
             extras_errors.append("frames_per_launch_sweep: " + repr(e))
         WORKLOADS.pop("_sweep", None)
         try:
-            dropin = dropin_api_fps(J, ctx, local)
+            dropin = dropin_api_fps(local)
         except Exception as e:          # noqa: BLE001
             extras_errors.append("dropin_api: " + repr(e))
 

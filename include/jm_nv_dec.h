@@ -57,6 +57,8 @@ typedef void *handle_nvdec;
 
 #define JM_NVDEC_RAW_MAGIC 0x53524D4Au      /* "JMRS" */
 #define JM_NVDEC_RAW_DEVICE_PTR 1u          /* flags: surface already in device memory at device_ptr */
+#define JM_NVDEC_RAW_SYNC       2u          /* flags: do not return before the conversion has READ the surface */
+#define JM_NVDEC_RAW_WAIT_EVENT 4u          /* flags: packet is a jm_nvdec_raw_packet_ex; order the conversion after ready_event */
 
 /* What cuvidMapVideoFrame hands the reference (a device pointer + pitch, nv_dec.cpp:439-442),
  * as a packet.  Without JM_NVDEC_RAW_DEVICE_PTR the header is followed by pitch*height*3/2
@@ -68,6 +70,17 @@ typedef struct jm_nvdec_raw_packet {
     uint32_t reserved;
     uint64_t device_ptr;
 } jm_nvdec_raw_packet;
+
+/* Device-pointer packets and ownership.  The header is consumed before jm_nvdec_decode_frame returns; the SURFACE
+ * it points to is read by a kernel that is only enqueued by then.  So, like a decoder's own surface ring, it must
+ * (a) be completely written when the call is made -- or carry the CUDA event that marks its completion
+ *     (JM_NVDEC_RAW_WAIT_EVENT, ready_event = a cudaEvent_t / CUevent recorded on the producing stream), and
+ * (b) stay untouched until jm_nvdec_output_frame has returned the frame made from it -- or the packet sets
+ *     JM_NVDEC_RAW_SYNC, then jm_nvdec_decode_frame itself waits until the surface has been read. */
+typedef struct jm_nvdec_raw_packet_ex {
+    jm_nvdec_raw_packet base;
+    uint64_t ready_event;
+} jm_nvdec_raw_packet_ex;
 
 /** create decode handle (new + zero, no CUDA; nv_dec.cpp:54-60) */
 JMDLL_FUNC handle_nvdec jm_nvdec_create_handle(void);
@@ -89,7 +102,14 @@ JMDLL_FUNC int jm_nvdec_deinit(handle_nvdec handle);
 /**
  *   decode video frame (nv_dec.cpp:481-494): consumes in_buf before returning; in_data_len == 0
  *   (or in_buf == NULL) flushes / signals end of stream; *got_frame = 1 if a frame is ready for
- *   jm_nvdec_output_frame.  At most one frame per call.  Always returns 0, like the reference.
+ *   jm_nvdec_output_frame.  At most one frame per call.  Returns 0 like the reference, with ONE
+ *   exception: -1 when decoded frames had to be dropped because the caller stopped fetching (the handle
+ *   keeps at most 32 converted frames; the reference's queue is unbounded and overwrites decode surfaces
+ *   instead).  Every surface that became available in this call is converted by one launch and its
+ *   delivery to the host is started before the call returns; nothing waits for it here.
+ *   With a display delay of n (jm_nvdec_set_display_delay) the frame announced is the one decoded n calls
+ *   earlier, as with the parser's own ulMaxDisplayDelay (nv_dec.cpp:346); flush with in_data_len == 0 until
+ *   jm_nvdec_is_exit(), as test_nv_dec.cpp:232-246 does.
  */
 JMDLL_FUNC int jm_nvdec_decode_frame(unsigned char *in_buf, int in_data_len, int *got_frame, handle_nvdec handle);
 
@@ -98,8 +118,10 @@ JMDLL_FUNC int jm_nvdec_decode_frame(unsigned char *in_buf, int in_data_len, int
  *   out_len [in] capacity of out_buf, [out] frame size w*h*3/2.
  *   return: w*h*3/2 (>0, NOT 0 -- nv_dec.cpp:827) on success; -1 no frame / NULL buffer;
  *           -2 capacity too small (*out_len left untouched, :773-774).
- *   out_buf may be pageable (as in the reference) or pinned (jm_nvdec_memory_alloc_host): a pinned
- *   buffer receives the frame by direct DMA.
+ *   out_buf may be pageable (as in the reference): the frame is copied out of the handle's pinned delivery
+ *   ring, where the DMA started by jm_nvdec_decode_frame has put (or is putting) it; or pinned
+ *   (jm_nvdec_memory_alloc_host / jm_nvdec_memory_register_host): it receives the frame by direct DMA; or a
+ *   device pointer: device-to-device copy.  May be called again for the same frame.
  */
 JMDLL_FUNC int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec handle);
 
@@ -118,6 +140,24 @@ JMDLL_FUNC int jm_nvdec_set_device(int device, handle_nvdec handle);
 /** pinned host memory for out_buf (mirror of jm_nvenc_memory_alloc_host, jmnv_enc.h:65-66) */
 JMDLL_FUNC int jm_nvdec_memory_alloc_host(void **buf, int buf_len, handle_nvdec handle);
 JMDLL_FUNC int jm_nvdec_memory_release_host(void *buf, handle_nvdec handle);
+/** page-lock a buffer the caller already owns (malloc'ed out_buf / packet buffer) so that it is reached by direct
+ *  DMA; unregister it BEFORE freeing it.  (JMC_NVDEC_LAZY_PIN=1 / option "lazy_pin" does this automatically for a
+ *  buffer passed on two consecutive calls -- opt-in, because the library cannot see the caller free it.) */
+JMDLL_FUNC int jm_nvdec_memory_register_host(void *buf, int buf_len, handle_nvdec handle);
+JMDLL_FUNC int jm_nvdec_memory_unregister_host(void *buf, handle_nvdec handle);
+/** frames held back before they are announced (0..20, default 0 or env JMC_NVDEC_DISPLAY_DELAY): with n >= 1 the
+ *  delivery of frame k overlaps the upload / decode / conversion of frame k+1 */
+JMDLL_FUNC int jm_nvdec_set_display_delay(int frames, handle_nvdec handle);
+/** "display_delay", "lazy_pin" (0/1), "copy_threads" (helper threads for copies from/to pageable memory, 0..16,
+ *  env JMC_NVDEC_COPY_THREADS), "map_limit" (decoder surfaces mapped and converted per launch, 1..8) */
+JMDLL_FUNC int jm_nvdec_set_option(const char *name, int value, handle_nvdec handle);
+/** zero-copy fetch: *frame points at the current frame inside the handle's pinned delivery ring (same bytes
+ *  jm_nvdec_output_frame would write), valid until the next jm_nvdec_decode_frame call.  Returns w*h*3/2 or -1. */
+JMDLL_FUNC int jm_nvdec_output_frame_ref(const unsigned char **frame, int *frame_len, handle_nvdec handle);
+/** decoded frames dropped so far because the caller did not fetch (see jm_nvdec_decode_frame) */
+JMDLL_FUNC int jm_nvdec_dropped_frames(handle_nvdec handle);
+/** conversion kernels this handle has launched (one per batch of surfaces, not one per frame) */
+JMDLL_FUNC long long jm_nvdec_launch_count(handle_nvdec handle);
 
 #ifdef __cplusplus
 }

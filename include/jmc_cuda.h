@@ -42,12 +42,20 @@ typedef struct jmc_pipeline jmc_pipeline; /* host-delivery ring: H2D -> convert 
 /* Human-readable description of the last failure on the calling thread. */
 JMC_API const char *jmc_last_error(void);
 JMC_API const char *jmc_version(void);
+/* The JMC_* environment switches (kernel-variant A/B: JMC_NO_BULK, JMC_NO_ROWS, JMC_RGB_FLAT ...) are read once per
+ * process, not per launch; call this after changing them in a running process. */
+JMC_API void jmc_reload_env(void);
 
 /* ---- device + context ------------------------------------------------------------------
  * Replaces nvdec_cuda_init()/nvenc_cuda_init(): cuInit + cuDeviceGetCount + cuCtxCreate on the
  * hard-coded device 0 (nv_dec/nv_dec.cpp:202-273, nv_enc/nv_enc.cpp:232-276).  The device is
  * now selectable so that streams can be sharded over 1..8 GPUs. */
 JMC_API int jmc_device_count(void);                              /* <=0: no usable device      */
+/* The calling thread's current CUDA device as this library's (statically linked) runtime sees it.  Every jmc_* /
+ * jm_nvdec_* / jm_nvenc_* entry point switches to its own device and RESTORES this one before returning, as the
+ * reference pushes / pops its context around each call (nv_dec.cpp:378,398,423,471). */
+JMC_API int jmc_current_device(void);
+JMC_API int jmc_set_current_device(int device);
 JMC_API int jmc_ctx_create(int device, jmc_ctx **out);
 JMC_API int jmc_ctx_destroy(jmc_ctx *ctx);                       /* cuCtxDestroy, nv_dec.cpp:104 */
 JMC_API int jmc_ctx_device(const jmc_ctx *ctx);
@@ -131,6 +139,11 @@ typedef struct jmc_job {
  * aligned (true for cudaMalloc'ed and decoder-mapped surfaces), so the 16-byte-vector kernel can be
  * chosen without reading the lists.  Without it, pointer lists take the any-alignment kernel. */
 #define JMC_JOB_ALIGNED16 1u
+/* every non-NULL surf.list / tight.list / rgb.list is a HOST array of at most JMC_INLINE_LIST_MAX device pointers:
+ * they are passed to the kernel as arguments, nothing is uploaded first (how jm_nvdec_* feeds the few decoder
+ * surfaces it has mapped into one launch).  Alignment is then checked on the host; ALIGNED16 is not needed. */
+#define JMC_JOB_LIST_ON_HOST 2u
+#define JMC_INLINE_LIST_MAX 8
 
 /* Geometry fillers: set width/height/pitch and every offset exactly as the named reference
  * function computes them (odd sizes included).  They leave op-independent fields (frames) alone.

@@ -73,7 +73,12 @@ typedef struct _nv_enc_param {
 JMDLL_FUNC handle_nvenc jm_nvenc_create_handle(void);
 JMDLL_FUNC int jm_nvenc_init(nv_enc_param *in_param, handle_nvenc handle);
 JMDLL_FUNC int jm_nvenc_deinit(handle_nvenc handle);
-/* NULL / 0 length = end of stream (nv_enc.cpp:87,113-117).  -1: no free surface (nv_enc.cpp:90-93). */
+/* NULL / 0 length = end of stream (nv_enc.cpp:87,113-117).  -1: no free surface (nv_enc.cpp:90-93).
+ * In surface-only mode there is no encoder to hand a surface back after its bitstream was fetched
+ * (nv_enc.cpp:204-225), so every uploaded surface stays locked until jm_nvenc_release_surface() is called:
+ * a caller following the reference's call sequence gets -1 on the 11th frame unless it releases.
+ * JM_NVENC_ERR_INVALID_PARAM: yuv_len is shorter than an NV12 / ARGB frame of the configured size (the
+ * reference over-reads the buffer instead, nv_enc.cpp:1029-1040,1096; the YV12 path clamps like the reference). */
 JMDLL_FUNC int jm_nvenc_enc_frame(const unsigned char *in_yuv_buf, const int yuv_len, int *got_packet, handle_nvenc handle);
 /* -1: no packet ready (nv_enc.cpp:175-178) -- always, in surface-only mode */
 JMDLL_FUNC int jm_nvenc_get_bitstream(unsigned char *out_buf, int *out_data_len, int *is_keyframe, handle_nvenc handle);

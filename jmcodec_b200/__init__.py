@@ -7,5 +7,6 @@ built, importing :mod:`jmcodec_b200.lib` raises, and without a CUDA device every
 """
 from .lib import (  # noqa: F401
     JMC_OP, JmcError, Ctx, Job, Frames, Pipeline, Event, NvDec, NvEnc, NvEncParam, RawPacket,
-    device_count, last_error, lib_path, load, build, version,
+    device_count, last_error, lib_path, load, build, version, reload_env,
+    JOB_ALIGNED16, JOB_LIST_ON_HOST, INLINE_LIST_MAX,
 )

@@ -106,6 +106,30 @@ typedef struct {
     void *Reserved3[3];
 } CUVIDPROCPARAMS;
 
+/* cuvidGetDecoderCaps (Video Codec SDK >= 8.0; the headers the reference vendors predate it, so this layout is
+ * restated from the published cuviddec.h and pinned by the static_asserts below: three IN words, three reserved
+ * words, then bIsSupported at byte 24; 88 bytes in every SDK from 8.0 to 12.x -- later SDKs only renamed
+ * reserved words at the end). */
+typedef struct {
+    int eCodecType, eChromaFormat;              /* IN: cudaVideoCodec, cudaVideoChromaFormat */
+    unsigned int nBitDepthMinus8;               /* IN */
+    unsigned int reserved1[3];
+    unsigned char bIsSupported;                 /* OUT */
+    unsigned char nNumNVDECs;                   /* OUT ("reserved2" in SDK 8) */
+    unsigned short nOutputFormatMask;
+    unsigned int nMaxWidth, nMaxHeight, nMaxMBCount;
+    unsigned short nMinWidth, nMinHeight;
+    unsigned char bIsHistogramSupported, nCounterBitDepth;
+    unsigned short nMaxHistogramBins;
+    unsigned int reserved3[10];
+} CUVIDDECODECAPS;
+#ifdef __cplusplus
+static_assert(sizeof(CUVIDDECODECAPS) == 88, "CUVIDDECODECAPS is 88 bytes");
+static_assert(__builtin_offsetof(CUVIDDECODECAPS, bIsSupported) == 24, "bIsSupported follows six 32-bit words");
+static_assert(__builtin_offsetof(CUVIDDECODECAPS, nMaxWidth) == 28 && __builtin_offsetof(CUVIDDECODECAPS, nMinWidth) == 40, "caps limits");
+#endif
+typedef CUVID_RESULT (*tcuvidGetDecoderCaps)(CUVIDDECODECAPS *);
+
 typedef CUVID_RESULT (*tcuvidCreateVideoParser)(CUvideoparser *, CUVIDPARSERPARAMS *);
 typedef CUVID_RESULT (*tcuvidParseVideoData)(CUvideoparser, CUVIDSOURCEDATAPACKET *);
 typedef CUVID_RESULT (*tcuvidDestroyVideoParser)(CUvideoparser);

@@ -1,47 +1,185 @@
 /*
  * jm_nv_dec.cu -- the jm_nvdec_* drop-in API (include/jm_nv_dec.h) over the jmc_* layer.
  *
- * Mirrors the control flow of the reference's nv_dec/nv_dec.cpp with the surface-format path moved
- * onto the device:
+ * Same calls, same return conventions as the reference's nv_dec/nv_dec.cpp; the surface-format path
+ * behind them is batched and overlapped instead of synchronous:
  *
  *   reference                                         here
- *   ------------------------------------------------  ---------------------------------------------
- *   decode_frame: parse -> display queue (:368-403)   decode_frame: front-end -> display queue
- *     pop 1 frame, cuvidMapVideoFrame (:439)            pop 1 frame (device surface + pitch)
- *     cuMemcpyDtoH pitch*h*3/2, SYNC (:452)             ONE kernel: NV12 -> tight NV12 / I420 in HBM
- *   output_frame: CPU strip/de-interleave (:782-820)  output_frame: D2H of the TIGHT frame only
+ *   ------------------------------------------------  ----------------------------------------------------
+ *   decode_frame: parse -> display queue (:368-403)   decode_frame: front-end -> pending surfaces
+ *     pop 1 frame, cuvidMapVideoFrame (:439)            ALL pending surfaces (up to the map limit) are mapped
+ *     cuMemcpyDtoH pitch*h*3/2, SYNC (:452)             and converted by ONE launch (NV12 -> tight NV12 / I420 in
+ *     ONE pinned buffer (MAX_OUTPUT_FRAMES 1)           HBM, pointer list as kernel arguments) into a RING of
+ *                                                       tight frames; the D2H of every tight frame is enqueued at
+ *                                                       once on the delivery stream into a pinned ring slot
+ *                                                       (prefetch); surfaces are unmapped when the convert event
+ *                                                       has fired -- nothing waits per frame
+ *   output_frame: CPU strip/de-interleave (:782-820)  output_frame: waits for THAT frame's delivery events only;
+ *                                                       pinned / registered out_buf: direct DMA of the tight frame;
+ *                                                       pageable out_buf: chunk-pipelined copy out of the pinned ring
+ *
+ * An optional display delay (jm_nvdec_set_display_delay, like the parser's ulMaxDisplayDelay nv_dec.cpp:346)
+ * lets frame k's delivery overlap the upload / decode / conversion of frames k+1.. .
  *
  * Front-ends:
  *   JM_NVDEC_CODEC_RAW_NV12  decoded surfaces as packets (host bytes or device pointers);
  *   bitstream codecs         NVDEC through libnvcuvid.so.1, bound at run time (dlopen): the same
- *                            parser/decoder callback structure as nv_dec.cpp:23-52,278-403,496-540, with
- *                            the mapped device surface fed straight into the conversion kernel
- *                            (no intermediate copy).  If the library or an NVDEC engine is not
- *                            available jm_nvdec_init fails (-4); nothing falls back to a CPU decoder.
+ *                            parser/decoder callback structure as nv_dec.cpp:23-52,278-403,496-540.
+ *                            If the library or an NVDEC engine is not available jm_nvdec_init fails (-4);
+ *                            nothing falls back to a CPU decoder.
  */
 #include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
 
+#include <condition_variable>
 #include <deque>
+#include <mutex>
 #include <new>
+#include <thread>
+#include <vector>
 
 #include "cuvid_min.h"
 #include "jm_nv_dec.h"
 #include "jmc_internal.h"
 
-#define NVDEC_MAX_FRAMES 10         /* display queue depth / decode surfaces, nv_dec/nv_dec.h:32 */
+#define NVDEC_MAX_FRAMES 10         /* decode surfaces / upload surfaces, nv_dec/nv_dec.h:32 */
 #define MAX_LEN_DEC_INFO 1024       /* nv_dec/nv_dec.h:33 */
+#define RING_MAX 32                 /* converted frames a handle holds at most (announced + not yet announced) */
+#define MAX_CHUNKS 8                /* delivery events per frame (chunk-pipelined copy-out) */
+#define MAP_LIMIT_MAX JMC_INLINE_LIST_MAX   /* decoder surfaces mapped at a time = frames per conversion launch */
+#define MAX_DECODE_SURFACES 64
+#define MAX_LAZY_REGS 8
+#define COPY_THREADS_MAX 16
 
 namespace {
 
+int env_int(const char *name, int dflt, int lo, int hi)
+{
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    int v = atoi(e);
+    return v < lo ? lo : (v > hi ? hi : v);
+}
+
+/* ---- host copies: calling thread + optional helper threads --------------------------------------- */
+struct copy_job {
+    uint8_t *dst; size_t dpitch;
+    const uint8_t *src; size_t spitch;
+    size_t width, rows;
+};
+
+void copy_rows(const copy_job &j, size_t r0, size_t r1)
+{
+    if (r1 <= r0) return;
+    if (j.width == j.spitch && j.width == j.dpitch) { memcpy(j.dst + r0 * j.width, j.src + r0 * j.width, (r1 - r0) * j.width); return; }
+    for (size_t r = r0; r < r1; r++) memcpy(j.dst + r * j.dpitch, j.src + r * j.spitch, j.width);
+}
+
+/* A handle's helper threads for host copies between pageable caller memory and the pinned rings.  With no
+ * helpers (the default) copy() is a plain loop on the calling thread. */
+struct copy_pool {
+    std::vector<std::thread> workers;
+    std::mutex m;
+    std::condition_variable cv_work, cv_done;
+    copy_job job;
+    int n_parts = 0, next_part = 0, done_parts = 0;
+    uint64_t gen = 0;
+    bool stop = false;
+
+    void worker()
+    {
+        uint64_t seen = 0;
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv_work.wait(lk, [&] { return stop || (gen != seen && next_part < n_parts); });
+            if (stop) return;
+            seen = gen;
+            while (next_part < n_parts) {
+                const int part = next_part++;
+                const copy_job j = job;
+                const int np = n_parts;
+                lk.unlock();
+                copy_rows(j, j.rows * part / np, j.rows * (part + 1) / np);
+                lk.lock();
+                if (++done_parts == n_parts) cv_done.notify_all();
+            }
+        }
+    }
+
+    void start(int n)
+    {
+        for (int i = (int)workers.size(); i < n; i++) workers.emplace_back([this] { worker(); });
+    }
+
+    void shutdown()
+    {
+        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        cv_work.notify_all();
+        for (auto &t : workers) t.join();
+        workers.clear();
+    }
+
+    void copy(const copy_job &j)
+    {
+        const size_t bytes = j.width * j.rows;
+        if (workers.empty() || bytes < (256u << 10) || j.rows < 2) { copy_rows(j, 0, j.rows); return; }
+        std::unique_lock<std::mutex> lk(m);
+        job = j;
+        n_parts = (int)workers.size() + 1;
+        if ((size_t)n_parts > j.rows) n_parts = (int)j.rows;
+        next_part = done_parts = 0;
+        gen++;
+        cv_work.notify_all();
+        while (next_part < n_parts) {                      /* the caller takes parts too */
+            const int part = next_part++;
+            const int np = n_parts;
+            lk.unlock();
+            copy_rows(j, j.rows * part / np, j.rows * (part + 1) / np);
+            lk.lock();
+            ++done_parts;
+        }
+        cv_done.wait(lk, [&] { return done_parts == n_parts; });
+    }
+
+    void copy_flat(uint8_t *dst, const uint8_t *src, size_t n)
+    {
+        const size_t unit = 4096, rows = n / unit;
+        if (rows) { copy_job j = { dst, unit, src, unit, unit, rows }; copy(j); }
+        if (n % unit) memcpy(dst + rows * unit, src + rows * unit, n % unit);
+    }
+};
+
+/* ---- state --------------------------------------------------------------------------------------- */
 struct decoded_surface {            /* what cuvidMapVideoFrame yields: device pointer + pitch */
     uint8_t *dptr;
     int pitch, width, height;
     int pool_slot;                  /* >= 0: one of our upload surfaces; -1: caller-owned device memory;
                                        -2: a CUVID picture still to be mapped (disp valid) */
+    bool sync_consume;              /* JM_NVDEC_RAW_SYNC: do not return before the kernel has read the surface */
     CUVIDPARSERDISPINFO disp;       /* copied, not pointed to (the reference queues the parser's pointer, nv_dec.cpp:156) */
+};
+
+/* One converted frame: tight NV12 / I420 in device memory, optionally on its way into pinned host memory. */
+struct ring_slot {
+    uint8_t *d_tight = nullptr; size_t d_bytes = 0;
+    uint8_t *h_tight = nullptr; size_t h_bytes = 0;
+    cudaEvent_t converted = nullptr;
+    cudaEvent_t direct = nullptr;           /* a direct D2H / D2D into the caller's buffer has finished */
+    cudaEvent_t delivered[MAX_CHUNKS] = {};
+    int n_chunks = 0;
+    size_t chunk_bytes = 0, total = 0;      /* total: the bytes the reference writes for this frame */
+    bool prefetched = false, busy = false;
+    int w = 0, h = 0;
+};
+
+struct unmap_batch {
+    cudaEvent_t done;
+    CUvideodecoder decoder;
+    int n;
+    unsigned long long ptr[MAP_LIMIT_MAX];
+    int pic[MAP_LIMIT_MAX];
 };
 
 struct cuvid_api {
@@ -56,41 +194,63 @@ struct cuvid_api {
     tcuvidUnmapVideoFrame64 unmap_frame;
 };
 
+struct lazy_reg { void *base; size_t len; };
+
 struct nvdec_b200 {
-    int device;
-    int codec_type;
-    int out_fmt;                    /* 0: NV12, else "YV12" = I420 (nv_dec.h:94) */
-    bool inited, is_eof, is_exit;
-    jmc_ctx *ctx;
+    int device = 0;
+    int codec_type = 0;
+    int out_fmt = 0;                /* 0: NV12, else "YV12" = I420 (nv_dec.h:94) */
+    bool inited = false, is_eof = false, is_exit = false;
+    jmc_ctx *ctx = nullptr;
 
-    /* display queue (nv_dec.h:88-91) */
-    std::deque<decoded_surface> *queue;
+    /* decoded surfaces waiting for conversion (the display queue of nv_dec.h:88-91) */
+    std::deque<decoded_surface> pending;
 
-    /* upload surfaces standing in for the decoder's surfaces (RAW front-end, host payloads) */
-    uint8_t *pool[NVDEC_MAX_FRAMES];
-    bool pool_busy[NVDEC_MAX_FRAMES];
-    size_t pool_bytes;
+    /* upload surfaces standing in for the decoder's surfaces (RAW front-end, host payloads), used round-robin;
+     * h_stage: pinned staging for pageable payloads (compact rows), stage_done: its H2D has been read */
+    uint8_t *pool[NVDEC_MAX_FRAMES] = {};
+    uint8_t *h_stage[NVDEC_MAX_FRAMES] = {};
+    cudaEvent_t stage_done[NVDEC_MAX_FRAMES] = {};
+    bool stage_used[NVDEC_MAX_FRAMES] = {};
+    size_t pool_bytes = 0, stage_bytes = 0;
+    int pool_next = 0;
 
-    /* current output frame (nv_dec.h:119-123): tight frame in device memory */
-    uint8_t *d_tight;
-    size_t d_tight_bytes;
-    bool have_cur;
-    int cur_w, cur_h;
-    int disp_w, disp_h;             /* dec_create_info.ulTargetWidth/Height */
+    /* converted frames: ring + FIFO of announced-later frames + the current output frame (nv_dec.h:119-123) */
+    std::vector<ring_slot> ring;
+    std::deque<int> ready;
+    int cur = -1;
+    int slot_rr = 0;
+    int delay = 0;                  /* frames kept back before they are announced (display delay) */
+    bool staged = true;             /* prefetch tight frames into the pinned ring (pageable out_buf callers) */
+    int lazy_pin = 0;               /* cudaHostRegister a pageable out_buf / in_buf seen twice (opt-in) */
+    const void *cand_out = nullptr, *cand_in = nullptr;
+    std::vector<lazy_reg> regs;     /* registered by us: lazily or through jm_nvdec_memory_register_host */
+    copy_pool copier;
+    int copy_threads = 0;
 
-    uint32_t num_frames;
-    struct timespec t_start;
-    bool started;
-    char dec_info[MAX_LEN_DEC_INFO];
+    int disp_w = 0, disp_h = 0;     /* dec_create_info.ulTargetWidth/Height */
+    uint32_t num_frames = 0, dropped = 0;
+    bool drop_flag = false;
+    struct timespec t_start = {};
+    bool started = false;
+    char dec_info[MAX_LEN_DEC_INFO] = "";
 
     /* NVDEC front-end (nv_dec.h:80-86) */
-    cuvid_api nv;
-    CUvideoparser parser;
-    CUvideodecoder decoder;
-    CUVIDEOFORMATEX parse_ext;
-    int cuvid_codec;
-    bool decoder_failed;
+    cuvid_api nv = {};
+    CUvideoparser parser = nullptr;
+    CUvideodecoder decoder = nullptr;
+    CUVIDEOFORMATEX parse_ext = {};
+    int cuvid_codec = 0;
+    bool decoder_failed = false;
+    int map_limit = MAP_LIMIT_MAX, n_mapped = 0;
+    int n_decode_surfaces = 0;
+    int in_use[MAX_DECODE_SURFACES] = {};   /* displayed, not yet converted + unmapped (nv_dec.h:90 is_frame_in_use) */
+    std::deque<unmap_batch> unmaps;
+    std::vector<cudaEvent_t> free_events;
 };
+
+cudaStream_t convert_stream(nvdec_b200 *c) { return (cudaStream_t)jmc_ctx_stream(c->ctx, 0); }
+cudaStream_t delivery_stream(nvdec_b200 *c) { return (cudaStream_t)jmc_ctx_stream(c->ctx, 2); }
 
 const char *codec_name(int t)
 {
@@ -126,18 +286,148 @@ void show_info(nvdec_b200 *c)       /* nv_dec.cpp:663-683 */
              (int)c->num_frames, (int)ms, ms > 0 ? c->num_frames * 1e3 / ms : 0.0);
 }
 
-int ensure_tight(nvdec_b200 *c, int w, int h)
+void mark_started(nvdec_b200 *c)
+{
+    if (!c->started) { clock_gettime(CLOCK_MONOTONIC, &c->t_start); c->started = true; }   /* nv_dec.cpp:537 */
+}
+
+/* ---- events, ring slots -------------------------------------------------------------------------- */
+cudaEvent_t get_event(nvdec_b200 *c)
+{
+    if (!c->free_events.empty()) { cudaEvent_t e = c->free_events.back(); c->free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return e;
+}
+
+/* bytes of a tight frame the reference actually writes: for odd sizes fewer than w*h*3/2, the rest of
+ * out_buf stays untouched (h>>1 chroma rows, w>>1 samples: nv_dec.cpp:792-796,807-818) */
+size_t written_bytes(int out_fmt, int w, int h)
+{
+    const size_t luma = (size_t)w * h;
+    return out_fmt == 0 ? luma + (size_t)(h >> 1) * w : luma + 2 * (size_t)(w >> 1) * (h >> 1);
+}
+
+/* A free ring slot able to hold a w x h frame, or -1 (ring full / out of memory).  Slots are taken round-robin
+ * so that a slot whose delivery may still be in flight is reused as late as possible; the convert stream waits
+ * for that delivery before the slot's device frame is overwritten. */
+int acquire_slot(nvdec_b200 *c, int w, int h)
 {
     size_t need = (size_t)jmc_tight_bytes(w, h);
     if (need == 0) need = 1;
-    if (c->d_tight && c->d_tight_bytes >= need) return 0;
-    if (c->d_tight) { jmc_ctx_sync(c->ctx); jmc_free_device(c->ctx, c->d_tight); c->d_tight = nullptr; }
-    void *p = nullptr;
-    int r = jmc_alloc_device(c->ctx, need, &p);     /* replaces cuMemAllocHost(pitch*h*3/2), nv_dec.cpp:569 */
-    if (r) return r;
-    c->d_tight = (uint8_t *)p;
-    c->d_tight_bytes = need;
-    return 0;
+    int idx = -1;
+    const int n = (int)c->ring.size();
+    for (int k = 0; k < n; k++) {
+        const int i = (c->slot_rr + k) % n;
+        if (!c->ring[i].busy) { idx = i; break; }
+    }
+    if (idx < 0) {
+        if (n >= RING_MAX) return -1;
+        c->ring.emplace_back();
+        idx = n;
+    }
+    ring_slot &s = c->ring[idx];
+    if (!s.converted) {
+        if (cudaEventCreateWithFlags(&s.converted, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
+        if (cudaEventCreateWithFlags(&s.direct, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
+        for (int i = 0; i < MAX_CHUNKS; i++)
+            if (cudaEventCreateWithFlags(&s.delivered[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
+    }
+    if (s.d_bytes < need) {                                   /* replaces cuMemAllocHost(pitch*h*3/2), nv_dec.cpp:569 */
+        if (s.d_tight) { cudaFree(s.d_tight); s.d_tight = nullptr; s.d_bytes = 0; }   /* cudaFree waits for the device */
+        if (cudaMalloc((void **)&s.d_tight, need) != cudaSuccess) { cudaGetLastError(); jmc_set_error("out of device memory for a %dx%d frame", w, h); return -1; }
+        s.d_bytes = need;
+        s.prefetched = false;
+    }
+    if (s.prefetched && s.n_chunks > 0)                       /* the previous frame's D2H may still be reading d_tight */
+        cudaStreamWaitEvent(convert_stream(c), s.delivered[s.n_chunks - 1], 0);
+    s.prefetched = false;
+    s.n_chunks = 0;
+    s.w = w; s.h = h;
+    s.total = written_bytes(c->out_fmt, w, h);
+    s.busy = true;
+    c->slot_rr = (idx + 1) % (int)c->ring.size();
+    return idx;
+}
+
+void release_slot(nvdec_b200 *c, int idx)
+{
+    if (idx >= 0) c->ring[idx].busy = false;
+}
+
+/* Enqueue the D2H of a converted frame into the slot's pinned buffer on the delivery stream, in chunks with an
+ * event each, so that output_frame can copy chunk i out while chunk i+1 is still crossing PCIe. */
+bool prefetch_slot(nvdec_b200 *c, ring_slot &s)
+{
+    if (s.prefetched) return true;
+    if (s.h_bytes < s.d_bytes) {
+        if (s.h_tight) { cudaFreeHost(s.h_tight); s.h_tight = nullptr; s.h_bytes = 0; }
+        if (cudaHostAlloc((void **)&s.h_tight, s.d_bytes, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError();
+            jmc_set_error("out of pinned host memory for the delivery ring");
+            return false;
+        }
+        s.h_bytes = s.d_bytes;
+    }
+    cudaStream_t ds = delivery_stream(c);
+    if (cudaStreamWaitEvent(ds, s.converted, 0) != cudaSuccess) return false;
+    /* no display delay: output_frame is waiting for this very frame, so pipeline its copy-out against the DMA;
+     * with a delay the frame lands long before it is fetched and one copy is cheapest for the link */
+    int chunks = c->delay > 0 ? 1 : (int)(s.total / (512u << 10));
+    chunks = chunks < 1 ? 1 : (chunks > MAX_CHUNKS ? MAX_CHUNKS : chunks);
+    const size_t cb = ((s.total + chunks - 1) / chunks + 4095) & ~(size_t)4095;
+    s.chunk_bytes = cb ? cb : 4096;
+    s.n_chunks = 0;
+    for (size_t off = 0; off < s.total || s.n_chunks == 0; off += s.chunk_bytes) {
+        const size_t n = s.total - off < s.chunk_bytes ? s.total - off : s.chunk_bytes;
+        if (n && cudaMemcpyAsync(s.h_tight + off, s.d_tight + off, n, cudaMemcpyDeviceToHost, ds) != cudaSuccess) return false;
+        if (cudaEventRecord(s.delivered[s.n_chunks], ds) != cudaSuccess) return false;
+        s.n_chunks++;
+        if (s.total == 0) break;
+    }
+    s.prefetched = true;
+    return true;
+}
+
+/* ---- host memory classification / registration ----------------------------------------------------- */
+enum { MEM_PAGEABLE = 0, MEM_PINNED = 1, MEM_DEVICE = 2 };
+
+/* What kind of memory is [p, p+len)?  Both ends must agree; anything the copy engine cannot reach directly
+ * (plain malloc memory, managed memory) counts as pageable. */
+int host_kind_of(const void *p, size_t len)
+{
+    if (!p) return MEM_PAGEABLE;
+    int kind = -1;
+    cudaPointerAttributes a;
+    for (int end = 0; end < 2; end++) {
+        const void *q = end ? (const uint8_t *)p + (len ? len - 1 : 0) : p;
+        if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return MEM_PAGEABLE; }
+        const int k = a.type == cudaMemoryTypeHost ? MEM_PINNED : (a.type == cudaMemoryTypeDevice ? MEM_DEVICE : MEM_PAGEABLE);
+        if (kind >= 0 && k != kind) return MEM_PAGEABLE;
+        kind = k;
+    }
+    return kind;
+}
+
+bool is_device_accessible_host(const void *p, size_t len) { return host_kind_of(p, len) == MEM_PINNED; }
+
+bool register_range(nvdec_b200 *c, const void *p, size_t len)
+{
+    const uintptr_t page = 4096, lo = (uintptr_t)p & ~(page - 1), hi = ((uintptr_t)p + len + page - 1) & ~(page - 1);
+    if ((int)c->regs.size() >= MAX_LAZY_REGS * 4) return false;
+    if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return false; }
+    c->regs.push_back({ (void *)lo, hi - lo });
+    return true;
+}
+
+/* Opt-in (JMC_NVDEC_LAZY_PIN=1 / jm_nvdec_set_option): a pageable caller buffer seen on two consecutive calls is
+ * page-locked in place so that it receives / supplies frames by direct DMA.  Off by default: the registration
+ * outlives a free() of the buffer by the caller, which the library cannot observe. */
+bool maybe_lazy_pin(nvdec_b200 *c, const void *p, size_t len, const void **cand)
+{
+    if (!c->lazy_pin) return false;
+    if (*cand != p) { *cand = p; return false; }
+    return register_range(c, p, len);
 }
 
 /* ---- NVDEC front-end ------------------------------------------------------------------------ */
@@ -175,30 +465,57 @@ bool cuvid_load(nvdec_b200 *c)
         jmc_set_error("the NVDEC library lacks a required cuvid* entry point");
         return false;
     }
-    /* Is there an engine behind it?  (cuvidGetDecoderCaps exists since SDK 8; CUVIDDECODECAPS starts with
-     * codec, chroma, bit depth, 3 reserved words, then bIsSupported.) */
-    typedef int (*tcaps)(void *);
-    tcaps caps = (tcaps)dlsym(l, "cuvidGetDecoderCaps");
+    /* Is there an engine behind it?  (cuvidGetDecoderCaps exists since Video Codec SDK 8; layout: cuvid_min.h) */
+    tcuvidGetDecoderCaps caps = (tcuvidGetDecoderCaps)dlsym(l, "cuvidGetDecoderCaps");
     if (caps) {
-        struct { int codec, chroma; unsigned int depth_minus8, r1[3]; unsigned char supported, n_engines; unsigned char rest[80]; } q;
+        CUVIDDECODECAPS q;
         memset(&q, 0, sizeof(q));
-        q.codec = c->cuvid_codec; q.chroma = CUVID_CHROMA_420;
+        q.eCodecType = c->cuvid_codec; q.eChromaFormat = CUVID_CHROMA_420; q.nBitDepthMinus8 = 0;
         int r = caps(&q);
-        if (r != 0 || !q.supported) {
-            jmc_set_error("NVDEC is not usable here: cuvidGetDecoderCaps returned %d, supported=%d", r, (int)q.supported);
+        if (r != 0 || !q.bIsSupported) {
+            jmc_set_error("NVDEC is not usable here: cuvidGetDecoderCaps returned %d, supported=%d", r, (int)q.bIsSupported);
             return false;
         }
     }
     return true;
 }
 
+int convert_stage(nvdec_b200 *c, bool must_progress);
+void reap_unmaps(nvdec_b200 *c, bool wait_all);
+
+/* Everything that still refers to the current decoder -- displayed pictures not yet converted, mapped
+ * surfaces not yet unmapped -- is converted into ring slots and released.  Frames the ring cannot take are
+ * dropped (counted, reported by jm_nvdec_decode_frame). */
+void cuvid_drain(nvdec_b200 *c)
+{
+    while (!c->pending.empty()) {
+        if (convert_stage(c, true) <= 0) break;
+    }
+    while (!c->pending.empty()) {                                         /* ring full and nothing fetchable: give up on them */
+        if (c->pending.front().pool_slot == -2) {
+            const int idx = c->pending.front().disp.picture_index;
+            if (idx >= 0 && idx < MAX_DECODE_SURFACES && c->in_use[idx] > 0) c->in_use[idx]--;
+        }
+        c->pending.pop_front();
+        c->dropped++; c->drop_flag = true;
+    }
+    reap_unmaps(c, true);
+}
+
 /* nvdec_create_decoder, nv_dec.cpp:496-540, called from the parser on the caller's thread */
 int cuvid_on_sequence(void *user, CUVIDEOFORMAT *f)
 {
     nvdec_b200 *c = (nvdec_b200 *)user;
-    if (c->decoder) { c->nv.destroy_decoder(c->decoder); c->decoder = nullptr; }
+    if (c->decoder) {
+        /* format change: pictures of the old decoder are still queued -- convert and unmap them first, the
+         * indices mean nothing to the new decoder */
+        cuvid_drain(c);
+        c->nv.destroy_decoder(c->decoder);
+        c->decoder = nullptr;
+    }
     unsigned surfaces = NVDEC_MAX_FRAMES;                                 /* :526 */
     if (f->min_num_decode_surfaces > surfaces) surfaces = f->min_num_decode_surfaces;
+    if (surfaces > MAX_DECODE_SURFACES) surfaces = MAX_DECODE_SURFACES;
     CUVIDDECODECREATEINFO ci;
     memset(&ci, 0, sizeof(ci));
     ci.CodecType = f->codec;
@@ -215,7 +532,9 @@ int cuvid_on_sequence(void *user, CUVIDEOFORMAT *f)
     ci.display_area.right = (short)f->display_area.right;
     ci.display_area.bottom = (short)f->display_area.bottom;
     ci.ulNumDecodeSurfaces = surfaces;
-    ci.ulNumOutputSurfaces = 2;                                           /* the reference maps one at a time (:527) */
+    /* the reference maps one surface at a time (:527); here up to map_limit displayed pictures are mapped
+     * together and converted by one launch */
+    ci.ulNumOutputSurfaces = (unsigned long)c->map_limit;
     ci.ulCreationFlags = CUVID_CREATE_PREFER_CUVID;                       /* :528 */
     ci.vidLock = nullptr;                                                 /* as the reference: never created (nv_dec.h:96) */
     int r = c->nv.create_decoder(&c->decoder, &ci);
@@ -227,9 +546,12 @@ int cuvid_on_sequence(void *user, CUVIDEOFORMAT *f)
         return 0;                                                         /* stop the parser */
     }
     c->decoder_failed = false;
+    c->n_decode_surfaces = (int)surfaces;
+    memset(c->in_use, 0, sizeof(c->in_use));
+    c->n_mapped = 0;
     c->disp_w = (int)ci.ulTargetWidth;
     c->disp_h = (int)ci.ulTargetHeight;
-    if (!c->started) { clock_gettime(CLOCK_MONOTONIC, &c->t_start); c->started = true; }   /* :537 */
+    mark_started(c);                                                      /* :537 */
     return (int)surfaces;                                                 /* > 1: tells newer parsers the surface count */
 }
 
@@ -237,6 +559,14 @@ int cuvid_on_decode(void *user, void *pic)                                /* nv_
 {
     nvdec_b200 *c = (nvdec_b200 *)user;
     if (!c->decoder) return 0;
+    /* The target surface may still hold a displayed picture that has not been converted yet (a packet with
+     * many pictures): get it out of the decoder before it is overwritten.  The reference sets is_frame_in_use
+     * (nv_dec.cpp:155) and never looks at it. */
+    const int idx = ((const CUVIDPICPARAMS_HEAD *)pic)->CurrPicIdx;
+    if (idx >= 0 && idx < MAX_DECODE_SURFACES && c->in_use[idx] > 0) {
+        cuvid_drain(c);
+        c->in_use[idx] = 0;
+    }
     return c->nv.decode_picture(c->decoder, pic) == 0 ? 1 : 0;
 }
 
@@ -249,7 +579,9 @@ int cuvid_on_display(void *user, CUVIDPARSERDISPINFO *d)                  /* nv_
     memset(&s, 0, sizeof(s));
     s.pool_slot = -2;
     s.disp = *d;
-    c->queue->push_back(s);
+    s.width = c->disp_w; s.height = c->disp_h;                            /* ulTargetWidth/Height, :440-442 */
+    if (d->picture_index >= 0 && d->picture_index < MAX_DECODE_SURFACES) c->in_use[d->picture_index]++;   /* :155 */
+    c->pending.push_back(s);
     return 1;
 }
 
@@ -270,7 +602,7 @@ int cuvid_open(nvdec_b200 *c, const char *extra, int len)                 /* nvd
         memcpy(c->parse_ext.raw_seqhdr_data, extra, (size_t)n);
     }
     pp.ulMaxNumDecodeSurfaces = NVDEC_MAX_FRAMES;                         /* :345 */
-    pp.ulMaxDisplayDelay = 2;                                             /* :346 */
+    pp.ulMaxDisplayDelay = (unsigned)env_int("JMC_NVDEC_PARSER_DELAY", 2, 0, 8);   /* :346 */
     pp.pUserData = c;
     pp.pfnSequenceCallback = cuvid_on_sequence;
     pp.pfnDecodePicture = cuvid_on_decode;
@@ -301,14 +633,33 @@ void cuvid_packet(nvdec_b200 *c, const unsigned char *buf, int len)       /* nvd
     c->nv.parse(c->parser, &pkt);
 }
 
+/* Surfaces go back to the decoder once the launch that read them has finished (nv_dec.cpp:469) -- checked
+ * without blocking on every call; waited for only when the map limit is reached or the decoder goes away. */
+void reap_unmaps(nvdec_b200 *c, bool wait_all)
+{
+    while (!c->unmaps.empty()) {
+        unmap_batch &b = c->unmaps.front();
+        if (wait_all) cudaEventSynchronize(b.done);
+        else if (cudaEventQuery(b.done) != cudaSuccess) { cudaGetLastError(); break; }
+        for (int i = 0; i < b.n; i++) {
+            if (b.decoder == c->decoder && c->decoder) c->nv.unmap_frame(c->decoder, b.ptr[i]);
+            if (b.pic[i] >= 0 && b.pic[i] < MAX_DECODE_SURFACES && c->in_use[b.pic[i]] > 0) c->in_use[b.pic[i]]--;   /* nvdec_frame_item_release, :458 */
+            c->n_mapped--;
+        }
+        c->free_events.push_back(b.done);
+        c->unmaps.pop_front();
+    }
+}
+
 void cuvid_close(nvdec_b200 *c)
 {
+    if (c->decoder) reap_unmaps(c, true);
     if (c->parser) { c->nv.destroy_parser(c->parser); c->parser = nullptr; }     /* nv_dec.cpp:95-101 */
     if (c->decoder) { c->nv.destroy_decoder(c->decoder); c->decoder = nullptr; }
     if (c->nv.lib) { dlclose(c->nv.lib); c->nv.lib = nullptr; }
 }
 
-/* RAW front-end: one packet = one decoded surface -> display queue */
+/* ---- RAW front-end: one packet = one decoded surface -> pending ------------------------------------ */
 int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
 {
     if (len < (int)sizeof(jm_nvdec_raw_packet)) return -1;
@@ -316,92 +667,238 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
     memcpy(&h, buf, sizeof(h));
     if (h.magic != JM_NVDEC_RAW_MAGIC || h.width < 0 || h.height < 0 || h.pitch < h.width) return -1;
     if ((int64_t)h.pitch * h.height * 3 / 2 > 0x7fffffffll) return -1;     /* the API counts frame bytes in int (nv_dec.cpp:773) */
-    if ((int)c->queue->size() >= NVDEC_MAX_FRAMES) return -1;            /* all decode surfaces in use */
     decoded_surface s;
     memset(&s, 0, sizeof(s));
     s.width = h.width; s.height = h.height; s.pitch = h.pitch;
+    s.sync_consume = (h.flags & JM_NVDEC_RAW_SYNC) != 0;
+    cudaStream_t st = convert_stream(c);
     if (h.flags & JM_NVDEC_RAW_DEVICE_PTR) {
         s.dptr = (uint8_t *)(uintptr_t)h.device_ptr;
         s.pool_slot = -1;
+        if (h.flags & JM_NVDEC_RAW_WAIT_EVENT) {
+            /* the surface is being produced on another stream: order the conversion after the caller's event */
+            if (len < (int)sizeof(jm_nvdec_raw_packet_ex)) return -1;
+            jm_nvdec_raw_packet_ex x;
+            memcpy(&x, buf, sizeof(x));
+            if (x.ready_event && cudaStreamWaitEvent(st, (cudaEvent_t)(uintptr_t)x.ready_event, 0) != cudaSuccess) { cudaGetLastError(); return -1; }
+        }
     } else {
         const size_t bytes = (size_t)h.pitch * h.height * 3 / 2;         /* nv_dec.cpp:453 */
         if ((size_t)len < sizeof(h) + bytes) return -1;
         if (bytes > c->pool_bytes) {                                     /* geometry grew: new surfaces */
-            jmc_ctx_sync(c->ctx);
-            if (!c->queue->empty()) return -1;
-            for (int i = 0; i < NVDEC_MAX_FRAMES; i++) if (c->pool[i]) { jmc_free_device(c->ctx, c->pool[i]); c->pool[i] = nullptr; }
+            cudaStreamSynchronize(st);
+            for (int i = 0; i < NVDEC_MAX_FRAMES; i++) if (c->pool[i]) { cudaFree(c->pool[i]); c->pool[i] = nullptr; }
             c->pool_bytes = bytes;
         }
-        int slot = -1;
-        for (int i = 0; i < NVDEC_MAX_FRAMES; i++) if (!c->pool_busy[i]) { slot = i; break; }
-        if (slot < 0) return -1;
+        const int slot = c->pool_next;
+        c->pool_next = (c->pool_next + 1) % NVDEC_MAX_FRAMES;
         if (!c->pool[slot]) {
-            void *p = nullptr;
-            if (jmc_alloc_device(c->ctx, c->pool_bytes ? c->pool_bytes : 1, &p)) return -1;
-            c->pool[slot] = (uint8_t *)p;
+            if (cudaMalloc((void **)&c->pool[slot], c->pool_bytes ? c->pool_bytes : 1) != cudaSuccess) { cudaGetLastError(); return -1; }
         }
-        /* the "decode": the surface lands in HBM.  in_buf is consumed before we return. */
-        cudaStream_t st = (cudaStream_t)jmc_ctx_stream(c->ctx, 0);
-        if (cudaMemcpyAsync(c->pool[slot], buf + sizeof(h), bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
-        if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
-        c->pool_busy[slot] = true;
+        /* the "decode": the surface lands in HBM; only the active `width` bytes of every row are moved.
+         * in_buf is consumed before we return. */
+        const uint8_t *src = buf + sizeof(h);
+        const size_t rows = (size_t)h.height * 3 / 2, wbytes = (size_t)h.width;
+        if (bytes > 0 && wbytes > 0 && rows > 0) {
+            bool pinned = is_device_accessible_host(src, bytes);
+            if (!pinned && maybe_lazy_pin(c, buf, (size_t)len, &c->cand_in)) pinned = true;
+            if (pinned) {
+                /* pinned / registered payload: DMA straight out of the caller's buffer, complete before returning */
+                if (cudaMemcpy2DAsync(c->pool[slot], (size_t)h.pitch, src, (size_t)h.pitch, wbytes, rows, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return -1; }
+                if (cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return -1; }
+            } else {
+                /* pageable payload: compact the rows into this surface's pinned staging buffer (the call returns when
+                 * in_buf has been read) and let the H2D run behind us */
+                const size_t need = wbytes * rows;
+                if (need > c->stage_bytes) {
+                    cudaStreamSynchronize(st);
+                    for (int i = 0; i < NVDEC_MAX_FRAMES; i++) if (c->h_stage[i]) { cudaFreeHost(c->h_stage[i]); c->h_stage[i] = nullptr; }
+                    c->stage_bytes = need;
+                }
+                if (!c->h_stage[slot] && cudaHostAlloc((void **)&c->h_stage[slot], c->stage_bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return -1; }
+                if (!c->stage_done[slot] && cudaEventCreateWithFlags(&c->stage_done[slot], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
+                if (c->stage_used[slot]) cudaEventSynchronize(c->stage_done[slot]);        /* ten uploads ago: long done */
+                copy_job cj = { c->h_stage[slot], wbytes, src, (size_t)h.pitch, wbytes, rows };
+                c->copier.copy(cj);
+                if (cudaMemcpy2DAsync(c->pool[slot], (size_t)h.pitch, c->h_stage[slot], wbytes, wbytes, rows, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return -1; }
+                cudaEventRecord(c->stage_done[slot], st);
+                c->stage_used[slot] = true;
+            }
+        }
         s.dptr = c->pool[slot];
         s.pool_slot = slot;
     }
-    if (!c->started) { clock_gettime(CLOCK_MONOTONIC, &c->t_start); c->started = true; }   /* nv_dec.cpp:537 */
+    mark_started(c);
     c->disp_w = h.width; c->disp_h = h.height;
     c->num_frames += 1;                                                   /* nv_dec.cpp:48 */
-    c->queue->push_back(s);
+    c->pending.push_back(s);
     return 0;
 }
 
-/* nvdec_decode_output_frame, nv_dec.cpp:406-478 */
-void output_stage(nvdec_b200 *c, int *got_frame)
+/* ---- conversion: nvdec_decode_output_frame (nv_dec.cpp:406-478) for a whole batch ------------------- */
+/* Converts the longest run of pending surfaces that share one geometry (at most MAP_LIMIT_MAX, at most the free
+ * ring slots, at most the free map slots) with ONE launch.  Returns the number of frames converted, 0 if
+ * nothing could be done now (ring full), < 0 on error.  must_progress: wait for outstanding unmaps instead of
+ * giving up when the map limit is reached. */
+int convert_stage(nvdec_b200 *c, bool must_progress)
 {
-    if (c->queue->empty()) {
-        if (c->is_eof) { c->is_exit = true; show_info(c); }               /* :460-466 */
-        return;
+    if (c->pending.empty()) return 0;
+    const bool cuvid = c->pending.front().pool_slot == -2;
+    if (cuvid && !c->decoder) {                                           /* :414-417 */
+        while (!c->pending.empty() && c->pending.front().pool_slot == -2) c->pending.pop_front();
+        return -1;
     }
-    decoded_surface s = c->queue->front();
-    c->queue->pop_front();
-    unsigned long long mapped = 0;
-    if (s.pool_slot == -2) {
-        /* cuvidMapVideoFrame (nv_dec.cpp:427-442): post-processed NV12 surface, produced on OUR convert
-         * stream so the kernel below is ordered after it without a host sync */
-        if (!c->decoder) return;                                          /* :414-417 */
-        CUVIDPROCPARAMS pp;
-        memset(&pp, 0, sizeof(pp));
-        pp.progressive_frame = s.disp.progressive_frame;
-        pp.top_field_first = s.disp.top_field_first;
-        pp.unpaired_field = s.disp.repeat_first_field < 0;
-        pp.output_stream = jmc_ctx_stream(c->ctx, 0);
-        unsigned int pitch = 0;
-        if (c->nv.map_frame(c->decoder, s.disp.picture_index, &mapped, &pitch, &pp) != 0 || !mapped) return;
-        s.dptr = (uint8_t *)(uintptr_t)mapped;
-        s.pitch = (int)pitch;
-        s.width = c->disp_w;                                              /* ulTargetWidth/Height, :440-442 */
-        s.height = c->disp_h;
+    int limit = MAP_LIMIT_MAX;
+    if (cuvid) {
+        if (c->n_mapped >= c->map_limit) reap_unmaps(c, false);
+        if (c->n_mapped >= c->map_limit) {
+            if (!must_progress && c->map_limit > 1) return 0;
+            reap_unmaps(c, true);
+        }
+        limit = c->map_limit - c->n_mapped;
+        if (limit > MAP_LIMIT_MAX) limit = MAP_LIMIT_MAX;
+        if (limit < 1) return 0;
     }
-    if (ensure_tight(c, s.width, s.height) == 0) {
-        jmc_job j;
-        memset(&j, 0, sizeof(j));
-        jmc_job_nvdec(&j, s.width, s.height, s.pitch, c->out_fmt);
-        j.n_frames = 1;
-        j.surf.base = s.dptr;
-        j.tight.base = c->d_tight;
-        /* same stream as the upload, so the surface slot can be recycled right away */
-        if (jmc_convert(c->ctx, &j, nullptr) == JMC_OK) {
-            c->have_cur = true;
-            c->cur_w = s.width; c->cur_h = s.height;
-            *got_frame = 1;                                               /* :455 */
+    const decoded_surface first = c->pending.front();
+    int slots[MAP_LIMIT_MAX];
+    decoded_surface surf[MAP_LIMIT_MAX];
+    unsigned long long mapped[MAP_LIMIT_MAX];
+    int k = 0;
+    int pitch = first.pitch;
+    while (k < limit && !c->pending.empty()) {
+        decoded_surface s = c->pending.front();
+        if ((s.pool_slot == -2) != cuvid || s.width != first.width || s.height != first.height) break;
+        if (!cuvid && s.pitch != pitch) break;
+        const int slot = acquire_slot(c, s.width, s.height);
+        if (slot < 0) break;
+        mapped[k] = 0;
+        if (cuvid) {
+            /* cuvidMapVideoFrame (nv_dec.cpp:427-442): post-processed NV12 surface, produced on OUR convert
+             * stream so that the kernel below is ordered after it without a host sync */
+            CUVIDPROCPARAMS pp;
+            memset(&pp, 0, sizeof(pp));
+            pp.progressive_frame = s.disp.progressive_frame;
+            pp.top_field_first = s.disp.top_field_first;
+            pp.unpaired_field = s.disp.repeat_first_field < 0;
+            pp.output_stream = convert_stream(c);
+            unsigned int mp = 0;
+            if (c->nv.map_frame(c->decoder, s.disp.picture_index, &mapped[k], &mp, &pp) != 0 || !mapped[k]) {
+                release_slot(c, slot);
+                if (k == 0) {                                             /* cannot be mapped at all: skip it */
+                    const int idx = s.disp.picture_index;
+                    if (idx >= 0 && idx < MAX_DECODE_SURFACES && c->in_use[idx] > 0) c->in_use[idx]--;
+                    c->pending.pop_front();
+                    c->dropped++; c->drop_flag = true;
+                    return -1;
+                }
+                break;
+            }
+            if (k > 0 && (int)mp != pitch) {                              /* never seen; a new launch takes it */
+                c->nv.unmap_frame(c->decoder, mapped[k]);
+                release_slot(c, slot);
+                break;
+            }
+            c->n_mapped++;
+            s.dptr = (uint8_t *)(uintptr_t)mapped[k];
+            s.pitch = pitch = (int)mp;
+        }
+        slots[k] = slot;
+        surf[k] = s;
+        c->pending.pop_front();
+        k++;
+    }
+    if (k == 0) return 0;
+
+    jmc_job j;
+    memset(&j, 0, sizeof(j));
+    jmc_job_nvdec(&j, first.width, first.height, pitch, c->out_fmt);
+    j.n_frames = k;
+    void *slist[MAP_LIMIT_MAX], *tlist[MAP_LIMIT_MAX];
+    if (k == 1) {
+        j.surf.base = surf[0].dptr;
+        j.tight.base = c->ring[slots[0]].d_tight;
+    } else {
+        for (int i = 0; i < k; i++) { slist[i] = surf[i].dptr; tlist[i] = c->ring[slots[i]].d_tight; }
+        j.surf.list = slist;
+        j.tight.list = tlist;
+        j.flags = JMC_JOB_LIST_ON_HOST;                                   /* the pointers ride in the kernel arguments */
+    }
+    cudaStream_t st = convert_stream(c);
+    const int r = jmc_launch_job(c->ctx, &j, st);
+    bool ok = r == JMC_OK;
+    bool need_sync = false;
+    for (int i = 0; i < k && ok; i++) {
+        ring_slot &s = c->ring[slots[i]];
+        ok = cudaEventRecord(s.converted, st) == cudaSuccess;
+        if (ok && c->staged) ok = prefetch_slot(c, s);
+        need_sync = need_sync || surf[i].sync_consume;
+    }
+    if (cuvid) {
+        unmap_batch b;
+        b.done = get_event(c);
+        b.decoder = c->decoder;
+        b.n = k;
+        for (int i = 0; i < k; i++) { b.ptr[i] = mapped[i]; b.pic[i] = surf[i].disp.picture_index; }
+        if (b.done && cudaEventRecord(b.done, st) == cudaSuccess) c->unmaps.push_back(b);
+        else {                                                            /* no event: fall back to waiting */
+            cudaStreamSynchronize(st);
+            for (int i = 0; i < k; i++) {
+                c->nv.unmap_frame(c->decoder, mapped[i]);
+                if (b.pic[i] >= 0 && b.pic[i] < MAX_DECODE_SURFACES && c->in_use[b.pic[i]] > 0) c->in_use[b.pic[i]]--;
+                c->n_mapped--;
+            }
+            if (b.done) c->free_events.push_back(b.done);
         }
     }
-    if (s.pool_slot >= 0) c->pool_busy[s.pool_slot] = false;              /* nvdec_frame_item_release, :458 */
-    if (mapped) {
-        /* the surface goes back to the decoder only after the kernel has consumed it (:469) */
-        cudaStreamSynchronize((cudaStream_t)jmc_ctx_stream(c->ctx, 0));
-        c->nv.unmap_frame(c->decoder, mapped);
+    if (!ok) {
+        cudaGetLastError();
+        for (int i = 0; i < k; i++) release_slot(c, slots[i]);
+        c->dropped += (uint32_t)k; c->drop_flag = true;
+        return -1;
     }
+    if (need_sync) cudaEventSynchronize(c->ring[slots[k - 1]].converted);
+    for (int i = 0; i < k; i++) c->ready.push_back(slots[i]);
+    return k;
+}
+
+void free_everything(nvdec_b200 *c)
+{
+    for (auto &s : c->ring) {
+        if (s.d_tight) cudaFree(s.d_tight);
+        if (s.h_tight) cudaFreeHost(s.h_tight);
+        if (s.converted) cudaEventDestroy(s.converted);
+        if (s.direct) cudaEventDestroy(s.direct);
+        for (int i = 0; i < MAX_CHUNKS; i++) if (s.delivered[i]) cudaEventDestroy(s.delivered[i]);
+    }
+    c->ring.clear();
+    c->ready.clear();
+    c->cur = -1;
+    for (int i = 0; i < NVDEC_MAX_FRAMES; i++) {
+        if (c->pool[i]) { cudaFree(c->pool[i]); c->pool[i] = nullptr; }
+        if (c->h_stage[i]) { cudaFreeHost(c->h_stage[i]); c->h_stage[i] = nullptr; }
+        if (c->stage_done[i]) { cudaEventDestroy(c->stage_done[i]); c->stage_done[i] = nullptr; }
+        c->stage_used[i] = false;
+    }
+    c->pool_bytes = c->stage_bytes = 0;
+    for (cudaEvent_t e : c->free_events) cudaEventDestroy(e);
+    c->free_events.clear();
+    for (auto &r : c->regs) cudaHostUnregister(r.base);
+    c->regs.clear();
+    c->pending.clear();
+}
+
+void teardown(nvdec_b200 *c)
+{
+    if (!c->ctx) return;
+    {
+        jmc_device_guard g(c->ctx);
+        jmc_ctx_sync(c->ctx);
+        cuvid_close(c);
+        free_everything(c);
+    }
+    jmc_ctx_destroy(c->ctx);
+    c->ctx = nullptr;
+    c->inited = false;
 }
 
 } /* namespace */
@@ -410,10 +907,13 @@ extern "C" {
 
 handle_nvdec jm_nvdec_create_handle(void)
 {
-    nvdec_b200 *c = (nvdec_b200 *)calloc(1, sizeof(nvdec_b200));
+    nvdec_b200 *c = new (std::nothrow) nvdec_b200();                   /* new + memset, nv_dec.cpp:54-60 */
     if (!c) return nullptr;
-    const char *e = getenv("JMC_DEVICE");
-    c->device = e ? atoi(e) : 0;
+    c->device = env_int("JMC_DEVICE", 0, 0, 1023);
+    c->delay = env_int("JMC_NVDEC_DISPLAY_DELAY", 0, 0, RING_MAX - MAP_LIMIT_MAX - 2);
+    c->copy_threads = env_int("JMC_NVDEC_COPY_THREADS", 0, 0, COPY_THREADS_MAX);
+    c->lazy_pin = env_int("JMC_NVDEC_LAZY_PIN", 0, 0, 1);
+    c->map_limit = env_int("JMC_NVDEC_MAP_LIMIT", MAP_LIMIT_MAX, 1, MAP_LIMIT_MAX);
     return c;
 }
 
@@ -425,21 +925,55 @@ int jm_nvdec_set_device(int device, handle_nvdec handle)
     return 0;
 }
 
+int jm_nvdec_set_display_delay(int frames, handle_nvdec handle)
+{
+    nvdec_b200 *c = (nvdec_b200 *)handle;
+    if (!c || frames < 0 || frames > RING_MAX - MAP_LIMIT_MAX - 2) return -1;
+    c->delay = frames;
+    return 0;
+}
+
+int jm_nvdec_set_option(const char *name, int value, handle_nvdec handle)
+{
+    nvdec_b200 *c = (nvdec_b200 *)handle;
+    if (!c || !name) return -1;
+    if (!strcmp(name, "display_delay")) return jm_nvdec_set_display_delay(value, handle);
+    if (!strcmp(name, "lazy_pin")) { c->lazy_pin = value != 0; return 0; }
+    if (!strcmp(name, "copy_threads")) {
+        if (value < 0 || value > COPY_THREADS_MAX) return -1;
+        if (value < (int)c->copier.workers.size()) { c->copier.shutdown(); c->copier.stop = false; }
+        c->copy_threads = value;
+        if (c->inited) c->copier.start(value);
+        return 0;
+    }
+    if (!strcmp(name, "map_limit")) {                                    /* takes effect when the next decoder is created */
+        if (value < 1 || value > MAP_LIMIT_MAX) return -1;
+        c->map_limit = value;
+        return 0;
+    }
+    return -1;
+}
+
 int jm_nvdec_init(int codec_type, int out_fmt, char *extra_data, int len, handle_nvdec handle)
 {
     nvdec_b200 *c = (nvdec_b200 *)handle;
     if (!c) return -1;
+    if (c->ctx) teardown(c);                                          /* init on a live handle: start over, leak nothing */
     c->out_fmt = out_fmt;
     c->codec_type = codec_type;
+    c->is_eof = c->is_exit = false;
+    c->num_frames = c->dropped = 0;
+    c->started = false;
+    c->staged = true;
     int r = jmc_ctx_create(c->device, &c->ctx);
     if (r == JMC_ERR_NO_DEVICE) return jmc_device_count() <= 0 ? -2 : -3;   /* nvdec_cuda_init, nv_dec.cpp:219-231 */
     if (r) return -1;
-    c->queue = new (std::nothrow) std::deque<decoded_surface>();
-    if (!c->queue) return -1;
     c->inited = true;
+    c->copier.start(c->copy_threads);
     if (codec_type != JM_NVDEC_CODEC_RAW_NV12) {
         /* bitstream codecs: NVDEC parser + decoder (nvdec_create_parser, nv_dec.cpp:278-366) */
-        int r2 = cuvid_open(c, extra_data, len);
+        jmc_device_guard g(c->ctx);
+        int r2 = g.err ? -1 : cuvid_open(c, extra_data, len);
         if (r2) { cuvid_close(c); return r2; }
     }
     return 0;
@@ -449,15 +983,9 @@ int jm_nvdec_deinit(handle_nvdec handle)
 {
     nvdec_b200 *c = (nvdec_b200 *)handle;
     if (!c) return -1;
-    if (c->ctx) {
-        jmc_ctx_sync(c->ctx);
-        cuvid_close(c);
-        for (int i = 0; i < NVDEC_MAX_FRAMES; i++) if (c->pool[i]) jmc_free_device(c->ctx, c->pool[i]);
-        if (c->d_tight) jmc_free_device(c->ctx, c->d_tight);
-        jmc_ctx_destroy(c->ctx);
-    }
-    delete c->queue;
-    free(c);
+    teardown(c);
+    c->copier.shutdown();
+    delete c;
     return 0;
 }
 
@@ -466,42 +994,97 @@ int jm_nvdec_decode_frame(unsigned char *in_buf, int in_data_len, int *got_frame
     nvdec_b200 *c = (nvdec_b200 *)handle;
     if (got_frame) *got_frame = 0;
     if (!c || !got_frame) return 0;
-    if (!c->inited || !c->ctx || !c->queue) return 0;         /* decoder never created: the reference swallows -1 (nv_dec.cpp:414-417,491-493) */
-    if (jmc_bind_thread(c->ctx)) return 0;                     /* the reference pushes its context around every call (nv_dec.cpp:378,423) */
+    if (!c->inited || !c->ctx) return 0;                       /* decoder never created: the reference swallows -1 (nv_dec.cpp:414-417,491-493) */
+    jmc_device_guard guard(c->ctx);                            /* the reference pushes / pops its context around every call (nv_dec.cpp:378,398,423,471) */
+    if (guard.err) return 0;
+    const bool cuvid = c->codec_type != JM_NVDEC_CODEC_RAW_NV12;
+    c->drop_flag = false;
+    if (cuvid && !c->unmaps.empty()) reap_unmaps(c, false);
     if (!c->is_eof) {                                          /* nv_dec.cpp:486-488 */
-        const bool cuvid = c->codec_type != JM_NVDEC_CODEC_RAW_NV12;
         if (in_buf && in_data_len > 0) {
-            if (!cuvid) raw_packet(c, in_buf, in_data_len);
+            if (!cuvid) raw_packet(c, in_buf, in_data_len);    /* malformed packet: consumed, no frame (errors swallowed like :491-493) */
             else if (c->parser) cuvid_packet(c, in_buf, in_data_len);      /* no parser: init failed, packet dropped */
         } else {
             if (cuvid && c->parser) cuvid_packet(c, nullptr, 0);           /* flush: the parser hands out its delayed pictures */
             c->is_eof = true;                                  /* CUVID_PKT_ENDOFSTREAM, nv_dec.cpp:389-392 */
         }
     }
-    output_stage(c, got_frame);
+    /* nvdec_decode_output_frame (nv_dec.cpp:406-478), for everything that is pending */
+    while (!c->pending.empty()) {
+        if (convert_stage(c, false) <= 0) break;
+    }
+    /* announce at most one frame per call (:455); frames beyond the display delay wait in `ready` */
+    if (!c->ready.empty() && ((int)c->ready.size() > c->delay || c->is_eof)) {
+        release_slot(c, c->cur);                               /* single current frame: fetch it before the next one is announced (nv_dec.h:119-123) */
+        c->cur = c->ready.front();
+        c->ready.pop_front();
+        *got_frame = 1;
+    } else if (c->ready.empty() && c->pending.empty() && c->is_eof) {
+        c->is_exit = true;                                     /* :460-466 */
+        show_info(c);
+    }
+    if (c->drop_flag) {
+        jmc_set_error("jm_nvdec_decode_frame: %u decoded frame(s) dropped so far (the handle holds at most %d converted frames; fetch them with jm_nvdec_output_frame)",
+                      c->dropped, RING_MAX);
+        return -1;                                             /* deviation: the reference cannot lose frames silently here, its queue is unbounded */
+    }
     return 0;
 }
 
 int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec handle)
 {
     nvdec_b200 *c = (nvdec_b200 *)handle;
-    if (!c || !c->have_cur) return -1;                         /* nv_dec.cpp:757-758 */
-    if (!c->d_tight || !out_buf || !out_len) return -1;        /* :768-771 */
-    if (jmc_bind_thread(c->ctx)) return -1;
-    const int need = c->cur_w * c->cur_h * 3 / 2;
+    if (!c || c->cur < 0) return -1;                           /* nv_dec.cpp:757-758 */
+    if (!out_buf || !out_len) return -1;                       /* :768-771 */
+    jmc_device_guard guard(c->ctx);
+    if (guard.err) return -1;
+    ring_slot &s = c->ring[c->cur];
+    const int need = s.w * s.h * 3 / 2;
     if (*out_len < need) return -2;                            /* :773-774 */
     *out_len = 0;                                              /* :776 */
-    cudaStream_t st = (cudaStream_t)jmc_ctx_stream(c->ctx, 0);
-    /* Only the tight frame crosses PCIe.  Pinned out_buf: direct DMA; pageable: the driver stages it.
-     * For odd sizes the reference writes fewer than w*h*3/2 bytes and leaves the rest of out_buf
-     * untouched (h>>1 chroma rows, w>>1 samples: nv_dec.cpp:792-796,807-818): copy exactly those. */
-    const size_t luma = (size_t)c->cur_w * c->cur_h;
-    const size_t written = c->out_fmt == 0 ? luma + (size_t)(c->cur_h >> 1) * c->cur_w
-                                           : luma + 2 * (size_t)(c->cur_w >> 1) * (c->cur_h >> 1);
-    if (written > 0 && cudaMemcpyAsync(out_buf, c->d_tight, written, cudaMemcpyDeviceToHost, st) != cudaSuccess) return -1;
-    if (cudaStreamSynchronize(st) != cudaSuccess) return -1;
+    if (s.total > 0) {
+        int kind = host_kind_of(out_buf, s.total);
+        if (kind == MEM_PAGEABLE && maybe_lazy_pin(c, out_buf, (size_t)need, &c->cand_out)) kind = MEM_PINNED;
+        if (kind != MEM_PAGEABLE) {
+            /* pinned / registered out_buf: only the tight frame crosses PCIe, by DMA straight into the caller's
+             * buffer (a device out_buf gets a device-to-device copy: the frame never leaves HBM) */
+            c->staged = false;
+            cudaStream_t ds = delivery_stream(c);
+            if (cudaStreamWaitEvent(ds, s.converted, 0) != cudaSuccess) return -1;
+            if (cudaMemcpyAsync(out_buf, s.d_tight, s.total, kind == MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ds) != cudaSuccess) { cudaGetLastError(); return -1; }
+            if (cudaEventRecord(s.direct, ds) != cudaSuccess || cudaEventSynchronize(s.direct) != cudaSuccess) { cudaGetLastError(); return -1; }
+        } else {
+            /* pageable out_buf (what the reference's callers pass): the frame is (being) prefetched into the pinned
+             * ring; copy chunk i out while chunk i+1 is still in flight */
+            c->staged = true;
+            if (!prefetch_slot(c, s)) return -1;
+            for (int i = 0; i < s.n_chunks; i++) {
+                if (cudaEventSynchronize(s.delivered[i]) != cudaSuccess) { cudaGetLastError(); return -1; }
+                const size_t off = (size_t)i * s.chunk_bytes;
+                const size_t n = s.total - off < s.chunk_bytes ? s.total - off : s.chunk_bytes;
+                c->copier.copy_flat(out_buf + off, s.h_tight + off, n);
+            }
+        }
+    }
     *out_len = need;                                           /* :824 */
     return need;                                               /* :827 */
+}
+
+int jm_nvdec_output_frame_ref(const unsigned char **frame, int *frame_len, handle_nvdec handle)
+{
+    nvdec_b200 *c = (nvdec_b200 *)handle;
+    if (!c || c->cur < 0 || !frame) return -1;
+    jmc_device_guard guard(c->ctx);
+    if (guard.err) return -1;
+    ring_slot &s = c->ring[c->cur];
+    c->staged = true;
+    if (!prefetch_slot(c, s)) return -1;
+    for (int i = 0; i < s.n_chunks; i++)
+        if (cudaEventSynchronize(s.delivered[i]) != cudaSuccess) { cudaGetLastError(); return -1; }
+    *frame = s.h_tight;
+    const int need = s.w * s.h * 3 / 2;
+    if (frame_len) *frame_len = need;
+    return need;
 }
 
 int jm_nvdec_stream_info(int *disp_width, int *disp_height, handle_nvdec handle)
@@ -546,6 +1129,47 @@ int jm_nvdec_memory_release_host(void *buf, handle_nvdec handle)
     nvdec_b200 *c = (nvdec_b200 *)handle;
     if (!c || !c->ctx) return -1;
     return jmc_free_host(c->ctx, buf) == JMC_OK ? 0 : -1;
+}
+
+int jm_nvdec_memory_register_host(void *buf, int buf_len, handle_nvdec handle)
+{
+    nvdec_b200 *c = (nvdec_b200 *)handle;
+    if (!c || !c->ctx || !buf || buf_len <= 0) return -1;
+    jmc_device_guard guard(c->ctx);
+    if (guard.err) return -1;
+    if (is_device_accessible_host(buf, (size_t)buf_len)) return 0;
+    return register_range(c, buf, (size_t)buf_len) ? 0 : -1;
+}
+
+int jm_nvdec_memory_unregister_host(void *buf, handle_nvdec handle)
+{
+    nvdec_b200 *c = (nvdec_b200 *)handle;
+    if (!c || !c->ctx || !buf) return -1;
+    jmc_device_guard guard(c->ctx);
+    if (guard.err) return -1;
+    for (size_t i = 0; i < c->regs.size(); i++) {
+        const uintptr_t lo = (uintptr_t)c->regs[i].base, hi = lo + c->regs[i].len;
+        if ((uintptr_t)buf >= lo && (uintptr_t)buf < hi) {
+            jmc_ctx_sync(c->ctx);
+            cudaHostUnregister(c->regs[i].base);
+            c->regs.erase(c->regs.begin() + (long)i);
+            if (c->cand_out == buf) c->cand_out = nullptr;
+            if (c->cand_in == buf) c->cand_in = nullptr;
+            return 0;
+        }
+    }
+    return -1;
+}
+
+int jm_nvdec_dropped_frames(handle_nvdec handle)
+{
+    return handle ? (int)((nvdec_b200 *)handle)->dropped : -1;
+}
+
+long long jm_nvdec_launch_count(handle_nvdec handle)
+{
+    nvdec_b200 *c = (nvdec_b200 *)handle;
+    return c && c->ctx ? (long long)jmc_ctx_launch_count(c->ctx) : 0;
 }
 
 } /* extern "C" */

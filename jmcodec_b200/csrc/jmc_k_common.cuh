@@ -10,14 +10,21 @@
 namespace jmc {
 
 
+/* Where frame f of a batch lives: base + f*stride; or list[f], a DEVICE array of frame pointers; or, for small
+ * batches (decoder-mapped surfaces drained a few at a time), inl[f]: the pointers themselves travel as kernel
+ * arguments, so nothing has to be uploaded before the launch (JMC_JOB_LIST_ON_HOST). */
+constexpr int INLINE_LIST_MAX = 8;
 struct FrameSet {
     uint8_t *base;
     size_t stride;
     uint8_t *const *list;
+    uint32_t n_inline, pad_;
+    uint8_t *inl[INLINE_LIST_MAX];
 };
 
 __device__ __forceinline__ uint8_t *frame_ptr(const FrameSet &s, uint32_t f)
 {
+    if (s.n_inline) return s.inl[f];
     return s.list ? s.list[f] : s.base + (size_t)f * s.stride;
 }
 

@@ -12,17 +12,43 @@
 using namespace jmc;
 
 typedef Cfg256x4 PlaneCfg;
+static_assert(INLINE_LIST_MAX == JMC_INLINE_LIST_MAX, "include/jmc_cuda.h and jmc_k_common.cuh disagree on the inline list size");
 
-static FrameSet to_set(const jmc_frames &f)
+/* JMC_JOB_LIST_ON_HOST: every non-NULL list of the job is a HOST array of <= INLINE_LIST_MAX device pointers,
+ * which travel to the kernel as arguments (checked in jmc_launch_job). */
+static FrameSet to_set(const jmc_job *j, const jmc_frames &f)
 {
     FrameSet s;
     s.base = (uint8_t *)f.base;
     s.stride = f.stride;
     s.list = (uint8_t *const *)f.list;
+    s.n_inline = 0;
+    s.pad_ = 0;
+    for (int i = 0; i < INLINE_LIST_MAX; i++) s.inl[i] = nullptr;
+    if (f.list && (j->flags & JMC_JOB_LIST_ON_HOST)) {
+        s.n_inline = (uint32_t)j->n_frames;
+        for (int i = 0; i < j->n_frames && i < INLINE_LIST_MAX; i++) s.inl[i] = (uint8_t *)f.list[i];
+        s.list = nullptr;
+    }
     return s;
 }
 
 static bool frames_ok(const jmc_frames &f) { return f.base != nullptr || f.list != nullptr; }
+
+/* OR of every address bit of a frame set the host can see: base | stride, or the pointers of a host-side
+ * list.  A device-side list cannot be read here: *known is cleared unless the caller vouches for 16-byte
+ * alignment with JMC_JOB_ALIGNED16 (then it contributes no bits). */
+static uint64_t frames_bits(const jmc_job *j, const jmc_frames &f, bool *known)
+{
+    if (!f.list) return (uint64_t)(uintptr_t)f.base | (uint64_t)f.stride;
+    if (j->flags & JMC_JOB_LIST_ON_HOST) {
+        uint64_t bits = 0;
+        for (int i = 0; i < j->n_frames && i < INLINE_LIST_MAX; i++) bits |= (uint64_t)(uintptr_t)f.list[i];
+        return bits;
+    }
+    if (!(j->flags & JMC_JOB_ALIGNED16)) *known = false;
+    return 0;
+}
 
 /* fast_div(): m = ceil(2^sh / d), sh = 31 + ceil(log2 d) */
 static FastDiv make_fastdiv(uint32_t d)
@@ -53,12 +79,6 @@ static Part make_part(int kind, uint32_t rows, uint32_t row_elems, int64_t p_off
     p.b_off = b_off;
     p.rdiv = make_fastdiv(row_elems);
     return p;
-}
-
-static bool getenv_flag(const char *name)
-{
-    const char *e = getenv(name);
-    return e && atoi(e) != 0;
 }
 
 /* Opt a kernel in to more than 48 KB of dynamic shared memory, once per (kernel, device); safe to race */
@@ -120,12 +140,9 @@ static int launch_bulk(jmc_ctx *ctx, const PlaneParams &pp, int k1, cudaStream_t
  * JMC_JOB_ALIGNED16. */
 static bool narrow_vectors(const jmc_job *j, const PlaneParams &p)
 {
-    uint64_t common = 0;
-    const jmc_frames *sets[2] = { &j->surf, &j->tight };
-    for (int i = 0; i < 2; i++) {
-        if (sets[i]->list) { if (!(j->flags & JMC_JOB_ALIGNED16)) return false; }     /* unknown: keep the per-frame in-kernel choice */
-        else common |= (uint64_t)(uintptr_t)sets[i]->base | (uint64_t)sets[i]->stride;
-    }
+    bool known = true;
+    const uint64_t common = frames_bits(j, j->surf, &known) | frames_bits(j, j->tight, &known);
+    if (!known) return false;                        /* unknown: keep the per-frame in-kernel choice */
     auto width = [](uint64_t bits) { const uint32_t low = (uint32_t)bits & 15u; return low == 0 ? 16u : (low & (0u - low)); };
     const Part &y = p.part[0], &c = p.part[1];
     const uint32_t vy = y.kind == PART_NONE ? 16u : width(common | (uint64_t)y.p_off | (uint32_t)y.p_pitch | (uint64_t)y.a_off | y.row_elems);
@@ -140,8 +157,10 @@ static bool narrow_vectors(const jmc_job *j, const PlaneParams &p)
  * to the next multiple of 16).  Returns 1 when that does not hold. */
 static int launch_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, int k1, cudaStream_t stream)
 {
-    if (j->surf.list) { if (!(j->flags & JMC_JOB_ALIGNED16)) return 1; }
-    else if (((uint64_t)(uintptr_t)j->surf.base | (uint64_t)j->surf.stride) & 15) return 1;
+    {
+        bool known = true;
+        if ((frames_bits(j, j->surf, &known) & 15) || !known) return 1;
+    }
     RowsParams r;
     r.pitched = pp.pitched;
     r.tight = pp.tight;
@@ -162,7 +181,7 @@ static int launch_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, in
         /* short rows: several whole rows per warp task, so that each lane still has up to four loads in flight */
         const uint32_t align = pt.kind == PART_COPY ? 16u : 32u;
         const uint32_t rs = (row_bytes + align - 1) & ~(align - 1);
-        if (r.segs[i] == 1 && 2 * rs <= (uint32_t)ROWS_SEG && !getenv_flag("JMC_ROWS_SINGLE")) {
+        if (r.segs[i] == 1 && 2 * rs <= (uint32_t)ROWS_SEG && !jmc_env().rows_single) {
             r.rpt[i] = std::min<uint32_t>(ROWS_SEG / rs, ROWS_MAX_RPT);
             r.rstride[i] = rs;
             r.cdiv[i] = make_fastdiv(rs / 16);
@@ -198,8 +217,10 @@ static int launch_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, in
  * preconditions as launch_rows(); returns 1 when they do not hold or the tile does not fit. */
 static int launch_bulk_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &pp, int k1, cudaStream_t stream)
 {
-    if (j->surf.list) { if (!(j->flags & JMC_JOB_ALIGNED16)) return 1; }
-    else if (((uint64_t)(uintptr_t)j->surf.base | (uint64_t)j->surf.stride) & 15) return 1;
+    {
+        bool known = true;
+        if ((frames_bits(j, j->surf, &known) & 15) || !known) return 1;
+    }
     BulkRowsParams b;
     b.pitched = pp.pitched;
     b.tight = pp.tight;
@@ -252,12 +273,9 @@ static int launch_bulk_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &p
 /* Can the host prove that every access of this job is 16-byte aligned?  (1080p, 4K, 720p ... are.) */
 static bool all_wide(const jmc_job *j, const PlaneParams &p)
 {
-    uint64_t bits = 0;
-    const jmc_frames *sets[2] = { &j->surf, &j->tight };
-    for (int i = 0; i < 2; i++) {
-        if (sets[i]->list) { if (!(j->flags & JMC_JOB_ALIGNED16)) return false; }
-        else bits |= (uint64_t)(uintptr_t)sets[i]->base | (uint64_t)sets[i]->stride;
-    }
+    bool known = true;
+    uint64_t bits = frames_bits(j, j->surf, &known) | frames_bits(j, j->tight, &known);
+    if (!known) return false;
     for (int i = 0; i < 2; i++) {
         const Part &pt = p.part[i];
         if (pt.kind == PART_NONE) continue;
@@ -272,8 +290,8 @@ static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     if (!frames_ok(j->surf) || !frames_ok(j->tight)) { jmc_set_error("jmc_convert: surf/tight frame set is empty"); return JMC_ERR_INVALID; }
     const uint32_t w = (uint32_t)j->width, h = (uint32_t)j->height;
     PlaneParams p;
-    p.pitched = to_set(j->surf);
-    p.tight = to_set(j->tight);
+    p.pitched = to_set(j, j->surf);
+    p.tight = to_set(j, j->tight);
     p.n_frames = (uint32_t)j->n_frames;
     p.to_tight = (j->op == JMC_OP_NV12_TO_NV12 || j->op == JMC_OP_NV12_TO_I420) ? 1 : 0;
     /* luma: h rows of w bytes (nv_dec.cpp:787-790,801-804; intel_enc.cpp:291-295; nv_enc.cpp:1043-1051) */
@@ -294,17 +312,17 @@ static int launch_planes(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     const uint32_t grid = p.total_tiles;             /* one CTA per 16 KB tile (see Cfg256x4) */
     const bool wide = all_wide(j, p);
     const int k1 = p.part[1].kind == PART_NONE ? PART_COPY : p.part[1].kind;
-    if (wide && !getenv_flag("JMC_NO_BULK")) {
+    if (wide && !jmc_env().no_bulk) {
         int r = launch_bulk(ctx, p, k1, stream);
         if (r != 1) return r;                        /* 1: geometry does not fit the bulk kernel, use LDG/STG */
     }
-    if (!wide && !getenv_flag("JMC_NO_ROWS")) {
+    if (!wide && !jmc_env().no_rows) {
         /* width not a multiple of 16 on an aligned surface: bulk-loaded row tiles, both directions */
-        if (!getenv_flag("JMC_NO_BULK")) {
+        if (!jmc_env().no_bulk) {
             int r = launch_bulk_rows(ctx, j, p, k1, stream);
             if (r != 1) return r;                    /* 1: surface side not 16-byte friendly or tile too large */
         }
-        if (narrow_vectors(j, p) || getenv_flag("JMC_ROWS_ALWAYS")) {
+        if (narrow_vectors(j, p) || jmc_env().rows_always) {
             int r = launch_rows(ctx, j, p, k1, stream);
             if (r != 1) return r;                    /* 1: surface side not 16-byte friendly, use the any-alignment kernel */
         }
@@ -336,9 +354,9 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     if ((j->width >> 1) < 1 || (j->height >> 1) < 1) { jmc_set_error("jmc_convert: RGB needs width,height >= 2"); return JMC_ERR_INVALID; }
     if (j->rgb_pitch < (argb ? 4 : 3) * j->width) { jmc_set_error("jmc_convert: rgb_pitch < %d*width", argb ? 4 : 3); return JMC_ERR_INVALID; }
     RgbParams p;
-    p.surf = to_set(j->surf);
-    p.tight = to_set(j->tight);
-    p.rgb = to_set(j->rgb);
+    p.surf = to_set(j, j->surf);
+    p.tight = to_set(j, j->tight);
+    p.rgb = to_set(j, j->rgb);
     p.n_frames = (uint32_t)j->n_frames;
     p.width = j->width; p.height = j->height; p.pitch = j->pitch;
     p.y_off = j->surf_y_off; p.uv_off = j->surf_uv_off;
@@ -360,28 +378,28 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
         uint64_t bits = (uint64_t)j->surf_y_off | (uint64_t)j->surf_uv_off | (uint32_t)j->pitch | (uint32_t)j->rgb_pitch | (uint32_t)j->width;
         if (fused) bits |= (uint32_t)(j->width >> 1);            /* U / V rows are bulk-stored too */
         const jmc_frames *sets[3] = { &j->surf, &j->rgb, fused ? &j->tight : nullptr };
-        const bool ok = !getenv_flag("JMC_NO_BULK") && !argb;    /* ARGB32 runs on the vector kernel */
-        bool known = true;                                       /* pointer lists: aligned only if the caller says so */
-        for (int i = 0; i < 3; i++) {
-            if (!sets[i]) continue;
-            if (sets[i]->list) known = known && (j->flags & JMC_JOB_ALIGNED16) != 0;
-            else bits |= (uint64_t)(uintptr_t)sets[i]->base | (uint64_t)sets[i]->stride;
-        }
+        const bool ok = !jmc_env().no_bulk && !argb;    /* ARGB32 runs on the vector kernel */
+        bool known = true;                                       /* device-side pointer lists: aligned only if the caller says so */
+        for (int i = 0; i < 3; i++)
+            if (sets[i]) bits |= frames_bits(j, *sets[i], &known);
         if (fused) bits |= (uint64_t)j->tight_u_off | (uint64_t)j->tight_v_off;
         /* !aligned: only the surface has to be 16-byte friendly (any even width; rows over-readable to the next
          * multiple of 16 inside the pitch) - RGB / tight rows at any address are written with re-aligned stores */
         const bool aligned = known && (bits & 15) == 0;
         bool surf_ok = (j->width & 1) == 0 && j->pitch >= ((j->width + 15) & ~15) &&
                        (((uint64_t)j->surf_y_off | (uint64_t)j->surf_uv_off | (uint32_t)j->pitch) & 15) == 0;
-        if (j->surf.list) surf_ok = surf_ok && (j->flags & JMC_JOB_ALIGNED16) != 0;
-        else surf_ok = surf_ok && (((uint64_t)(uintptr_t)j->surf.base | (uint64_t)j->surf.stride) & 15) == 0;
+        {
+            bool sknown = true;
+            const uint64_t sbits = frames_bits(j, j->surf, &sknown);
+            surf_ok = surf_ok && sknown && (sbits & 15) == 0;
+        }
         /* measured (profiles/r1_odd_sizes_rgb_bulk.txt): with unaligned rows the bulk-loaded variant wins for the
          * fused op (1366-wide: 0.88 vs 0.79 of peak) but not for RGB alone (0.77 vs 0.82; 1080-wide 0.68 vs 0.82) */
         /* ... and for RGB alone on narrow frames the warp-per-task kernel is ahead even when everything is aligned
          * (profiles/r1c_rgb_bulk_vs_vector.txt: 1536 wide 1.03 vs 0.99, 1376 wide 0.95 vs 0.92; from 1920 wide on the
          * bulk kernel wins, 1.02 vs 1.00) */
-        const bool bulk_pays = fused || j->width >= 1664 || getenv_flag("JMC_RGB_BULK_ALWAYS");
-        if (ok && ((aligned && bulk_pays) || (surf_ok && (fused || getenv_flag("JMC_RGB_BULK_ALWAYS"))))) {
+        const bool bulk_pays = fused || j->width >= 1664 || jmc_env().rgb_bulk_always;
+        if (ok && ((aligned && bulk_pays) || (surf_ok && (fused || jmc_env().rgb_bulk_always)))) {
             RgbBulkParams b;
             b.surf = p.surf; b.tight = p.tight; b.rgb = p.rgb;
             b.n_frames = p.n_frames; b.width = p.width; b.height = p.height; b.pitch = p.pitch;
@@ -418,11 +436,14 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     {
         bool surf_ok = !fused && (j->width & 1) == 0 && j->pitch >= ((j->width + 15) & ~15) &&
                        (((uint64_t)j->surf_y_off | (uint64_t)j->surf_uv_off | (uint32_t)j->pitch) & 15) == 0;
-        if (j->surf.list) surf_ok = surf_ok && (j->flags & JMC_JOB_ALIGNED16) != 0;
-        else surf_ok = surf_ok && (((uint64_t)(uintptr_t)j->surf.base | (uint64_t)j->surf.stride) & 15) == 0;
-        const char *force = getenv("JMC_RGB_FLAT");
+        {
+            bool sknown = true;
+            const uint64_t sbits = frames_bits(j, j->surf, &sknown);
+            surf_ok = surf_ok && sknown && (sbits & 15) == 0;
+        }
+        const int force = jmc_env().rgb_flat;
         const uint32_t units = ((uint32_t)j->width + 15) / 16, slots = 32 * ((units + 31) / 32);
-        const bool want = force ? atoi(force) != 0 : units * 100 < slots * 86;
+        const bool want = force >= 0 ? force != 0 : units * 100 < slots * 86;
         if (surf_ok && want) {
             RgbFlatParams q;
             q.surf = p.surf; q.rgb = p.rgb; q.n_frames = p.n_frames;
@@ -459,8 +480,8 @@ static int launch_rgb_to_nv12(jmc_ctx *ctx, const jmc_job *j, cudaStream_t strea
     if (!frames_ok(j->surf) || !frames_ok(j->rgb)) { jmc_set_error("jmc_convert: surf/rgb frame set is empty"); return JMC_ERR_INVALID; }
     if (j->rgb_pitch < 3 * j->width) { jmc_set_error("jmc_convert: rgb_pitch %d < 3*width", j->rgb_pitch); return JMC_ERR_INVALID; }
     Rgb2Params p;
-    p.rgb = to_set(j->rgb);
-    p.surf = to_set(j->surf);
+    p.rgb = to_set(j, j->rgb);
+    p.surf = to_set(j, j->surf);
     p.n_frames = (uint32_t)j->n_frames;
     p.width = j->width; p.height = j->height; p.pitch = j->pitch; p.rgb_pitch = j->rgb_pitch;
     p.y_off = j->surf_y_off; p.uv_off = j->surf_uv_off;
@@ -487,6 +508,10 @@ int jmc_launch_job(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
     if ((uint64_t)j->width * (uint64_t)j->height > 0x7fffffffull) { jmc_set_error("jmc_convert: frame too large"); return JMC_ERR_INVALID; }
     if (j->n_frames == 0 || j->width == 0 || j->height == 0) return JMC_OK;
     if (j->pitch < j->width) { jmc_set_error("jmc_convert: pitch %d < width %d", j->pitch, j->width); return JMC_ERR_INVALID; }
+    if ((j->flags & JMC_JOB_LIST_ON_HOST) && j->n_frames > INLINE_LIST_MAX) {
+        jmc_set_error("jmc_convert: JMC_JOB_LIST_ON_HOST carries at most %d frames per launch", INLINE_LIST_MAX);
+        return JMC_ERR_INVALID;
+    }
     switch (j->op) {
     case JMC_OP_NV12_TO_NV12:
     case JMC_OP_NV12_TO_I420:

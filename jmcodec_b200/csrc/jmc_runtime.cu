@@ -41,6 +41,19 @@ int jmc_device_count(void)
     return n;
 }
 
+int jmc_current_device(void)
+{
+    int d = -1;
+    if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+    return d;
+}
+
+int jmc_set_current_device(int device)
+{
+    JMC_CUDA(cudaSetDevice(device));
+    return JMC_OK;
+}
+
 int jmc_ctx_create(int device, jmc_ctx **out)
 {
     if (!out) { jmc_set_error("jmc_ctx_create: NULL out"); return JMC_ERR_INVALID; }
@@ -48,34 +61,81 @@ int jmc_ctx_create(int device, jmc_ctx **out)
     int n = jmc_device_count();
     if (n <= 0) { if (!g_err[0]) jmc_set_error("no CUDA device"); return JMC_ERR_NO_DEVICE; }       /* nv_dec.cpp:219-222 */
     if (device < 0 || device >= n) { jmc_set_error("invalid device id %d (have %d)", device, n); return JMC_ERR_NO_DEVICE; }   /* :227-231 */
-    JMC_CUDA(cudaSetDevice(device));
+    jmc_device_guard guard_(device);
+    if (guard_.err) return guard_.err;
     jmc_ctx *c = new (std::nothrow) jmc_ctx();
     if (!c) return JMC_ERR_NOMEM;
     c->device = device;
     c->launches = 0;
-    cudaDeviceProp prop;
-    cudaError_t e = cudaGetDeviceProperties(&prop, device);
-    if (e != cudaSuccess) { delete c; return jmc_cuda_fail(e, "cudaGetDeviceProperties"); }
-    c->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 3; i++) c->stream[i] = nullptr;
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) { delete c; return jmc_cuda_fail(e, "cudaDeviceGetAttribute"); }
+    c->sm_count = sms;
     for (int i = 0; i < 3; i++) {
         e = cudaStreamCreateWithFlags(&c->stream[i], cudaStreamNonBlocking);
-        if (e != cudaSuccess) { delete c; return jmc_cuda_fail(e, "cudaStreamCreateWithFlags"); }
+        if (e != cudaSuccess) {
+            for (int k = 0; k < i; k++) cudaStreamDestroy(c->stream[k]);       /* do not leak the streams already created */
+            delete c;
+            return jmc_cuda_fail(e, "cudaStreamCreateWithFlags");
+        }
     }
     *out = c;
     return JMC_OK;
 }
 
-static int bind(const jmc_ctx *c)
-{
-    if (!c) { jmc_set_error("NULL jmc_ctx"); return JMC_ERR_INVALID; }
-    JMC_CUDA(cudaSetDevice(c->device));
-    return JMC_OK;
-}
-#define JMC_BIND(c) do { int r_ = bind(c); if (r_) return r_; } while (0)
-
 } /* extern "C" */
-int jmc_bind_thread(const jmc_ctx *c) { return bind(c); }
+
+/* ---- device guard + environment switches ------------------------------------------------------ */
+void jmc_device_guard::enter(int device)
+{
+    prev = -1; err = 0; switched = false;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e != cudaSuccess) { prev = -1; cudaGetLastError(); }
+    if (prev == device) return;
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) { err = jmc_cuda_fail(e, "cudaSetDevice"); return; }
+    switched = prev >= 0;
+}
+jmc_device_guard::jmc_device_guard(int device) { enter(device); }
+jmc_device_guard::jmc_device_guard(const jmc_ctx *c)
+{
+    if (!c) { prev = -1; switched = false; jmc_set_error("NULL jmc_ctx"); err = JMC_ERR_INVALID; return; }
+    enter(c->device);
+}
+jmc_device_guard::~jmc_device_guard()
+{
+    if (switched) cudaSetDevice(prev);                  /* hand the caller's device back (nv_dec.cpp:398,471 cuCtxPopCurrent) */
+}
+
+static jmc_env_flags g_env;
+static bool g_env_loaded = false;
+static bool env_on(const char *name) { const char *e = getenv(name); return e && atoi(e) != 0; }
+static int env_tri(const char *name) { const char *e = getenv(name); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }
+static void env_load()
+{
+    jmc_env_flags f;
+    f.no_bulk = env_on("JMC_NO_BULK");
+    f.no_rows = env_on("JMC_NO_ROWS");
+    f.rows_single = env_on("JMC_ROWS_SINGLE");
+    f.rows_always = env_on("JMC_ROWS_ALWAYS");
+    f.rgb_bulk_always = env_on("JMC_RGB_BULK_ALWAYS");
+    f.no_tensor_map = env_on("JMC_NO_TENSOR_MAP");
+    f.pipeline_h2d_2d = env_tri("JMC_PIPELINE_H2D_2D") != 0;
+    f.rgb_flat = env_tri("JMC_RGB_FLAT");
+    f.rgb2_flat = env_tri("JMC_RGB2_FLAT");
+    g_env = f;
+    g_env_loaded = true;
+}
+const jmc_env_flags &jmc_env()
+{
+    if (!g_env_loaded) env_load();                      /* racing first calls read the same environment: benign */
+    return g_env;
+}
+
 extern "C" {
+
+void jmc_reload_env(void) { env_load(); }
 
 int jmc_ctx_destroy(jmc_ctx *c)
 {
@@ -436,8 +496,7 @@ int jmc_pipeline_submit(jmc_pipeline *p, const void *host_in, const void *dev_in
         /* upload stream: the slot's input buffer is free once its previous conversion has run */
         JMC_CUDA(cudaStreamWaitEvent(c->stream[1], s.converted, 0));
         const jmc_job &g = p->shape;
-        static const bool allow_2d = !(getenv("JMC_PIPELINE_H2D_2D") && atoi(getenv("JMC_PIPELINE_H2D_2D")) == 0);
-        const bool rows_only = allow_2d && op_is_decode_side(g.op) && g.width < g.pitch && g.surf_y_off == 0 &&
+        const bool rows_only = jmc_env().pipeline_h2d_2d && op_is_decode_side(g.op) && g.width < g.pitch && g.surf_y_off == 0 &&
                                g.surf_uv_off == (int64_t)g.pitch * g.height && p->in_bytes % (size_t)g.pitch == 0;
         if (rows_only) {
             /* NV12 surfaces back to back = one 2-D array of `pitch`-byte rows: the DMA engine skips the

@@ -43,6 +43,26 @@ struct nvenc_b200 {
 
 bool is_rgb(int f) { return f == JM_NVENC_FMT_ARGB || f == JM_NVENC_FMT_ABGR; }
 
+/* Everything jm_nvenc_init allocated: surfaces, staging frame, context.  Used by deinit, by a failing init (the
+ * reference's nvenc_register_frame leaks on both paths, nv_enc.cpp:954-1007) and by init on a live handle. */
+void release_all(nvenc_b200 *c)
+{
+    if (c->ctx) {
+        jmc_ctx_sync(c->ctx);
+        for (int i = 0; i < JM_NVENC_NUM_SURFACES; i++) {
+            if (c->surf[i].dptr) jmc_free_device(c->ctx, c->surf[i].dptr);
+            c->surf[i] = enc_surface();
+        }
+        if (c->d_stage) jmc_free_device(c->ctx, c->d_stage);
+        c->d_stage = nullptr;
+        c->stage_bytes = 0;
+        jmc_ctx_destroy(c->ctx);
+        c->ctx = nullptr;
+    }
+    c->inited = false;
+    c->last = -1;
+}
+
 } /* namespace */
 
 extern "C" {
@@ -69,6 +89,7 @@ int jm_nvenc_init(nv_enc_param *in_param, handle_nvenc handle)
 {
     nvenc_b200 *c = (nvenc_b200 *)handle;
     if (!c || !in_param) return JM_NVENC_ERR_INVALID_PARAM;
+    if (c->ctx) release_all(c);                                       /* init on a live handle: start over, leak nothing */
     c->param = *in_param;
     c->width = in_param->src_width;
     c->height = in_param->src_height;
@@ -98,16 +119,16 @@ int jm_nvenc_init(nv_enc_param *in_param, handle_nvenc handle)
     for (int i = 0; i < JM_NVENC_NUM_SURFACES; i++) {
         void *p = nullptr;
         size_t pitch = 0;
-        if (jmc_alloc_pitched(c->ctx, wbytes, (size_t)c->rows, &p, &pitch) != JMC_OK) return JM_NVENC_ERR_GENERIC;
-        if (jmc_memset_device(c->ctx, p, 0, pitch * (size_t)c->rows) != JMC_OK) return JM_NVENC_ERR_GENERIC;
+        if (jmc_alloc_pitched(c->ctx, wbytes, (size_t)c->rows, &p, &pitch) != JMC_OK) { release_all(c); return JM_NVENC_ERR_GENERIC; }
         c->surf[i].dptr = (uint8_t *)p;
         c->surf[i].pitch = pitch;
+        if (jmc_memset_device(c->ctx, p, 0, pitch * (size_t)c->rows) != JMC_OK) { release_all(c); return JM_NVENC_ERR_GENERIC; }
     }
     if (c->format == JM_NVENC_FMT_YV12) {
         /* one staging frame; the reference stages U and V separately in uv_tmp_ptr[0..1] (:972-973) */
         c->stage_bytes = (size_t)c->width * c->height * 3 / 2 + 16;
         void *p = nullptr;
-        if (jmc_alloc_device(c->ctx, c->stage_bytes, &p) != JMC_OK) return JM_NVENC_ERR_GENERIC;
+        if (jmc_alloc_device(c->ctx, c->stage_bytes, &p) != JMC_OK) { release_all(c); return JM_NVENC_ERR_GENERIC; }
         c->d_stage = (uint8_t *)p;
     }
     c->inited = true;
@@ -118,12 +139,7 @@ int jm_nvenc_deinit(handle_nvenc handle)
 {
     nvenc_b200 *c = (nvenc_b200 *)handle;
     if (!c) return -1;
-    if (c->ctx) {
-        jmc_ctx_sync(c->ctx);
-        for (int i = 0; i < JM_NVENC_NUM_SURFACES; i++) if (c->surf[i].dptr) jmc_free_device(c->ctx, c->surf[i].dptr);
-        if (c->d_stage) jmc_free_device(c->ctx, c->d_stage);
-        jmc_ctx_destroy(c->ctx);
-    }
+    release_all(c);
     free(c);
     return 0;
 }
@@ -134,7 +150,18 @@ int jm_nvenc_enc_frame(const unsigned char *in_yuv_buf, const int yuv_len, int *
     if (got_packet) *got_packet = 0;
     if (!c || !c->inited) return -1;
     if (!in_yuv_buf || yuv_len <= 0) return 0;                        /* EOS, nv_enc.cpp:113-117 */
-    if (jmc_bind_thread(c->ctx)) return JM_NVENC_ERR_GENERIC;          /* CCudaAutoLock, nv_enc.cpp:1025 */
+    jmc_device_guard guard(c->ctx);                                    /* CCudaAutoLock, nv_enc.cpp:1025; the caller's device is restored on return */
+    if (guard.err) return JM_NVENC_ERR_GENERIC;
+    /* a buffer shorter than the format needs would be over-read by the DMA (the reference does over-read,
+     * nv_enc.cpp:1029-1040,1096): refuse it instead.  YV12 keeps the reference's clamp-to-yuv_len behaviour. */
+    {
+        const int64_t px = (int64_t)c->width * c->height;
+        const int64_t want = is_rgb(c->format) ? px * 4 : (c->format == JM_NVENC_FMT_NV12 ? (int64_t)c->width * (c->height * 3 / 2) : 0);
+        if (want > (int64_t)yuv_len) {
+            jmc_set_error("jm_nvenc_enc_frame: yuv_len %d is shorter than the %lld bytes a %dx%d frame of this format holds", yuv_len, (long long)want, c->width, c->height);
+            return JM_NVENC_ERR_INVALID_PARAM;
+        }
+    }
 
     int idx = -1;                                                     /* nvenc_get_free_frame, :916-927 */
     for (int i = 0; i < JM_NVENC_NUM_SURFACES; i++) if (!c->surf[i].lock_count) { idx = i; break; }

@@ -33,6 +33,8 @@ class JMC_OP(enum.IntEnum):
 
 
 JOB_ALIGNED16 = 1
+JOB_LIST_ON_HOST = 2
+INLINE_LIST_MAX = 8
 
 
 class Frames(C.Structure):
@@ -53,7 +55,7 @@ class RawPacket(C.Structure):
     _fields_ = [("magic", C.c_uint32), ("width", C.c_int32), ("height", C.c_int32), ("pitch", C.c_int32),
                 ("flags", C.c_uint32), ("reserved", C.c_uint32), ("device_ptr", C.c_uint64)]
     MAGIC = 0x53524D4A
-    DEVICE_PTR = 1
+    DEVICE_PTR, SYNC, WAIT_EVENT = 1, 2, 4
 
 
 class NvEncParam(C.Structure):
@@ -77,7 +79,10 @@ _SIGS = {
     # name: (restype, argtypes)
     "jmc_last_error": (C.c_char_p, []),
     "jmc_version": (C.c_char_p, []),
+    "jmc_reload_env": (None, []),
     "jmc_device_count": (C.c_int, []),
+    "jmc_current_device": (C.c_int, []),
+    "jmc_set_current_device": (C.c_int, [C.c_int]),
     "jmc_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
     "jmc_ctx_destroy": (C.c_int, [C.c_void_p]),
     "jmc_ctx_device": (C.c_int, [C.c_void_p]),
@@ -132,6 +137,13 @@ _SIGS = {
     "jm_nvdec_set_device": (C.c_int, [C.c_int, C.c_void_p]),
     "jm_nvdec_memory_alloc_host": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
     "jm_nvdec_memory_release_host": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "jm_nvdec_memory_register_host": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "jm_nvdec_memory_unregister_host": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "jm_nvdec_set_display_delay": (C.c_int, [C.c_int, C.c_void_p]),
+    "jm_nvdec_set_option": (C.c_int, [C.c_char_p, C.c_int, C.c_void_p]),
+    "jm_nvdec_output_frame_ref": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_void_p]),
+    "jm_nvdec_dropped_frames": (C.c_int, [C.c_void_p]),
+    "jm_nvdec_launch_count": (C.c_longlong, [C.c_void_p]),
     # jmnv_enc.h
     "jm_nvenc_create_handle": (C.c_void_p, []),
     "jm_nvenc_init": (C.c_int, [C.POINTER(NvEncParam), C.c_void_p]),
@@ -172,6 +184,11 @@ def last_error() -> str:
 
 def version() -> str:
     return load().jmc_version().decode()
+
+
+def reload_env() -> None:
+    """Re-read the JMC_* kernel-variant switches (they are cached per process, not read per launch)."""
+    load().jmc_reload_env()
 
 
 def device_count() -> int:
@@ -435,15 +452,46 @@ class NvDec:
             raise JmcError("jm_nvdec_memory_alloc_host failed: " + last_error())
         return p.value
 
+    def register_host(self, arr: np.ndarray) -> int:
+        return self.L.jm_nvdec_memory_register_host(_hptr(arr), arr.nbytes, self.h)
+
+    def unregister_host(self, arr: np.ndarray) -> int:
+        return self.L.jm_nvdec_memory_unregister_host(_hptr(arr), self.h)
+
+    def set_display_delay(self, n: int) -> int:
+        return self.L.jm_nvdec_set_display_delay(n, self.h)
+
+    def set_option(self, name: str, value: int) -> int:
+        return self.L.jm_nvdec_set_option(name.encode(), value, self.h)
+
+    def output_frame_ref(self):
+        """Returns (ret, numpy view of the frame inside the pinned delivery ring or None)."""
+        p, n = C.c_void_p(), C.c_int(0)
+        r = self.L.jm_nvdec_output_frame_ref(C.byref(p), C.byref(n), self.h)
+        if r <= 0:
+            return r, None
+        return r, np.ctypeslib.as_array((C.c_uint8 * n.value).from_address(p.value))
+
+    @property
+    def dropped_frames(self) -> int:
+        return self.L.jm_nvdec_dropped_frames(self.h)
+
+    @property
+    def launches(self) -> int:
+        return int(self.L.jm_nvdec_launch_count(self.h))
+
     def free_host(self, ptr: int):
         self.L.jm_nvdec_memory_release_host(ptr, self.h)
 
     @staticmethod
-    def raw_packet(surface: np.ndarray | None, w: int, h: int, pitch: int, device_ptr: int = 0) -> np.ndarray:
+    def raw_packet(surface: np.ndarray | None, w: int, h: int, pitch: int, device_ptr: int = 0, flags: int = 0,
+                   ready_event: int = 0) -> np.ndarray:
         """Build a JM_NVDEC_CODEC_RAW_NV12 packet: header + pitched surface bytes (or a device pointer)."""
-        hdr = RawPacket(RawPacket.MAGIC, w, h, pitch, RawPacket.DEVICE_PTR if device_ptr else 0, 0, device_ptr)
+        hdr = RawPacket(RawPacket.MAGIC, w, h, pitch, (RawPacket.DEVICE_PTR if device_ptr else 0) | flags, 0, device_ptr)
         hb = np.frombuffer(bytes(hdr), dtype=np.uint8)
         if device_ptr:
+            if flags & RawPacket.WAIT_EVENT:
+                return np.concatenate([hb, np.array([ready_event], dtype=np.uint64).view(np.uint8)])
             return hb.copy()
         return np.concatenate([hb, surface.reshape(-1)])
 

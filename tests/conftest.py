@@ -28,3 +28,24 @@ def pytest_collection_modifyitems(config, items):
     for it in items:
         if "gpu" in it.keywords:
             it.add_marker(skip)
+
+
+@pytest.fixture(autouse=True)
+def _jmc_env_switches(monkeypatch):
+    """The library caches its JMC_* switches per process (not per launch): re-read them at the start of every test
+    (the previous test's monkeypatch has been undone by now) and whenever a test sets one."""
+    def reload():
+        try:
+            import jmcodec_b200
+            jmcodec_b200.reload_env()
+        except Exception:
+            pass
+    reload()
+    orig = monkeypatch.setenv
+
+    def setenv(name, value, *a, **k):
+        orig(name, value, *a, **k)
+        if name.startswith("JMC_"):
+            reload()
+    monkeypatch.setenv = setenv
+    yield

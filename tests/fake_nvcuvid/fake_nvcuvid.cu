@@ -14,6 +14,15 @@
  *
  * Select it with JMC_NVCUVID_LIB=<this .so>.  FAKE_NVCUVID_NO_ENGINE=1 makes cuvidGetDecoderCaps fail
  * like the real boxes do.
+ *
+ * Hazards a client can get wrong are made to HURT, so that the parity tests catch them:
+ *   - at most ulNumOutputSurfaces frames can be mapped at a time (a further cuvidMapVideoFrame fails);
+ *   - cuvidUnmapVideoFrame POISONS the output surface at once, on a private stream that is not ordered with the
+ *     client's: a client that unmaps before its kernel has read the surface converts garbage;
+ *   - cuvidDecodePicture overwrites the decode surface immediately (it does not wait for a post-processing copy
+ *     the client has only enqueued): a client that lets the parser reuse a picture index whose frame it has not
+ *     consumed yet gets the wrong picture;
+ *   - fake_nvcuvid_stats() reports how many frames were mapped at once, for tests of the batch drain.
  */
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -47,6 +56,9 @@ struct fake_parser {
     std::deque<int> delayed;        /* decoded, not yet displayed (display delay) */
     std::vector<unsigned char> rbsp;
 };
+
+struct stats_t { int maps, unmaps, cur_mapped, max_mapped, map_refused, decoders; } g_stats;
+cudaStream_t g_poison = nullptr;
 
 struct fake_decoder {
     CUVIDDECODECREATEINFO ci;
@@ -84,6 +96,8 @@ void handle_nal(fake_parser *ps, const unsigned char *nal, size_t n)
     const unsigned char type = nal[0];
     unescape(nal + 1, n - 1, ps->rbsp);
     if (type == 0x67 && ps->rbsp.size() >= 8) {
+        /* a new sequence: the pictures of the old one are displayed first, as the real parser does */
+        while (!ps->delayed.empty()) { display(ps, ps->delayed.front()); ps->delayed.pop_front(); }
         uint32_t w, h;
         memcpy(&w, &ps->rbsp[0], 4);
         memcpy(&h, &ps->rbsp[4], 4);
@@ -125,9 +139,10 @@ FAKE_API int cuvidGetDecoderCaps(void *caps)
 {
     const char *e = getenv("FAKE_NVCUVID_NO_ENGINE");
     if (e && atoi(e)) return 100;                                       /* CUDA_ERROR_NO_DEVICE, as on the real boxes */
-    unsigned char *c = (unsigned char *)caps;
-    c[24] = 1;                                                          /* bIsSupported */
-    c[25] = 1;                                                          /* nNumNVDECs */
+    CUVIDDECODECAPS *c = (CUVIDDECODECAPS *)caps;
+    c->bIsSupported = 1;
+    c->nNumNVDECs = 1;
+    c->nMaxWidth = c->nMaxHeight = 8192;
     return 0;
 }
 
@@ -196,6 +211,7 @@ FAKE_API int cuvidCreateDecoder(CUvideodecoder *out, CUVIDDECODECREATEINFO *ci)
         d->out_surf.push_back(p);
         d->out_busy.push_back(false);
     }
+    g_stats.decoders++;
     *out = d;
     return 0;
 }
@@ -229,13 +245,15 @@ FAKE_API int cuvidMapVideoFrame64(CUvideodecoder h, int idx, unsigned long long 
     if (!d || !dptr || !pitch || idx < 0 || (size_t)idx >= d->decode_surf.size()) return 1;
     size_t slot = 0;
     while (slot < d->out_surf.size() && d->out_busy[slot]) slot++;
-    if (slot == d->out_surf.size()) return 3;                           /* more frames mapped than ulNumOutputSurfaces */
+    if (slot == d->out_surf.size()) { g_stats.map_refused++; return 3; }    /* more frames mapped than ulNumOutputSurfaces */
     /* post-processing is ENQUEUED on the caller's stream and not waited for, like the real decoder:
      * a client that reads the surface on another stream without ordering sees stale data */
     cudaStream_t st = pp ? (cudaStream_t)pp->output_stream : 0;
     if (cudaMemsetAsync(d->out_surf[slot], 0xEE, d->pitch * d->rows, st) != cudaSuccess) return 2;
     if (cudaMemcpyAsync(d->out_surf[slot], d->decode_surf[idx], d->pitch * d->rows, cudaMemcpyDeviceToDevice, st) != cudaSuccess) return 2;
     d->out_busy[slot] = true;
+    g_stats.maps++;
+    if (++g_stats.cur_mapped > g_stats.max_mapped) g_stats.max_mapped = g_stats.cur_mapped;
     *dptr = (unsigned long long)(uintptr_t)d->out_surf[slot];
     *pitch = (unsigned int)d->pitch;
     return 0;
@@ -246,6 +264,23 @@ FAKE_API int cuvidUnmapVideoFrame64(CUvideodecoder h, unsigned long long dptr)
     fake_decoder *d = (fake_decoder *)h;
     if (!d) return 1;
     for (size_t i = 0; i < d->out_surf.size(); i++)
-        if ((unsigned long long)(uintptr_t)d->out_surf[i] == dptr && d->out_busy[i]) { d->out_busy[i] = false; return 0; }
+        if ((unsigned long long)(uintptr_t)d->out_surf[i] == dptr && d->out_busy[i]) {
+            /* the surface goes back to the decoder NOW: poison it without waiting for anything the client enqueued */
+            if (!g_poison) cudaStreamCreateWithFlags(&g_poison, cudaStreamNonBlocking);
+            cudaMemsetAsync(d->out_surf[i], 0xDD, d->pitch * d->rows, g_poison);
+            cudaStreamSynchronize(g_poison);
+            d->out_busy[i] = false;
+            g_stats.unmaps++;
+            g_stats.cur_mapped--;
+            return 0;
+        }
     return 1;
+}
+
+/* test hook (not part of the NVDEC ABI): v[0..5] = maps, unmaps, currently mapped, max mapped at once, refused maps,
+ * decoders created; reset != 0 clears the counters afterwards */
+FAKE_API void fake_nvcuvid_stats(int *v, int reset)
+{
+    if (v) { v[0] = g_stats.maps; v[1] = g_stats.unmaps; v[2] = g_stats.cur_mapped; v[3] = g_stats.max_mapped; v[4] = g_stats.map_refused; v[5] = g_stats.decoders; }
+    if (reset) { const int cur = g_stats.cur_mapped; memset(&g_stats, 0, sizeof(g_stats)); g_stats.cur_mapped = cur; }
 }

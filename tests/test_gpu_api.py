@@ -529,3 +529,206 @@ def test_raw_packet_fuzz_never_crashes(J):
     assert dec.decode_frame(good) == (0, 1)
     assert dec.output_frame(out, out.size) == (out.size, out.size)
     dec.deinit()
+
+
+# --------------------------------------------------------------------------------------------
+# delivery design behind jm_nvdec_decode_frame / jm_nvdec_output_frame
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("delay", [1, 2, 5])
+@pytest.mark.parametrize("out_fmt", [0, 1])
+def test_nvdec_display_delay(J, out_fmt, delay):
+    """With a display delay of n the frame announced is the one decoded n calls earlier (like ulMaxDisplayDelay,
+    nv_dec.cpp:346); end of stream hands out the rest one per call, then is_exit (test_nv_dec.cpp:232-246)."""
+    w, h, pitch, n = 354, 290, 512, 11
+    need = w * h * 3 // 2
+    chk = oracle.best()
+    dec = J.NvDec(0)
+    assert dec.set_display_delay(delay) == 0
+    assert dec.init(J.NvDec.CODEC_RAW_NV12, out_fmt) == 0
+    surfs = [synth.nv12_surface(w, h, pitch, 90, f) for f in range(n)]
+    out = np.full(need + 16, synth.OUT_FILL, np.uint8)
+    got_frames, gots = [], []
+    for s in surfs:
+        r, got = dec.decode_frame(J.NvDec.raw_packet(s, w, h, pitch))
+        assert r == 0
+        gots.append(got)
+        if got:
+            assert dec.output_frame(out, need + 16) == (need, need)
+            got_frames.append(out.copy())
+    assert gots == [0] * delay + [1] * (n - delay)
+    calls = 0
+    while not dec.is_exit():
+        r, got = dec.decode_frame(None, 0)
+        if got:
+            assert dec.output_frame(out, need + 16) == (need, need)
+            got_frames.append(out.copy())
+        calls += 1
+        assert calls <= delay + 2
+    assert len(got_frames) == n
+    want = np.full(need + 16, synth.OUT_FILL, np.uint8)
+    for i, s in enumerate(surfs):
+        chk.nvdec_output_frame(s, pitch, w, h, out_fmt, want, need + 16)
+        assert np.array_equal(got_frames[i], want), f"frame {i}"
+    assert f"Frame Count:\t{n}" in dec.show_dec_info()
+    dec.deinit()
+
+
+@pytest.mark.parametrize("geom", [(1920, 1080, 2048), (1919, 1079, 2048), (66, 34, 128)])
+@pytest.mark.parametrize("mode", ["pageable", "pageable_threads", "pinned", "registered", "lazy_pin", "device", "ref"])
+def test_nvdec_output_destinations(J, ctx, mode, geom):
+    """Every kind of out_buf receives exactly the bytes the reference writes (odd sizes: the tail stays untouched):
+    pageable (copy out of the pinned delivery ring, optionally with helper threads), pinned / registered / lazily
+    registered (direct DMA), device memory (device-to-device), and the zero-copy view of the ring."""
+    w, h, pitch = geom
+    need = w * h * 3 // 2
+    cap = need + 32
+    chk = oracle.best()
+    dec = J.NvDec(0)
+    if mode == "pageable_threads":
+        assert dec.set_option("copy_threads", 3) == 0
+    if mode == "lazy_pin":
+        assert dec.set_option("lazy_pin", 1) == 0
+    assert dec.init(J.NvDec.CODEC_RAW_NV12, 1) == 0
+    pinned = dbuf = None
+    if mode == "pinned":
+        pinned = dec.alloc_host(cap)
+        out = np.ctypeslib.as_array((C.c_uint8 * cap).from_address(pinned))
+    else:
+        out = np.empty(cap, np.uint8)
+    if mode == "registered":
+        assert dec.register_host(out) == 0
+    if mode == "device":
+        dbuf = ctx.alloc(cap)
+    want = np.empty(cap, np.uint8)
+    for f in range(5):
+        s = synth.nv12_surface(w, h, pitch, 91, f)
+        # alternate host payloads and device-pointer packets (SYNC: the surface is freed right after the call)
+        if f % 2:
+            d = ctx.upload(s)
+            assert dec.decode_frame(J.NvDec.raw_packet(None, w, h, pitch, device_ptr=d, flags=J.RawPacket.SYNC)) == (0, 1)
+            ctx.memset(d, 0x5A, s.size)
+            ctx.free(d)
+        else:
+            assert dec.decode_frame(J.NvDec.raw_packet(s, w, h, pitch)) == (0, 1)
+        want[:] = synth.OUT_FILL
+        assert chk.nvdec_output_frame(s, pitch, w, h, 1, want, cap) == (need, need)
+        if mode == "ref":
+            r, view = dec.output_frame_ref()
+            assert r == need and view.size == need
+            total = w * h + 2 * (w >> 1) * (h >> 1)                        # the bytes the reference writes (nv_dec.cpp:801-818)
+            assert np.array_equal(view[:total], want[:total])
+            continue
+        if mode == "device":
+            ctx.memset(dbuf, synth.OUT_FILL, cap)
+            assert dec.output_frame(dbuf, cap) == (need, need)
+            ctx.d2h(out, dbuf)
+        else:
+            out[:] = synth.OUT_FILL
+            assert dec.output_frame(out, cap) == (need, need)
+            assert dec.output_frame(out, cap) == (need, need)              # fetching the same frame again is allowed
+        assert np.array_equal(out, want), f"frame {f}"
+    if mode == "registered":
+        assert dec.unregister_host(out) == 0
+        assert dec.unregister_host(out) == -1
+    if pinned:
+        dec.free_host(pinned)
+    dec.deinit()
+    if dbuf:
+        ctx.free(dbuf)
+
+
+def test_nvdec_wait_event_packet_and_reinit(J, ctx):
+    """A device-pointer packet can carry the CUDA event that marks the surface complete; jm_nvdec_init on a live
+    handle starts over without leaking."""
+    w, h, pitch = 320, 200, 384
+    need = w * h * 3 // 2
+    chk = oracle.best()
+    dec = J.NvDec(0)
+    out, want = np.empty(need, np.uint8), np.empty(need, np.uint8)
+    for rnd in range(3):
+        assert dec.init(J.NvDec.CODEC_RAW_NV12, rnd % 2) == 0
+        s = synth.nv12_surface(w, h, pitch, 92, rnd)
+        d = ctx.upload(s)
+        ev = J.Event(ctx)
+        ev.record(0)
+        pkt = J.NvDec.raw_packet(None, w, h, pitch, device_ptr=d, flags=J.RawPacket.WAIT_EVENT, ready_event=ev.h.value)
+        assert dec.decode_frame(pkt) == (0, 1)
+        assert dec.output_frame(out, need) == (need, need)
+        chk.nvdec_output_frame(s, pitch, w, h, rnd % 2, want, need)
+        assert np.array_equal(out, want)
+        # truncated extended packet: refused, nothing announced
+        assert dec.decode_frame(pkt[:pkt.size - 4]) == (0, 0)
+        ev.close()
+        ctx.free(d)
+    dec.deinit()
+
+
+def test_calls_restore_the_callers_device(J):
+    """Every entry point switches to its handle's device and hands the caller's device back (the reference pushes /
+    pops its context per call, nv_dec.cpp:378,398,423,471)."""
+    if J.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    L = J.load()
+    w, h, pitch = 64, 32, 64
+    need = w * h * 3 // 2
+    assert L.jmc_set_current_device(0) == 0
+    dec = J.NvDec(1)
+    assert dec.init(J.NvDec.CODEC_RAW_NV12, 1) == 0
+    assert L.jmc_current_device() == 0
+    out = np.empty(need, np.uint8)
+    assert dec.decode_frame(J.NvDec.raw_packet(synth.nv12_surface(w, h, pitch, 93, 0), w, h, pitch)) == (0, 1)
+    assert L.jmc_current_device() == 0
+    assert dec.output_frame(out, need) == (need, need)
+    assert L.jmc_current_device() == 0
+    c1 = J.Ctx(1)
+    d = c1.alloc(1024)
+    c1.memset(d, 1, 1024)
+    c1.free(d)
+    assert L.jmc_current_device() == 0
+    enc = J.NvEnc(1)
+    assert enc.init(w, h, J.NvEnc.FMT_YV12) == 0
+    assert enc.enc_frame(synth.i420_frame(w, h, 93, 1))[0] == 0
+    assert L.jmc_current_device() == 0
+    enc.deinit(), dec.deinit(), c1.close()
+    assert L.jmc_current_device() == 0
+
+
+def test_nvenc_short_buffer_and_reinit(J):
+    w, h = 128, 64
+    enc = J.NvEnc(0)
+    for fmt, n_in in ((J.NvEnc.FMT_NV12, w * h * 3 // 2), (J.NvEnc.FMT_ARGB, w * h * 4)):
+        assert enc.init(w, h, fmt) == 0                                # second round: init on a live handle
+        src = synth.random_bytes(n_in, 5)
+        assert enc.enc_frame(src, n_in - 1)[0] == 8                    # NV_ENC_ERR_INVALID_PARAM, nothing over-read
+        assert "shorter" in J.last_error()
+        assert enc.enc_frame(src)[0] == 0
+    enc.deinit()
+
+
+def test_job_with_host_side_pointer_list(J, ctx):
+    """JMC_JOB_LIST_ON_HOST: up to 8 frame pointers travel as kernel arguments (how jm_nvdec_* batches mapped
+    surfaces); alignment is judged from the pointers themselves, so skewed pointers take the any-alignment kernel."""
+    w, h, pitch = 640, 360, 768
+    surf_bytes, need = pitch * h * 3 // 2, w * h * 3 // 2
+    chk = oracle.best()
+    for skew in (0, 3):
+        n = 5
+        surfs = [synth.nv12_surface(w, h, pitch, 94, f) for f in range(n)]
+        dsurf = [ctx.upload(s) for s in surfs]
+        dout = [ctx.alloc(need + 16) for _ in range(n)]
+        j = ctx.job_nvdec(w, h, pitch, 1)
+        sl = (C.c_void_p * n)(*dsurf)
+        tl = (C.c_void_p * n)(*[d + skew for d in dout])
+        j.n_frames, j.flags = n, J.JOB_LIST_ON_HOST
+        j.surf.list, j.tight.list = C.cast(sl, C.c_void_p), C.cast(tl, C.c_void_p)
+        ctx.convert(j)
+        got, want = np.empty(need, np.uint8), np.empty(need, np.uint8)
+        for f in range(n):
+            ctx.d2h(got, dout[f] + skew)
+            chk.nvdec_output_frame(surfs[f], pitch, w, h, 1, want, need)
+            assert np.array_equal(got, want), (skew, f)
+        j.n_frames = 9
+        with pytest.raises(J.JmcError):
+            ctx.convert(j)                                             # more than JMC_INLINE_LIST_MAX frames
+        for d in dsurf + dout:
+            ctx.free(d)
