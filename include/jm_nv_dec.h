@@ -104,7 +104,7 @@ JMDLL_FUNC int jm_nvdec_deinit(handle_nvdec handle);
  *   (or in_buf == NULL) flushes / signals end of stream; *got_frame = 1 if a frame is ready for
  *   jm_nvdec_output_frame.  At most one frame per call.  Returns 0 like the reference, with ONE
  *   exception: -1 when decoded frames had to be dropped because the caller stopped fetching (the handle
- *   keeps at most 32 converted frames; the reference's queue is unbounded and overwrites decode surfaces
+ *   keeps at most 64 converted frames; the reference's queue is unbounded and overwrites decode surfaces
  *   instead).  Every surface that became available in this call is converted by one launch and its
  *   delivery to the host is started before the call returns; nothing waits for it here.
  *   With a display delay of n (jm_nvdec_set_display_delay) the frame announced is the one decoded n calls
@@ -141,15 +141,17 @@ JMDLL_FUNC int jm_nvdec_set_device(int device, handle_nvdec handle);
 JMDLL_FUNC int jm_nvdec_memory_alloc_host(void **buf, int buf_len, handle_nvdec handle);
 JMDLL_FUNC int jm_nvdec_memory_release_host(void *buf, handle_nvdec handle);
 /** page-lock a buffer the caller already owns (malloc'ed out_buf / packet buffer) so that it is reached by direct
- *  DMA; unregister it BEFORE freeing it.  (JMC_NVDEC_LAZY_PIN=1 / option "lazy_pin" does this automatically for a
- *  buffer passed on two consecutive calls -- opt-in, because the library cannot see the caller free it.) */
+ *  DMA; unregister it BEFORE freeing it.  Only the whole pages INSIDE the buffer are locked (its partial first / last
+ *  page may hold other allocations of the caller); those < 4 KB edges are copied through a pinned bounce buffer.
+ *  Buffers with less than 64 KB of whole pages are left pageable (returns -1).  (JMC_NVDEC_LAZY_PIN=1 / option "lazy_pin" does this automatically for a
+ *  buffer it sees for the second time -- opt-in, because the library cannot see the caller free it.) */
 JMDLL_FUNC int jm_nvdec_memory_register_host(void *buf, int buf_len, handle_nvdec handle);
 JMDLL_FUNC int jm_nvdec_memory_unregister_host(void *buf, handle_nvdec handle);
 /** frames held back before they are announced (0..20, default 0 or env JMC_NVDEC_DISPLAY_DELAY): with n >= 1 the
  *  delivery of frame k overlaps the upload / decode / conversion of frame k+1 */
 JMDLL_FUNC int jm_nvdec_set_display_delay(int frames, handle_nvdec handle);
-/** "display_delay", "lazy_pin" (0/1), "copy_threads" (helper threads for copies from/to pageable memory, 0..16,
- *  env JMC_NVDEC_COPY_THREADS), "map_limit" (decoder surfaces mapped and converted per launch, 1..8) */
+/** "display_delay", "lazy_pin" (0/1), "copy_threads" (helper threads for copies from/to PAGEABLE caller memory, 0..16; default
+ *  min(4, cores/4) or env JMC_NVDEC_COPY_THREADS; started only when such a copy happens), "map_limit" (decoder surfaces mapped and converted per launch, 1..8) */
 JMDLL_FUNC int jm_nvdec_set_option(const char *name, int value, handle_nvdec handle);
 /** zero-copy fetch: *frame points at the current frame inside the handle's pinned delivery ring (same bytes
  *  jm_nvdec_output_frame would write), valid until the next jm_nvdec_decode_frame call.  Returns w*h*3/2 or -1. */

@@ -11,9 +11,12 @@
  *     cuMemcpyDtoH pitch*h*3/2, SYNC (:452)             and converted by ONE launch (NV12 -> tight NV12 / I420 in
  *     ONE pinned buffer (MAX_OUTPUT_FRAMES 1)           HBM, pointer list as kernel arguments) into a RING of
  *                                                       tight frames; the D2H of every tight frame is enqueued at
- *                                                       once on the delivery stream into a pinned ring slot
- *                                                       (prefetch); surfaces are unmapped when the convert event
- *                                                       has fired -- nothing waits per frame
+ *                                                       once behind its kernel into a pinned ring slot (prefetch);
+ *                                                       surfaces are unmapped when the launch's event has fired --
+ *                                                       nothing waits per frame.  Batches alternate between two
+ *                                                       streams ("lanes"): upload, kernel and delivery of a batch
+ *                                                       are ordered by their stream alone (no cross-stream
+ *                                                       semaphores), while the other lane's kernel overlaps them
  *   output_frame: CPU strip/de-interleave (:782-820)  output_frame: waits for THAT frame's delivery events only;
  *                                                       pinned / registered out_buf: direct DMA of the tight frame;
  *                                                       pageable out_buf: chunk-pipelined copy out of the pinned ring
@@ -33,6 +36,8 @@
 #include <string.h>
 #include <time.h>
 
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -46,12 +51,13 @@
 
 #define NVDEC_MAX_FRAMES 10         /* decode surfaces / upload surfaces, nv_dec/nv_dec.h:32 */
 #define MAX_LEN_DEC_INFO 1024       /* nv_dec/nv_dec.h:33 */
-#define RING_MAX 32                 /* converted frames a handle holds at most (announced + not yet announced) */
+#define RING_MAX 64                 /* converted frames a handle holds at most (announced + not yet announced) */
 #define MAX_CHUNKS 8                /* delivery events per frame (chunk-pipelined copy-out) */
 #define MAP_LIMIT_MAX JMC_INLINE_LIST_MAX   /* decoder surfaces mapped at a time = frames per conversion launch */
 #define MAX_DECODE_SURFACES 64
 #define MAX_LAZY_REGS 8
 #define COPY_THREADS_MAX 16
+#define DELAY_MAX 20
 
 namespace {
 
@@ -63,11 +69,13 @@ int env_int(const char *name, int dflt, int lo, int hi)
     return v < lo ? lo : (v > hi ? hi : v);
 }
 
-/* ---- host copies: calling thread + optional helper threads --------------------------------------- */
+/* ---- host copies: calling thread + helper threads -------------------------------------------------- */
 struct copy_job {
     uint8_t *dst; size_t dpitch;
     const uint8_t *src; size_t spitch;
     size_t width, rows;
+    size_t phase_rows;              /* rows per phase; phase p may be copied once `ready` > p */
+    int n_phases;
 };
 
 void copy_rows(const copy_job &j, size_t r0, size_t r1)
@@ -77,78 +85,108 @@ void copy_rows(const copy_job &j, size_t r0, size_t r1)
     for (size_t r = r0; r < r1; r++) memcpy(j.dst + r * j.dpitch, j.src + r * j.spitch, j.width);
 }
 
-/* A handle's helper threads for host copies between pageable caller memory and the pinned rings.  With no
- * helpers (the default) copy() is a plain loop on the calling thread. */
+/* A handle's helper threads for host copies between pageable caller memory and the pinned rings (the reference's
+ * callers pass malloc'ed buffers, test_nv_dec.cpp:207).  A job is cut into PHASES (the chunks of a frame that is
+ * still arriving by DMA) and every phase into one slice per thread: the threads are woken once per frame and
+ * spin on `ready` while the next chunk is in flight, so the copy-out runs at several cores' memcpy rate right
+ * behind the DMA.  Threads are started on first use; with none, everything runs on the calling thread. */
 struct copy_pool {
     std::vector<std::thread> workers;
     std::mutex m;
     std::condition_variable cv_work, cv_done;
     copy_job job;
+    int want_threads = 0;
     int n_parts = 0, next_part = 0, done_parts = 0;
-    uint64_t gen = 0;
-    bool stop = false;
+    std::atomic<uint64_t> gen{0};
+    std::atomic<bool> stop{false};
+    std::atomic<int> ready{0};
+
+    void run_part(const copy_job &j, int part, int np)
+    {
+        for (int ph = 0; ph < j.n_phases; ph++) {
+            while (ready.load(std::memory_order_acquire) <= ph) __builtin_ia32_pause();
+            const size_t r0 = (size_t)ph * j.phase_rows;
+            const size_t r1 = r0 + j.phase_rows < j.rows ? r0 + j.phase_rows : j.rows;
+            if (r1 > r0) copy_rows(j, r0 + (r1 - r0) * part / np, r0 + (r1 - r0) * (part + 1) / np);
+        }
+    }
 
     void worker()
     {
         uint64_t seen = 0;
-        std::unique_lock<std::mutex> lk(m);
         for (;;) {
-            cv_work.wait(lk, [&] { return stop || (gen != seen && next_part < n_parts); });
-            if (stop) return;
-            seen = gen;
-            while (next_part < n_parts) {
+            /* a streaming caller hands over the next copy within tens of microseconds: spin that long before
+             * going to sleep, a condition-variable wake-up costs more than the wait */
+            const auto t0 = std::chrono::steady_clock::now();
+            while (gen.load(std::memory_order_acquire) == seen && !stop.load(std::memory_order_relaxed) &&
+                   std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(150)) __builtin_ia32_pause();
+            std::unique_lock<std::mutex> lk(m);
+            cv_work.wait(lk, [&] { return stop.load() || (gen.load() != seen && next_part < n_parts); });
+            if (stop.load()) return;
+            seen = gen.load();
+            if (next_part < n_parts) {
                 const int part = next_part++;
                 const copy_job j = job;
                 const int np = n_parts;
                 lk.unlock();
-                copy_rows(j, j.rows * part / np, j.rows * (part + 1) / np);
+                run_part(j, part, np);
                 lk.lock();
                 if (++done_parts == n_parts) cv_done.notify_all();
             }
         }
     }
 
-    void start(int n)
+    void ensure_started()
     {
-        for (int i = (int)workers.size(); i < n; i++) workers.emplace_back([this] { worker(); });
+        for (int i = (int)workers.size(); i < want_threads; i++) workers.emplace_back([this] { worker(); });
     }
 
     void shutdown()
     {
-        { std::lock_guard<std::mutex> lk(m); stop = true; }
+        { std::lock_guard<std::mutex> lk(m); stop.store(true); }
         cv_work.notify_all();
         for (auto &t : workers) t.join();
         workers.clear();
+        stop.store(false);
     }
 
-    void copy(const copy_job &j)
+    /* wait_phase(p): called on the calling thread before phase p is released (NULL: everything is there). */
+    template <class Wait> void run(copy_job j, Wait wait_phase)
     {
+        if (j.n_phases < 1) { j.n_phases = 1; j.phase_rows = j.rows; }
         const size_t bytes = j.width * j.rows;
-        if (workers.empty() || bytes < (256u << 10) || j.rows < 2) { copy_rows(j, 0, j.rows); return; }
+        if (want_threads > 0 && bytes >= (512u << 10) && j.rows >= 8) ensure_started();
+        if (workers.empty() || bytes < (512u << 10) || j.rows < 8) {
+            for (int ph = 0; ph < j.n_phases; ph++) {
+                wait_phase(ph);
+                const size_t r0 = (size_t)ph * j.phase_rows;
+                copy_rows(j, r0, r0 + j.phase_rows < j.rows ? r0 + j.phase_rows : j.rows);
+            }
+            return;
+        }
         std::unique_lock<std::mutex> lk(m);
         job = j;
         n_parts = (int)workers.size() + 1;
-        if ((size_t)n_parts > j.rows) n_parts = (int)j.rows;
-        next_part = done_parts = 0;
-        gen++;
+        next_part = 1;                                     /* part 0 is the caller's */
+        done_parts = 0;
+        ready.store(0, std::memory_order_release);
+        gen.fetch_add(1, std::memory_order_release);
+        lk.unlock();
         cv_work.notify_all();
-        while (next_part < n_parts) {                      /* the caller takes parts too */
-            const int part = next_part++;
-            const int np = n_parts;
-            lk.unlock();
-            copy_rows(j, j.rows * part / np, j.rows * (part + 1) / np);
-            lk.lock();
-            ++done_parts;
+        const int np = n_parts;
+        for (int ph = 0; ph < j.n_phases; ph++) {
+            wait_phase(ph);
+            ready.store(ph + 1, std::memory_order_release);
+            const size_t r0 = (size_t)ph * j.phase_rows;
+            const size_t r1 = r0 + j.phase_rows < j.rows ? r0 + j.phase_rows : j.rows;
+            if (r1 > r0) copy_rows(j, r0, r0 + (r1 - r0) / np);     /* slice 0 */
         }
+        lk.lock();
+        ++done_parts;
         cv_done.wait(lk, [&] { return done_parts == n_parts; });
     }
 
-    void copy_flat(uint8_t *dst, const uint8_t *src, size_t n)
-    {
-        const size_t unit = 4096, rows = n / unit;
-        if (rows) { copy_job j = { dst, unit, src, unit, unit, rows }; copy(j); }
-        if (n % unit) memcpy(dst + rows * unit, src + rows * unit, n % unit);
-    }
+    void copy(const copy_job &j) { run(j, [](int) {}); }
 };
 
 /* ---- state --------------------------------------------------------------------------------------- */
@@ -158,6 +196,8 @@ struct decoded_surface {            /* what cuvidMapVideoFrame yields: device po
     int pool_slot;                  /* >= 0: one of our upload surfaces; -1: caller-owned device memory;
                                        -2: a CUVID picture still to be mapped (disp valid) */
     bool sync_consume;              /* JM_NVDEC_RAW_SYNC: do not return before the kernel has read the surface */
+    int lane;                       /* >= 0: the surface is being produced on this lane (upload of a host payload, a
+                                       caller's event awaited there) and must be converted on it; -1: any lane */
     CUVIDPARSERDISPINFO disp;       /* copied, not pointed to (the reference queues the parser's pointer, nv_dec.cpp:156) */
 };
 
@@ -165,8 +205,9 @@ struct decoded_surface {            /* what cuvidMapVideoFrame yields: device po
 struct ring_slot {
     uint8_t *d_tight = nullptr; size_t d_bytes = 0;
     uint8_t *h_tight = nullptr; size_t h_bytes = 0;
-    cudaEvent_t converted = nullptr;
+    cudaEvent_t converted = nullptr;        /* recorded only for JM_NVDEC_RAW_SYNC packets */
     cudaEvent_t direct = nullptr;           /* a direct D2H / D2D into the caller's buffer has finished */
+    int lane = -1;                          /* the stream this slot's frame was converted on */
     cudaEvent_t delivered[MAX_CHUNKS] = {};
     int n_chunks = 0;
     size_t chunk_bytes = 0, total = 0;      /* total: the bytes the reference writes for this frame */
@@ -220,11 +261,14 @@ struct nvdec_b200 {
     std::deque<int> ready;
     int cur = -1;
     int slot_rr = 0;
+    int lane_next = 0;              /* lane of the next batch */
     int delay = 0;                  /* frames kept back before they are announced (display delay) */
     bool staged = true;             /* prefetch tight frames into the pinned ring (pageable out_buf callers) */
     int lazy_pin = 0;               /* cudaHostRegister a pageable out_buf / in_buf seen twice (opt-in) */
-    const void *cand_out = nullptr, *cand_in = nullptr;
+    const void *cand[MAX_LAZY_REGS] = {};    /* pageable buffers seen once (callers rotate over a few) */
+    int cand_next = 0;
     std::vector<lazy_reg> regs;     /* registered by us: lazily or through jm_nvdec_memory_register_host */
+    uint8_t *h_edge = nullptr;      /* pinned bounce buffer for the unregistered < 4 KB edges of such buffers: 2 x 4 KB out, 2 x 4 KB in */
     copy_pool copier;
     int copy_threads = 0;
 
@@ -249,8 +293,13 @@ struct nvdec_b200 {
     std::vector<cudaEvent_t> free_events;
 };
 
-cudaStream_t convert_stream(nvdec_b200 *c) { return (cudaStream_t)jmc_ctx_stream(c->ctx, 0); }
-cudaStream_t delivery_stream(nvdec_b200 *c) { return (cudaStream_t)jmc_ctx_stream(c->ctx, 2); }
+/* Two lanes = two streams of the handle's context.  Everything that belongs to one batch of frames -- upload of a
+ * host payload, the decoder's post-processing, the conversion launch, the delivery copies -- is enqueued on ONE
+ * lane, so it is ordered without events; consecutive batches take alternate lanes, so a batch's kernel overlaps
+ * the previous batch's delivery.  A ring slot stays with the lane that used it last (reuse is then ordered by the
+ * stream too).  Measured: with cross-stream events instead (convert stream -> delivery stream and back) four
+ * handles on one GPU fell from 17 k to 3-16 k frames/s, erratically (profiles/r2_dropin_lanes.txt). */
+cudaStream_t lane_stream(nvdec_b200 *c, int lane) { return (cudaStream_t)jmc_ctx_stream(c->ctx, lane ? 2 : 0); }
 
 const char *codec_name(int t)
 {
@@ -311,21 +360,24 @@ size_t written_bytes(int out_fmt, int w, int h)
 /* A free ring slot able to hold a w x h frame, or -1 (ring full / out of memory).  Slots are taken round-robin
  * so that a slot whose delivery may still be in flight is reused as late as possible; the convert stream waits
  * for that delivery before the slot's device frame is overwritten. */
-int acquire_slot(nvdec_b200 *c, int w, int h)
+int acquire_slot(nvdec_b200 *c, int w, int h, int lane)
 {
     size_t need = (size_t)jmc_tight_bytes(w, h);
     if (need == 0) need = 1;
-    int idx = -1;
+    int idx = -1, other = -1;
     const int n = (int)c->ring.size();
     for (int k = 0; k < n; k++) {
         const int i = (c->slot_rr + k) % n;
-        if (!c->ring[i].busy) { idx = i; break; }
+        if (c->ring[i].busy) continue;
+        if (c->ring[i].lane == lane || c->ring[i].lane < 0) { idx = i; break; }
+        if (other < 0) other = i;
     }
-    if (idx < 0) {
-        if (n >= RING_MAX) return -1;
+    if (idx < 0 && n < RING_MAX) {
         c->ring.emplace_back();
         idx = n;
     }
+    if (idx < 0) idx = other;                                 /* ring at its limit: take over a slot of the other lane */
+    if (idx < 0) return -1;
     ring_slot &s = c->ring[idx];
     if (!s.converted) {
         if (cudaEventCreateWithFlags(&s.converted, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
@@ -339,8 +391,10 @@ int acquire_slot(nvdec_b200 *c, int w, int h)
         s.d_bytes = need;
         s.prefetched = false;
     }
-    if (s.prefetched && s.n_chunks > 0)                       /* the previous frame's D2H may still be reading d_tight */
-        cudaStreamWaitEvent(convert_stream(c), s.delivered[s.n_chunks - 1], 0);
+    /* a slot changing lanes: its previous delivery (on the other stream) may still be reading d_tight */
+    if (s.lane >= 0 && s.lane != lane && s.prefetched && s.n_chunks > 0)
+        cudaStreamWaitEvent(lane_stream(c, lane), s.delivered[s.n_chunks - 1], 0);
+    s.lane = lane;
     s.prefetched = false;
     s.n_chunks = 0;
     s.w = w; s.h = h;
@@ -355,7 +409,7 @@ void release_slot(nvdec_b200 *c, int idx)
     if (idx >= 0) c->ring[idx].busy = false;
 }
 
-/* Enqueue the D2H of a converted frame into the slot's pinned buffer on the delivery stream, in chunks with an
+/* Enqueue the D2H of a converted frame into the slot's pinned buffer on the slot's lane (behind its kernel), in chunks with an
  * event each, so that output_frame can copy chunk i out while chunk i+1 is still crossing PCIe. */
 bool prefetch_slot(nvdec_b200 *c, ring_slot &s)
 {
@@ -369,8 +423,7 @@ bool prefetch_slot(nvdec_b200 *c, ring_slot &s)
         }
         s.h_bytes = s.d_bytes;
     }
-    cudaStream_t ds = delivery_stream(c);
-    if (cudaStreamWaitEvent(ds, s.converted, 0) != cudaSuccess) return false;
+    cudaStream_t ds = lane_stream(c, s.lane);
     /* no display delay: output_frame is waiting for this very frame, so pipeline its copy-out against the DMA;
      * with a delay the frame lands long before it is fetched and one copy is cheapest for the link */
     int chunks = c->delay > 0 ? 1 : (int)(s.total / (512u << 10));
@@ -411,23 +464,50 @@ int host_kind_of(const void *p, size_t len)
 
 bool is_device_accessible_host(const void *p, size_t len) { return host_kind_of(p, len) == MEM_PINNED; }
 
+/* Page-lock the WHOLE PAGES INSIDE [p, p+len) -- never the partial pages at its ends: those may hold other
+ * allocations of the caller, and a buffer that is only partly registered makes every CUDA copy from / to it fail
+ * ("invalid argument"), also copies that have nothing to do with this library.  The < 4 KB edges of such a buffer
+ * go through a small pinned bounce buffer (split_*). */
 bool register_range(nvdec_b200 *c, const void *p, size_t len)
 {
-    const uintptr_t page = 4096, lo = (uintptr_t)p & ~(page - 1), hi = ((uintptr_t)p + len + page - 1) & ~(page - 1);
+    const uintptr_t page = 4096, lo = ((uintptr_t)p + page - 1) & ~(page - 1), hi = ((uintptr_t)p + len) & ~(page - 1);
+    if (hi <= lo || hi - lo < (64u << 10)) return false;                  /* not worth a registration */
     if ((int)c->regs.size() >= MAX_LAZY_REGS * 4) return false;
     if (cudaHostRegister((void *)lo, hi - lo, cudaHostRegisterDefault) != cudaSuccess) { cudaGetLastError(); return false; }
     c->regs.push_back({ (void *)lo, hi - lo });
     return true;
 }
 
-/* Opt-in (JMC_NVDEC_LAZY_PIN=1 / jm_nvdec_set_option): a pageable caller buffer seen on two consecutive calls is
+/* The part of [p, p+len) that this handle has registered, if it leaves at most 4 KB at either end. */
+bool registered_interior(nvdec_b200 *c, const void *p, size_t len, uint8_t **lo, uint8_t **hi)
+{
+    const uintptr_t a = (uintptr_t)p, b = a + len;
+    for (const lazy_reg &r : c->regs) {
+        const uintptr_t l = a > (uintptr_t)r.base ? a : (uintptr_t)r.base;
+        const uintptr_t h = b < (uintptr_t)r.base + r.len ? b : (uintptr_t)r.base + r.len;
+        if (h > l && l - a <= 4096 && b - h <= 4096) { *lo = (uint8_t *)l; *hi = (uint8_t *)h; return true; }
+    }
+    return false;
+}
+
+bool ensure_edges(nvdec_b200 *c)
+{
+    if (c->h_edge) return true;
+    if (cudaHostAlloc((void **)&c->h_edge, 4 * 4096, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); c->h_edge = nullptr; return false; }
+    return true;
+}
+
+/* Opt-in (JMC_NVDEC_LAZY_PIN=1 / jm_nvdec_set_option): a pageable caller buffer seen for the second time is
  * page-locked in place so that it receives / supplies frames by direct DMA.  Off by default: the registration
  * outlives a free() of the buffer by the caller, which the library cannot observe. */
-bool maybe_lazy_pin(nvdec_b200 *c, const void *p, size_t len, const void **cand)
+bool maybe_lazy_pin(nvdec_b200 *c, const void *p, size_t len)
 {
     if (!c->lazy_pin) return false;
-    if (*cand != p) { *cand = p; return false; }
-    return register_range(c, p, len);
+    for (int i = 0; i < MAX_LAZY_REGS; i++)
+        if (c->cand[i] == p) { c->cand[i] = nullptr; return register_range(c, p, len); }
+    c->cand[c->cand_next] = p;
+    c->cand_next = (c->cand_next + 1) % MAX_LAZY_REGS;
+    return false;
 }
 
 /* ---- NVDEC front-end ------------------------------------------------------------------------ */
@@ -671,11 +751,14 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
     memset(&s, 0, sizeof(s));
     s.width = h.width; s.height = h.height; s.pitch = h.pitch;
     s.sync_consume = (h.flags & JM_NVDEC_RAW_SYNC) != 0;
-    cudaStream_t st = convert_stream(c);
+    s.lane = -1;
     if (h.flags & JM_NVDEC_RAW_DEVICE_PTR) {
         s.dptr = (uint8_t *)(uintptr_t)h.device_ptr;
         s.pool_slot = -1;
         if (h.flags & JM_NVDEC_RAW_WAIT_EVENT) {
+            s.lane = c->lane_next;
+            c->lane_next ^= 1;
+            cudaStream_t st = lane_stream(c, s.lane);
             /* the surface is being produced on another stream: order the conversion after the caller's event */
             if (len < (int)sizeof(jm_nvdec_raw_packet_ex)) return -1;
             jm_nvdec_raw_packet_ex x;
@@ -686,12 +769,16 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
         const size_t bytes = (size_t)h.pitch * h.height * 3 / 2;         /* nv_dec.cpp:453 */
         if ((size_t)len < sizeof(h) + bytes) return -1;
         if (bytes > c->pool_bytes) {                                     /* geometry grew: new surfaces */
-            cudaStreamSynchronize(st);
+            jmc_ctx_sync(c->ctx);
             for (int i = 0; i < NVDEC_MAX_FRAMES; i++) if (c->pool[i]) { cudaFree(c->pool[i]); c->pool[i] = nullptr; }
             c->pool_bytes = bytes;
         }
         const int slot = c->pool_next;
         c->pool_next = (c->pool_next + 1) % NVDEC_MAX_FRAMES;
+        /* an upload surface always works on the same lane (NVDEC_MAX_FRAMES is even): its next upload is ordered behind
+         * the kernel that read it by the stream itself */
+        s.lane = slot & 1;
+        cudaStream_t st = lane_stream(c, s.lane);
         if (!c->pool[slot]) {
             if (cudaMalloc((void **)&c->pool[slot], c->pool_bytes ? c->pool_bytes : 1) != cudaSuccess) { cudaGetLastError(); return -1; }
         }
@@ -700,9 +787,27 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
         const uint8_t *src = buf + sizeof(h);
         const size_t rows = (size_t)h.height * 3 / 2, wbytes = (size_t)h.width;
         if (bytes > 0 && wbytes > 0 && rows > 0) {
-            bool pinned = is_device_accessible_host(src, bytes);
-            if (!pinned && maybe_lazy_pin(c, buf, (size_t)len, &c->cand_in)) pinned = true;
-            if (pinned) {
+            const bool pinned = is_device_accessible_host(src, bytes);
+            uint8_t *blo = nullptr, *bhi = nullptr;
+            bool split = false;
+            if (!pinned) {
+                split = registered_interior(c, src, bytes, &blo, &bhi);
+                if (!split && maybe_lazy_pin(c, src, bytes)) split = registered_interior(c, src, bytes, &blo, &bhi);
+                if (split && !ensure_edges(c)) split = false;
+            }
+            if (split) {
+                /* registered interior of a malloc'ed packet: the whole pitched payload moves by DMA out of the caller's
+                 * buffer (one linear copy, like the reference's own cuMemcpyDtoH of pitch*h*3/2, nv_dec.cpp:452-453, in the
+                 * other direction); its two < 4 KB edges take the pinned bounce buffer */
+                const size_t head = (size_t)(blo - src), body = (size_t)(bhi - blo), tail = bytes - head - body;
+                uint8_t *e = c->h_edge + 2 * 4096;
+                cudaError_t er = cudaSuccess;
+                if (head) { memcpy(e, src, head); er = cudaMemcpyAsync(c->pool[slot], e, head, cudaMemcpyHostToDevice, st); }
+                if (er == cudaSuccess) er = cudaMemcpyAsync(c->pool[slot] + head, blo, body, cudaMemcpyHostToDevice, st);
+                if (er == cudaSuccess && tail) { memcpy(e + 4096, bhi, tail); er = cudaMemcpyAsync(c->pool[slot] + head + body, e + 4096, tail, cudaMemcpyHostToDevice, st); }
+                if (er == cudaSuccess) er = cudaStreamSynchronize(st);
+                if (er != cudaSuccess) { cudaGetLastError(); return -1; }
+            } else if (pinned) {
                 /* pinned / registered payload: DMA straight out of the caller's buffer, complete before returning */
                 if (cudaMemcpy2DAsync(c->pool[slot], (size_t)h.pitch, src, (size_t)h.pitch, wbytes, rows, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return -1; }
                 if (cudaStreamSynchronize(st) != cudaSuccess) { cudaGetLastError(); return -1; }
@@ -711,16 +816,23 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
                  * in_buf has been read) and let the H2D run behind us */
                 const size_t need = wbytes * rows;
                 if (need > c->stage_bytes) {
-                    cudaStreamSynchronize(st);
+                    jmc_ctx_sync(c->ctx);
                     for (int i = 0; i < NVDEC_MAX_FRAMES; i++) if (c->h_stage[i]) { cudaFreeHost(c->h_stage[i]); c->h_stage[i] = nullptr; }
                     c->stage_bytes = need;
                 }
                 if (!c->h_stage[slot] && cudaHostAlloc((void **)&c->h_stage[slot], c->stage_bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return -1; }
                 if (!c->stage_done[slot] && cudaEventCreateWithFlags(&c->stage_done[slot], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
                 if (c->stage_used[slot]) cudaEventSynchronize(c->stage_done[slot]);        /* ten uploads ago: long done */
-                copy_job cj = { c->h_stage[slot], wbytes, src, (size_t)h.pitch, wbytes, rows };
-                c->copier.copy(cj);
-                if (cudaMemcpy2DAsync(c->pool[slot], (size_t)h.pitch, c->h_stage[slot], wbytes, wbytes, rows, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return -1; }
+                /* rows are compacted by the copy threads in a few pieces; each piece's H2D starts while the next is
+                 * being compacted */
+                const size_t pieces = (need >= (2u << 20) && c->delay == 0) ? 4 : 1, prow = (rows + pieces - 1) / pieces;
+                for (size_t r0 = 0; r0 < rows; r0 += prow) {
+                    const size_t nr = rows - r0 < prow ? rows - r0 : prow;
+                    copy_job cj = { c->h_stage[slot] + r0 * wbytes, wbytes, src + r0 * (size_t)h.pitch, (size_t)h.pitch, wbytes, nr, nr, 1 };
+                    c->copier.copy(cj);
+                    if (cudaMemcpy2DAsync(c->pool[slot] + r0 * (size_t)h.pitch, (size_t)h.pitch, c->h_stage[slot] + r0 * wbytes, wbytes, wbytes, nr,
+                                          cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return -1; }
+                }
                 cudaEventRecord(c->stage_done[slot], st);
                 c->stage_used[slot] = true;
             }
@@ -765,11 +877,15 @@ int convert_stage(nvdec_b200 *c, bool must_progress)
     unsigned long long mapped[MAP_LIMIT_MAX];
     int k = 0;
     int pitch = first.pitch;
+    int lane = first.lane;
+    if (lane < 0) { lane = c->lane_next; c->lane_next ^= 1; }
+    cudaStream_t st = lane_stream(c, lane);
     while (k < limit && !c->pending.empty()) {
         decoded_surface s = c->pending.front();
         if ((s.pool_slot == -2) != cuvid || s.width != first.width || s.height != first.height) break;
         if (!cuvid && s.pitch != pitch) break;
-        const int slot = acquire_slot(c, s.width, s.height);
+        if (s.lane >= 0 && s.lane != lane) break;                         /* produced on the other lane: next launch */
+        const int slot = acquire_slot(c, s.width, s.height, lane);
         if (slot < 0) break;
         mapped[k] = 0;
         if (cuvid) {
@@ -780,7 +896,7 @@ int convert_stage(nvdec_b200 *c, bool must_progress)
             pp.progressive_frame = s.disp.progressive_frame;
             pp.top_field_first = s.disp.top_field_first;
             pp.unpaired_field = s.disp.repeat_first_field < 0;
-            pp.output_stream = convert_stream(c);
+            pp.output_stream = st;
             unsigned int mp = 0;
             if (c->nv.map_frame(c->decoder, s.disp.picture_index, &mapped[k], &mp, &pp) != 0 || !mapped[k]) {
                 release_slot(c, slot);
@@ -823,16 +939,13 @@ int convert_stage(nvdec_b200 *c, bool must_progress)
         j.tight.list = tlist;
         j.flags = JMC_JOB_LIST_ON_HOST;                                   /* the pointers ride in the kernel arguments */
     }
-    cudaStream_t st = convert_stream(c);
     const int r = jmc_launch_job(c->ctx, &j, st);
     bool ok = r == JMC_OK;
     bool need_sync = false;
-    for (int i = 0; i < k && ok; i++) {
-        ring_slot &s = c->ring[slots[i]];
-        ok = cudaEventRecord(s.converted, st) == cudaSuccess;
-        if (ok && c->staged) ok = prefetch_slot(c, s);
-        need_sync = need_sync || surf[i].sync_consume;
-    }
+    for (int i = 0; i < k; i++) need_sync = need_sync || surf[i].sync_consume;
+    if (ok && need_sync) ok = cudaEventRecord(c->ring[slots[k - 1]].converted, st) == cudaSuccess;
+    for (int i = 0; i < k && ok; i++)
+        if (c->staged) ok = prefetch_slot(c, c->ring[slots[i]]);         /* delivery starts right behind the kernel, same lane */
     if (cuvid) {
         unmap_batch b;
         b.done = get_event(c);
@@ -882,8 +995,9 @@ void free_everything(nvdec_b200 *c)
     c->pool_bytes = c->stage_bytes = 0;
     for (cudaEvent_t e : c->free_events) cudaEventDestroy(e);
     c->free_events.clear();
-    for (auto &r : c->regs) cudaHostUnregister(r.base);
+    for (auto &r : c->regs) if (cudaHostUnregister(r.base) != cudaSuccess) cudaGetLastError();
     c->regs.clear();
+    if (c->h_edge) { cudaFreeHost(c->h_edge); c->h_edge = nullptr; }
     c->pending.clear();
 }
 
@@ -910,8 +1024,11 @@ handle_nvdec jm_nvdec_create_handle(void)
     nvdec_b200 *c = new (std::nothrow) nvdec_b200();                   /* new + memset, nv_dec.cpp:54-60 */
     if (!c) return nullptr;
     c->device = env_int("JMC_DEVICE", 0, 0, 1023);
-    c->delay = env_int("JMC_NVDEC_DISPLAY_DELAY", 0, 0, RING_MAX - MAP_LIMIT_MAX - 2);
-    c->copy_threads = env_int("JMC_NVDEC_COPY_THREADS", 0, 0, COPY_THREADS_MAX);
+    c->delay = env_int("JMC_NVDEC_DISPLAY_DELAY", 0, 0, DELAY_MAX);
+    /* helper threads for copies from / to PAGEABLE caller buffers (started only when such a copy happens):
+     * a quarter of the host's cores, at most 4, unless JMC_NVDEC_COPY_THREADS / option "copy_threads" says otherwise */
+    const int hw = (int)std::thread::hardware_concurrency();
+    c->copy_threads = env_int("JMC_NVDEC_COPY_THREADS", hw / 4 > 4 ? 4 : hw / 4, 0, COPY_THREADS_MAX);
     c->lazy_pin = env_int("JMC_NVDEC_LAZY_PIN", 0, 0, 1);
     c->map_limit = env_int("JMC_NVDEC_MAP_LIMIT", MAP_LIMIT_MAX, 1, MAP_LIMIT_MAX);
     return c;
@@ -928,7 +1045,7 @@ int jm_nvdec_set_device(int device, handle_nvdec handle)
 int jm_nvdec_set_display_delay(int frames, handle_nvdec handle)
 {
     nvdec_b200 *c = (nvdec_b200 *)handle;
-    if (!c || frames < 0 || frames > RING_MAX - MAP_LIMIT_MAX - 2) return -1;
+    if (!c || frames < 0 || frames > DELAY_MAX) return -1;
     c->delay = frames;
     return 0;
 }
@@ -941,9 +1058,8 @@ int jm_nvdec_set_option(const char *name, int value, handle_nvdec handle)
     if (!strcmp(name, "lazy_pin")) { c->lazy_pin = value != 0; return 0; }
     if (!strcmp(name, "copy_threads")) {
         if (value < 0 || value > COPY_THREADS_MAX) return -1;
-        if (value < (int)c->copier.workers.size()) { c->copier.shutdown(); c->copier.stop = false; }
-        c->copy_threads = value;
-        if (c->inited) c->copier.start(value);
+        if (value < (int)c->copier.workers.size()) c->copier.shutdown();
+        c->copy_threads = c->copier.want_threads = value;
         return 0;
     }
     if (!strcmp(name, "map_limit")) {                                    /* takes effect when the next decoder is created */
@@ -969,7 +1085,7 @@ int jm_nvdec_init(int codec_type, int out_fmt, char *extra_data, int len, handle
     if (r == JMC_ERR_NO_DEVICE) return jmc_device_count() <= 0 ? -2 : -3;   /* nvdec_cuda_init, nv_dec.cpp:219-231 */
     if (r) return -1;
     c->inited = true;
-    c->copier.start(c->copy_threads);
+    c->copier.want_threads = c->copy_threads;                /* started on the first large copy from / to pageable memory */
     if (codec_type != JM_NVDEC_CODEC_RAW_NV12) {
         /* bitstream codecs: NVDEC parser + decoder (nvdec_create_parser, nv_dec.cpp:278-366) */
         jmc_device_guard g(c->ctx);
@@ -1043,14 +1159,34 @@ int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec han
     if (*out_len < need) return -2;                            /* :773-774 */
     *out_len = 0;                                              /* :776 */
     if (s.total > 0) {
-        int kind = host_kind_of(out_buf, s.total);
-        if (kind == MEM_PAGEABLE && maybe_lazy_pin(c, out_buf, (size_t)need, &c->cand_out)) kind = MEM_PINNED;
-        if (kind != MEM_PAGEABLE) {
+        const int kind = host_kind_of(out_buf, s.total);
+        uint8_t *blo = nullptr, *bhi = nullptr;
+        bool split = false;
+        if (kind == MEM_PAGEABLE) {
+            split = registered_interior(c, out_buf, s.total, &blo, &bhi);
+            if (!split && maybe_lazy_pin(c, out_buf, (size_t)need)) split = registered_interior(c, out_buf, s.total, &blo, &bhi);
+            if (split && !ensure_edges(c)) split = false;
+        }
+        if (split) {
+            /* malloc'ed out_buf whose interior pages are registered: the body arrives by direct DMA, the two < 4 KB
+             * edges through the pinned bounce buffer */
+            c->staged = false;
+            const size_t head = (size_t)(blo - out_buf), body = (size_t)(bhi - blo), tail = s.total - head - body;
+            cudaStream_t ds = lane_stream(c, s.lane);                     /* behind the frame's kernel, no event needed */
+            cudaError_t er = cudaSuccess;
+            if (head) er = cudaMemcpyAsync(c->h_edge, s.d_tight, head, cudaMemcpyDeviceToHost, ds);
+            if (er == cudaSuccess) er = cudaMemcpyAsync(blo, s.d_tight + head, body, cudaMemcpyDeviceToHost, ds);
+            if (er == cudaSuccess && tail) er = cudaMemcpyAsync(c->h_edge + 4096, s.d_tight + head + body, tail, cudaMemcpyDeviceToHost, ds);
+            if (er == cudaSuccess) er = cudaEventRecord(s.direct, ds);
+            if (er == cudaSuccess) er = cudaEventSynchronize(s.direct);
+            if (er != cudaSuccess) { cudaGetLastError(); return -1; }
+            if (head) memcpy(out_buf, c->h_edge, head);
+            if (tail) memcpy(bhi, c->h_edge + 4096, tail);
+        } else if (kind != MEM_PAGEABLE) {
             /* pinned / registered out_buf: only the tight frame crosses PCIe, by DMA straight into the caller's
              * buffer (a device out_buf gets a device-to-device copy: the frame never leaves HBM) */
             c->staged = false;
-            cudaStream_t ds = delivery_stream(c);
-            if (cudaStreamWaitEvent(ds, s.converted, 0) != cudaSuccess) return -1;
+            cudaStream_t ds = lane_stream(c, s.lane);                     /* behind the frame's kernel, no event needed */
             if (cudaMemcpyAsync(out_buf, s.d_tight, s.total, kind == MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ds) != cudaSuccess) { cudaGetLastError(); return -1; }
             if (cudaEventRecord(s.direct, ds) != cudaSuccess || cudaEventSynchronize(s.direct) != cudaSuccess) { cudaGetLastError(); return -1; }
         } else {
@@ -1058,12 +1194,20 @@ int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec han
              * ring; copy chunk i out while chunk i+1 is still in flight */
             c->staged = true;
             if (!prefetch_slot(c, s)) return -1;
-            for (int i = 0; i < s.n_chunks; i++) {
-                if (cudaEventSynchronize(s.delivered[i]) != cudaSuccess) { cudaGetLastError(); return -1; }
-                const size_t off = (size_t)i * s.chunk_bytes;
-                const size_t n = s.total - off < s.chunk_bytes ? s.total - off : s.chunk_bytes;
-                c->copier.copy_flat(out_buf + off, s.h_tight + off, n);
+            const size_t unit = 4096, rows = s.total / unit;
+            bool failed = false;
+            auto wait_chunk = [&](int i) { if (cudaEventSynchronize(s.delivered[i]) != cudaSuccess) { cudaGetLastError(); failed = true; } };
+            if (rows) {
+                copy_job cj = { out_buf, unit, s.h_tight, unit, unit, rows, s.chunk_bytes / unit, s.n_chunks };
+                c->copier.run(cj, wait_chunk);
+            } else {
+                wait_chunk(0);
             }
+            if (s.total % unit) {
+                wait_chunk(s.n_chunks - 1);
+                memcpy(out_buf + rows * unit, s.h_tight + rows * unit, s.total % unit);
+            }
+            if (failed) return -1;
         }
     }
     *out_len = need;                                           /* :824 */
@@ -1138,6 +1282,8 @@ int jm_nvdec_memory_register_host(void *buf, int buf_len, handle_nvdec handle)
     jmc_device_guard guard(c->ctx);
     if (guard.err) return -1;
     if (is_device_accessible_host(buf, (size_t)buf_len)) return 0;
+    uint8_t *lo, *hi;
+    if (registered_interior(c, buf, (size_t)buf_len, &lo, &hi)) return 0;
     return register_range(c, buf, (size_t)buf_len) ? 0 : -1;
 }
 
@@ -1149,12 +1295,10 @@ int jm_nvdec_memory_unregister_host(void *buf, handle_nvdec handle)
     if (guard.err) return -1;
     for (size_t i = 0; i < c->regs.size(); i++) {
         const uintptr_t lo = (uintptr_t)c->regs[i].base, hi = lo + c->regs[i].len;
-        if ((uintptr_t)buf >= lo && (uintptr_t)buf < hi) {
+        if ((uintptr_t)buf + 4096 > lo && (uintptr_t)buf < hi) {          /* buf starts at most one page before its registered interior */
             jmc_ctx_sync(c->ctx);
-            cudaHostUnregister(c->regs[i].base);
+            if (cudaHostUnregister(c->regs[i].base) != cudaSuccess) cudaGetLastError();
             c->regs.erase(c->regs.begin() + (long)i);
-            if (c->cand_out == buf) c->cand_out = nullptr;
-            if (c->cand_in == buf) c->cand_in = nullptr;
             return 0;
         }
     }

@@ -23,6 +23,7 @@ void jmc_set_error(const char *fmt, ...)
 int jmc_cuda_fail(cudaError_t e, const char *what)
 {
     jmc_set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+    cudaGetLastError();             /* reported: do not let it surface again at the next launch's error check */
     return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInvalidDevice) ? JMC_ERR_NO_DEVICE
          : (e == cudaErrorMemoryAllocation) ? JMC_ERR_NOMEM : JMC_ERR_CUDA;
 }

@@ -221,11 +221,11 @@ def test_batch_drain_of_a_64_frame_stream(fake_env, map_limit, per_packet):
 
 
 def test_many_pictures_in_one_packet_overflow_is_reported(fake_env):
-    """More pictures in ONE packet than the handle can hold (32 converted frames): the surplus is dropped, the
+    """More pictures in ONE packet than the handle can hold (64 converted frames): the surplus is dropped, the
     call returns -1 (the reference would have let the decoder overwrite queued surfaces silently), and every
     frame that does come out is a correct picture of the stream, in order."""
     import jmcodec_b200 as J
-    w, h, n = 64, 36, 60
+    w, h, n = 64, 36, 110
     need = w * h * 3 // 2
     frames = _frames(w, h, n, stream=35)
     chk = oracle.best()

@@ -33,27 +33,31 @@ struct Variant {
 };
 
 static const Variant VARIANTS[] = {
-    /* the reference's calling convention: pageable packet in, pageable frame out */
-    { "host_packet_pageable_out_fps", false, "pageable", 0, 0, 1 },
-    { "host_packet_pageable_out_delay2_fps", false, "pageable", 2, 0, 1 },
-    { "host_packet_pageable_out_delay2_threads4_fps", false, "pageable", 2, 4, 1 },
-    { "host_packet_lazy_pin_fps", false, "lazy", 0, 0, 1 },
-    { "host_packet_lazy_pin_delay2_fps", false, "lazy", 2, 0, 1 },
+    /* the reference's calling convention: pageable packet in, pageable frame out.  threads -1 = the library's
+     * default (min(4, cores/4) copy helper threads, started on the first pageable copy) */
+    { "host_packet_pageable_out_fps", false, "pageable", 0, -1, 1 },
+    { "host_packet_pageable_out_1thread_fps", false, "pageable", 0, 0, 1 },
+    { "host_packet_pageable_out_delay2_fps", false, "pageable", 2, -1, 1 },
+    { "host_packet_pageable_out_delay2_1thread_fps", false, "pageable", 2, 0, 1 },
+    { "host_packet_lazy_pin_fps", false, "lazy", 0, -1, 1 },
+    { "host_packet_lazy_pin_delay2_fps", false, "lazy", 2, -1, 1 },
     /* behind NVDEC: device-resident surface in */
-    { "device_surface_pageable_out_fps", true, "pageable", 0, 0, 1 },
-    { "device_surface_pageable_out_threads4_fps", true, "pageable", 0, 4, 1 },
-    { "device_surface_pageable_out_delay2_fps", true, "pageable", 2, 0, 1 },
-    { "device_surface_pageable_out_delay2_threads4_fps", true, "pageable", 2, 4, 1 },
-    { "device_surface_lazy_pin_fps", true, "lazy", 0, 0, 1 },
-    { "device_surface_lazy_pin_delay2_fps", true, "lazy", 2, 0, 1 },
-    { "device_surface_registered_out_fps", true, "registered", 0, 0, 1 },
-    { "device_surface_pinned_out_fps", true, "pinned", 0, 0, 1 },
-    { "device_surface_pinned_out_delay2_fps", true, "pinned", 2, 0, 1 },
-    { "device_surface_ref_delay2_fps", true, "ref", 2, 0, 1 },
-    { "device_surface_pinned_out_4_handles_fps", true, "pinned", 0, 0, 4 },
-    { "device_surface_pinned_out_delay2_4_handles_fps", true, "pinned", 2, 0, 4 },
-    { "device_surface_pageable_out_delay2_4_handles_fps", true, "pageable", 2, 0, 4 },
-    { "device_surface_ref_delay2_4_handles_fps", true, "ref", 2, 0, 4 },
+    { "device_surface_pageable_out_fps", true, "pageable", 0, -1, 1 },
+    { "device_surface_pageable_out_1thread_fps", true, "pageable", 0, 0, 1 },
+    { "device_surface_pageable_out_delay2_fps", true, "pageable", 2, -1, 1 },
+    { "device_surface_pageable_out_delay2_1thread_fps", true, "pageable", 2, 0, 1 },
+    { "device_surface_pageable_out_delay2_8threads_fps", true, "pageable", 2, 8, 1 },
+    { "device_surface_lazy_pin_fps", true, "lazy", 0, -1, 1 },
+    { "device_surface_lazy_pin_delay2_fps", true, "lazy", 2, -1, 1 },
+    { "device_surface_registered_out_fps", true, "registered", 0, -1, 1 },
+    { "device_surface_pinned_out_fps", true, "pinned", 0, -1, 1 },
+    { "device_surface_pinned_out_delay2_fps", true, "pinned", 2, -1, 1 },
+    { "device_surface_ref_fps", true, "ref", 0, -1, 1 },
+    { "device_surface_ref_delay2_fps", true, "ref", 2, -1, 1 },
+    { "device_surface_pinned_out_4_handles_fps", true, "pinned", 0, -1, 4 },
+    { "device_surface_pinned_out_delay2_4_handles_fps", true, "pinned", 2, -1, 4 },
+    { "device_surface_pageable_out_delay2_4_handles_fps", true, "pageable", 2, -1, 4 },
+    { "device_surface_ref_delay2_4_handles_fps", true, "ref", 2, -1, 4 },
 };
 
 struct Options { int device = 0, frames = 400, width = 1920, height = 1080, pitch = 2048; std::string only; };
@@ -87,7 +91,7 @@ static void run_handle(const Options &o, const Variant &v, int tid, int warm, in
     handle_nvdec dec = jm_nvdec_create_handle();
     jm_nvdec_set_device(o.device, dec);
     jm_nvdec_set_display_delay(v.delay, dec);
-    jm_nvdec_set_option("copy_threads", v.threads, dec);
+    if (v.threads >= 0) jm_nvdec_set_option("copy_threads", v.threads, dec);
     jm_nvdec_set_option("lazy_pin", !strcmp(v.out, "lazy") ? 1 : 0, dec);
     if (jm_nvdec_init(JM_NVDEC_CODEC_RAW_NV12, 1, nullptr, 0, dec) != 0) { res->error = std::string("init: ") + jmc_last_error(); return; }
 
@@ -175,7 +179,7 @@ int main(int argc, char **argv)
         std::vector<Result> res((size_t)v.handles);
         std::vector<std::thread> th;
         volatile int go = 0;
-        const int timed = v.device_in ? o.frames * 3 : o.frames;
+        const int timed = v.device_in ? o.frames * 4 : o.frames;
         for (int t = 0; t < v.handles; t++) th.emplace_back(run_handle, std::cref(o), std::cref(v), t, 20, timed, &go, &res[(size_t)t]);
         for (auto &t : th) t.join();
         long long frames = 0;
