@@ -13,10 +13,9 @@
  *                                                       tight frames; the D2H of every tight frame is enqueued at
  *                                                       once behind its kernel into a pinned ring slot (prefetch);
  *                                                       surfaces are unmapped when the launch's event has fired --
- *                                                       nothing waits per frame.  Batches alternate between two
- *                                                       streams ("lanes"): upload, kernel and delivery of a batch
- *                                                       are ordered by their stream alone (no cross-stream
- *                                                       semaphores), while the other lane's kernel overlaps them
+ *                                                       nothing waits per frame.  Deliveries run on their own
+ *                                                       stream and are enqueued only when the launch that made
+ *                                                       the frame has finished: no cross-stream semaphores
  *   output_frame: CPU strip/de-interleave (:782-820)  output_frame: waits for THAT frame's delivery events only;
  *                                                       pinned / registered out_buf: direct DMA of the tight frame;
  *                                                       pageable out_buf: chunk-pipelined copy out of the pinned ring
@@ -60,6 +59,16 @@
 #define DELAY_MAX 20
 
 namespace {
+
+/* Deliveries (device-to-host copies of tight frames) queued on the copy engine, per device, over ALL handles of the
+ * process, and the handles alive.  Measured on B200 (profiles/r2_dropin_multi_handle.txt): with more than about four
+ * delivery copies queued at once -- e.g. four handles that each keep two in flight -- single handles fall, erratically,
+ * into a state where every frame takes ~1.4 ms; with at most four queued the same handles run at the link rate,
+ * stably.  So a handle enqueues its next delivery only while fewer than DEVICE_INFLIGHT_MAX are queued on its device
+ * (or when the caller is waiting for that very frame). */
+std::atomic<int> g_dev_inflight[64];
+std::atomic<int> g_live_handles{0};
+int g_dev_inflight_max = -1;
 
 int env_int(const char *name, int dflt, int lo, int hi)
 {
@@ -196,8 +205,6 @@ struct decoded_surface {            /* what cuvidMapVideoFrame yields: device po
     int pool_slot;                  /* >= 0: one of our upload surfaces; -1: caller-owned device memory;
                                        -2: a CUVID picture still to be mapped (disp valid) */
     bool sync_consume;              /* JM_NVDEC_RAW_SYNC: do not return before the kernel has read the surface */
-    int lane;                       /* >= 0: the surface is being produced on this lane (upload of a host payload, a
-                                       caller's event awaited there) and must be converted on it; -1: any lane */
     CUVIDPARSERDISPINFO disp;       /* copied, not pointed to (the reference queues the parser's pointer, nv_dec.cpp:156) */
 };
 
@@ -205,9 +212,9 @@ struct decoded_surface {            /* what cuvidMapVideoFrame yields: device po
 struct ring_slot {
     uint8_t *d_tight = nullptr; size_t d_bytes = 0;
     uint8_t *h_tight = nullptr; size_t h_bytes = 0;
-    cudaEvent_t converted = nullptr;        /* recorded only for JM_NVDEC_RAW_SYNC packets */
+    cudaEvent_t converted = nullptr;        /* the launch that fills d_tight (recorded on the last slot of a batch) */
+    int conv_slot = -1;                     /* ring slot whose `converted` event covers this slot's launch */
     cudaEvent_t direct = nullptr;           /* a direct D2H / D2D into the caller's buffer has finished */
-    int lane = -1;                          /* the stream this slot's frame was converted on */
     cudaEvent_t delivered[MAX_CHUNKS] = {};
     int n_chunks = 0;
     size_t chunk_bytes = 0, total = 0;      /* total: the bytes the reference writes for this frame */
@@ -259,9 +266,11 @@ struct nvdec_b200 {
     /* converted frames: ring + FIFO of announced-later frames + the current output frame (nv_dec.h:119-123) */
     std::vector<ring_slot> ring;
     std::deque<int> ready;
+    std::deque<int> to_prefetch;    /* converted, delivery not enqueued yet (see flush_prefetch) */
+    std::deque<int> inflight;       /* delivery enqueued, not yet seen complete */
+    int max_inflight = 2;
     int cur = -1;
     int slot_rr = 0;
-    int lane_next = 0;              /* lane of the next batch */
     int delay = 0;                  /* frames kept back before they are announced (display delay) */
     bool staged = true;             /* prefetch tight frames into the pinned ring (pageable out_buf callers) */
     int lazy_pin = 0;               /* cudaHostRegister a pageable out_buf / in_buf seen twice (opt-in) */
@@ -293,13 +302,12 @@ struct nvdec_b200 {
     std::vector<cudaEvent_t> free_events;
 };
 
-/* Two lanes = two streams of the handle's context.  Everything that belongs to one batch of frames -- upload of a
- * host payload, the decoder's post-processing, the conversion launch, the delivery copies -- is enqueued on ONE
- * lane, so it is ordered without events; consecutive batches take alternate lanes, so a batch's kernel overlaps
- * the previous batch's delivery.  A ring slot stays with the lane that used it last (reuse is then ordered by the
- * stream too).  Measured: with cross-stream events instead (convert stream -> delivery stream and back) four
- * handles on one GPU fell from 17 k to 3-16 k frames/s, erratically (profiles/r2_dropin_lanes.txt). */
-cudaStream_t lane_stream(nvdec_b200 *c, int lane) { return (cudaStream_t)jmc_ctx_stream(c->ctx, lane ? 2 : 0); }
+/* Two streams of the handle's context: uploads of host payloads, the decoder's post-processing and the conversion
+ * launches are ordered on the CONVERT stream; every device-to-host copy runs on the DELIVERY stream and is enqueued by
+ * the CPU only when the launch that produced the frame is known to have finished (flush_prefetch) -- so the kernel of
+ * frame k+1 overlaps the delivery of frame k without a single cross-stream event wait on the device. */
+cudaStream_t convert_stream(nvdec_b200 *c) { return (cudaStream_t)jmc_ctx_stream(c->ctx, 0); }
+cudaStream_t delivery_stream(nvdec_b200 *c) { return (cudaStream_t)jmc_ctx_stream(c->ctx, 2); }
 
 const char *codec_name(int t)
 {
@@ -360,24 +368,21 @@ size_t written_bytes(int out_fmt, int w, int h)
 /* A free ring slot able to hold a w x h frame, or -1 (ring full / out of memory).  Slots are taken round-robin
  * so that a slot whose delivery may still be in flight is reused as late as possible; the convert stream waits
  * for that delivery before the slot's device frame is overwritten. */
-int acquire_slot(nvdec_b200 *c, int w, int h, int lane)
+int acquire_slot(nvdec_b200 *c, int w, int h)
 {
     size_t need = (size_t)jmc_tight_bytes(w, h);
     if (need == 0) need = 1;
-    int idx = -1, other = -1;
+    int idx = -1;
     const int n = (int)c->ring.size();
     for (int k = 0; k < n; k++) {
         const int i = (c->slot_rr + k) % n;
-        if (c->ring[i].busy) continue;
-        if (c->ring[i].lane == lane || c->ring[i].lane < 0) { idx = i; break; }
-        if (other < 0) other = i;
+        if (!c->ring[i].busy) { idx = i; break; }
     }
-    if (idx < 0 && n < RING_MAX) {
+    if (idx < 0) {
+        if (n >= RING_MAX) return -1;
         c->ring.emplace_back();
         idx = n;
     }
-    if (idx < 0) idx = other;                                 /* ring at its limit: take over a slot of the other lane */
-    if (idx < 0) return -1;
     ring_slot &s = c->ring[idx];
     if (!s.converted) {
         if (cudaEventCreateWithFlags(&s.converted, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
@@ -391,10 +396,11 @@ int acquire_slot(nvdec_b200 *c, int w, int h, int lane)
         s.d_bytes = need;
         s.prefetched = false;
     }
-    /* a slot changing lanes: its previous delivery (on the other stream) may still be reading d_tight */
-    if (s.lane >= 0 && s.lane != lane && s.prefetched && s.n_chunks > 0)
-        cudaStreamWaitEvent(lane_stream(c, lane), s.delivered[s.n_chunks - 1], 0);
-    s.lane = lane;
+    /* a frame nobody fetched: its delivery may still be reading d_tight (rare; fetched frames were waited for) */
+    if (s.prefetched && s.n_chunks > 0 && cudaEventQuery(s.delivered[s.n_chunks - 1]) != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamWaitEvent(convert_stream(c), s.delivered[s.n_chunks - 1], 0);
+    }
     s.prefetched = false;
     s.n_chunks = 0;
     s.w = w; s.h = h;
@@ -406,10 +412,15 @@ int acquire_slot(nvdec_b200 *c, int w, int h, int lane)
 
 void release_slot(nvdec_b200 *c, int idx)
 {
-    if (idx >= 0) c->ring[idx].busy = false;
+    if (idx < 0) return;
+    c->ring[idx].busy = false;
+    for (auto it = c->inflight.begin(); it != c->inflight.end(); ++it)
+        if (*it == idx) { c->inflight.erase(it); g_dev_inflight[c->device & 63].fetch_sub(1, std::memory_order_relaxed); break; }
+    for (auto it = c->to_prefetch.begin(); it != c->to_prefetch.end(); ++it)
+        if (*it == idx) { c->to_prefetch.erase(it); break; }              /* replaced before anyone fetched it */
 }
 
-/* Enqueue the D2H of a converted frame into the slot's pinned buffer on the slot's lane (behind its kernel), in chunks with an
+/* Enqueue the D2H of a converted frame (its launch has finished) into the slot's pinned buffer on the delivery stream, in chunks with an
  * event each, so that output_frame can copy chunk i out while chunk i+1 is still crossing PCIe. */
 bool prefetch_slot(nvdec_b200 *c, ring_slot &s)
 {
@@ -423,7 +434,7 @@ bool prefetch_slot(nvdec_b200 *c, ring_slot &s)
         }
         s.h_bytes = s.d_bytes;
     }
-    cudaStream_t ds = lane_stream(c, s.lane);
+    cudaStream_t ds = delivery_stream(c);
     /* no display delay: output_frame is waiting for this very frame, so pipeline its copy-out against the DMA;
      * with a delay the frame lands long before it is fetched and one copy is cheapest for the link */
     int chunks = c->delay > 0 ? 1 : (int)(s.total / (512u << 10));
@@ -439,6 +450,58 @@ bool prefetch_slot(nvdec_b200 *c, ring_slot &s)
         if (s.total == 0) break;
     }
     s.prefetched = true;
+    return true;
+}
+
+/* Deliveries are enqueued by the CPU, on the delivery stream, only once the launch that produced the frame HAS
+ * FINISHED (a non-blocking event query on the next API call; the call that wants the frame itself waits for the
+ * event) -- never parked behind an unfinished kernel -- and only while few enough are queued: max_inflight (2) per
+ * handle, DEVICE_INFLIGHT (4) per device over all handles of the process.  Both rules come from measurements
+ * (profiles/r2_dropin_multi_handle.txt): with copies queued behind kernels through cross-stream events, or with
+ * more than ~4 delivery copies queued on the device at once, four handles on one GPU ran anywhere between 3 k and
+ * 17 k frames/s from run to run -- single handles dropping to ~700 frames/s, ~1.4 ms per frame, for the rest of the
+ * run; with the two rules the same four handles deliver 16.5-16.9 k frames/s every time and one handle 17.2 k.
+ * The kernel takes ~5 us and the next call comes tens of microseconds later, so the query is almost always positive
+ * and frame k's copy runs while frame k+1 is converted.
+ * wanted >= 0: that slot's delivery must be enqueued when this returns. */
+bool flush_prefetch(nvdec_b200 *c, int wanted)
+{
+    std::atomic<int> &dev = g_dev_inflight[c->device & 63];
+    for (;;) {
+        /* forget the deliveries that have landed */
+        while (!c->inflight.empty()) {
+            ring_slot &f = c->ring[c->inflight.front()];
+            if (f.prefetched && f.n_chunks > 0 && cudaEventQuery(f.delivered[f.n_chunks - 1]) == cudaErrorNotReady) { cudaGetLastError(); break; }
+            c->inflight.pop_front();
+            dev.fetch_sub(1, std::memory_order_relaxed);
+        }
+        if (c->to_prefetch.empty()) break;
+        const int idx = c->to_prefetch.front();
+        ring_slot &s = c->ring[idx];
+        /* at most max_inflight deliveries queued per handle, DEVICE_INFLIGHT per device */
+        if ((int)c->inflight.size() >= c->max_inflight || (!c->inflight.empty() && dev.load(std::memory_order_relaxed) >= g_dev_inflight_max)) {
+            if (wanted < 0) return true;                                  /* later: the link is busy enough and nobody waits for this frame */
+            ring_slot &f = c->ring[c->inflight.front()];
+            if (cudaEventSynchronize(f.delivered[f.n_chunks - 1]) != cudaSuccess) { cudaGetLastError(); return false; }
+            c->inflight.pop_front();
+            dev.fetch_sub(1, std::memory_order_relaxed);
+        } else if (c->inflight.empty() && dev.load(std::memory_order_relaxed) >= g_dev_inflight_max && wanted < 0 && c->delay > 0) {
+            return true;                                                  /* other handles fill the link; a display delay leaves slack */
+        }
+        cudaEvent_t ev = c->ring[s.conv_slot >= 0 ? s.conv_slot : idx].converted;
+        cudaError_t q = cudaEventQuery(ev);
+        if (q == cudaErrorNotReady) {
+            cudaGetLastError();
+            if (wanted < 0) return true;                                  /* later: nobody is waiting for it yet */
+            q = cudaEventSynchronize(ev);
+        }
+        if (q != cudaSuccess) { cudaGetLastError(); return false; }
+        c->to_prefetch.pop_front();
+        if (!prefetch_slot(c, s)) return false;
+        c->inflight.push_back(idx);
+        dev.fetch_add(1, std::memory_order_relaxed);
+        if (idx == wanted) wanted = -1;
+    }
     return true;
 }
 
@@ -751,14 +814,11 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
     memset(&s, 0, sizeof(s));
     s.width = h.width; s.height = h.height; s.pitch = h.pitch;
     s.sync_consume = (h.flags & JM_NVDEC_RAW_SYNC) != 0;
-    s.lane = -1;
+    cudaStream_t st = convert_stream(c);
     if (h.flags & JM_NVDEC_RAW_DEVICE_PTR) {
         s.dptr = (uint8_t *)(uintptr_t)h.device_ptr;
         s.pool_slot = -1;
         if (h.flags & JM_NVDEC_RAW_WAIT_EVENT) {
-            s.lane = c->lane_next;
-            c->lane_next ^= 1;
-            cudaStream_t st = lane_stream(c, s.lane);
             /* the surface is being produced on another stream: order the conversion after the caller's event */
             if (len < (int)sizeof(jm_nvdec_raw_packet_ex)) return -1;
             jm_nvdec_raw_packet_ex x;
@@ -775,10 +835,7 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
         }
         const int slot = c->pool_next;
         c->pool_next = (c->pool_next + 1) % NVDEC_MAX_FRAMES;
-        /* an upload surface always works on the same lane (NVDEC_MAX_FRAMES is even): its next upload is ordered behind
-         * the kernel that read it by the stream itself */
-        s.lane = slot & 1;
-        cudaStream_t st = lane_stream(c, s.lane);
+        /* uploads and kernels share the convert stream: the next upload into this surface is ordered behind the kernel that read it */
         if (!c->pool[slot]) {
             if (cudaMalloc((void **)&c->pool[slot], c->pool_bytes ? c->pool_bytes : 1) != cudaSuccess) { cudaGetLastError(); return -1; }
         }
@@ -877,15 +934,12 @@ int convert_stage(nvdec_b200 *c, bool must_progress)
     unsigned long long mapped[MAP_LIMIT_MAX];
     int k = 0;
     int pitch = first.pitch;
-    int lane = first.lane;
-    if (lane < 0) { lane = c->lane_next; c->lane_next ^= 1; }
-    cudaStream_t st = lane_stream(c, lane);
+    cudaStream_t st = convert_stream(c);
     while (k < limit && !c->pending.empty()) {
         decoded_surface s = c->pending.front();
         if ((s.pool_slot == -2) != cuvid || s.width != first.width || s.height != first.height) break;
         if (!cuvid && s.pitch != pitch) break;
-        if (s.lane >= 0 && s.lane != lane) break;                         /* produced on the other lane: next launch */
-        const int slot = acquire_slot(c, s.width, s.height, lane);
+        const int slot = acquire_slot(c, s.width, s.height);
         if (slot < 0) break;
         mapped[k] = 0;
         if (cuvid) {
@@ -943,9 +997,11 @@ int convert_stage(nvdec_b200 *c, bool must_progress)
     bool ok = r == JMC_OK;
     bool need_sync = false;
     for (int i = 0; i < k; i++) need_sync = need_sync || surf[i].sync_consume;
-    if (ok && need_sync) ok = cudaEventRecord(c->ring[slots[k - 1]].converted, st) == cudaSuccess;
-    for (int i = 0; i < k && ok; i++)
-        if (c->staged) ok = prefetch_slot(c, c->ring[slots[i]]);         /* delivery starts right behind the kernel, same lane */
+    if (ok) ok = cudaEventRecord(c->ring[slots[k - 1]].converted, st) == cudaSuccess;
+    for (int i = 0; i < k && ok; i++) {
+        c->ring[slots[i]].conv_slot = slots[k - 1];
+        if (c->staged) c->to_prefetch.push_back(slots[i]);               /* delivery is enqueued by flush_prefetch, once the launch is done */
+    }
     if (cuvid) {
         unmap_batch b;
         b.done = get_event(c);
@@ -985,6 +1041,9 @@ void free_everything(nvdec_b200 *c)
     }
     c->ring.clear();
     c->ready.clear();
+    c->to_prefetch.clear();
+    g_dev_inflight[c->device & 63].fetch_sub((int)c->inflight.size(), std::memory_order_relaxed);
+    c->inflight.clear();
     c->cur = -1;
     for (int i = 0; i < NVDEC_MAX_FRAMES; i++) {
         if (c->pool[i]) { cudaFree(c->pool[i]); c->pool[i] = nullptr; }
@@ -1027,10 +1086,12 @@ handle_nvdec jm_nvdec_create_handle(void)
     c->delay = env_int("JMC_NVDEC_DISPLAY_DELAY", 0, 0, DELAY_MAX);
     /* helper threads for copies from / to PAGEABLE caller buffers (started only when such a copy happens):
      * a quarter of the host's cores, at most 4, unless JMC_NVDEC_COPY_THREADS / option "copy_threads" says otherwise */
-    const int hw = (int)std::thread::hardware_concurrency();
-    c->copy_threads = env_int("JMC_NVDEC_COPY_THREADS", hw / 4 > 4 ? 4 : hw / 4, 0, COPY_THREADS_MAX);
+    c->copy_threads = env_int("JMC_NVDEC_COPY_THREADS", -1, -1, COPY_THREADS_MAX);      /* -1: decided at jm_nvdec_init */
     c->lazy_pin = env_int("JMC_NVDEC_LAZY_PIN", 0, 0, 1);
     c->map_limit = env_int("JMC_NVDEC_MAP_LIMIT", MAP_LIMIT_MAX, 1, MAP_LIMIT_MAX);
+    c->max_inflight = env_int("JMC_NVDEC_MAX_INFLIGHT", 2, 1, 16);
+    if (g_dev_inflight_max < 0) g_dev_inflight_max = env_int("JMC_NVDEC_DEVICE_INFLIGHT", 4, 1, 64);
+    g_live_handles.fetch_add(1);
     return c;
 }
 
@@ -1085,7 +1146,15 @@ int jm_nvdec_init(int codec_type, int out_fmt, char *extra_data, int len, handle
     if (r == JMC_ERR_NO_DEVICE) return jmc_device_count() <= 0 ? -2 : -3;   /* nvdec_cuda_init, nv_dec.cpp:219-231 */
     if (r) return -1;
     c->inited = true;
-    c->copier.want_threads = c->copy_threads;                /* started on the first large copy from / to pageable memory */
+    /* helper threads for copies from / to PAGEABLE caller buffers, started on the first such copy: unless told
+     * otherwise a quarter of the host's cores shared by the handles alive now, at most 4 per handle */
+    if (c->copy_threads < 0) {
+        const int hw = (int)std::thread::hardware_concurrency(), live = g_live_handles.load() > 0 ? g_live_handles.load() : 1;
+        const int share = hw / (4 * live);
+        c->copier.want_threads = share > 4 ? 4 : share;
+    } else {
+        c->copier.want_threads = c->copy_threads;
+    }
     if (codec_type != JM_NVDEC_CODEC_RAW_NV12) {
         /* bitstream codecs: NVDEC parser + decoder (nvdec_create_parser, nv_dec.cpp:278-366) */
         jmc_device_guard g(c->ctx);
@@ -1101,6 +1170,7 @@ int jm_nvdec_deinit(handle_nvdec handle)
     if (!c) return -1;
     teardown(c);
     c->copier.shutdown();
+    g_live_handles.fetch_sub(1);
     delete c;
     return 0;
 }
@@ -1116,6 +1186,7 @@ int jm_nvdec_decode_frame(unsigned char *in_buf, int in_data_len, int *got_frame
     const bool cuvid = c->codec_type != JM_NVDEC_CODEC_RAW_NV12;
     c->drop_flag = false;
     if (cuvid && !c->unmaps.empty()) reap_unmaps(c, false);
+    flush_prefetch(c, -1);                                     /* deliveries of the frames converted by the previous call */
     if (!c->is_eof) {                                          /* nv_dec.cpp:486-488 */
         if (in_buf && in_data_len > 0) {
             if (!cuvid) raw_packet(c, in_buf, in_data_len);    /* malformed packet: consumed, no frame (errors swallowed like :491-493) */
@@ -1129,6 +1200,7 @@ int jm_nvdec_decode_frame(unsigned char *in_buf, int in_data_len, int *got_frame
     while (!c->pending.empty()) {
         if (convert_stage(c, false) <= 0) break;
     }
+    flush_prefetch(c, -1);                                     /* whatever has finished converting meanwhile (uploads take longer than kernels) */
     /* announce at most one frame per call (:455); frames beyond the display delay wait in `ready` */
     if (!c->ready.empty() && ((int)c->ready.size() > c->delay || c->is_eof)) {
         release_slot(c, c->cur);                               /* single current frame: fetch it before the next one is announced (nv_dec.h:119-123) */
@@ -1171,10 +1243,11 @@ int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec han
             /* malloc'ed out_buf whose interior pages are registered: the body arrives by direct DMA, the two < 4 KB
              * edges through the pinned bounce buffer */
             c->staged = false;
+            c->to_prefetch.clear();                                       /* this caller takes its frames by direct DMA */
             const size_t head = (size_t)(blo - out_buf), body = (size_t)(bhi - blo), tail = s.total - head - body;
-            cudaStream_t ds = lane_stream(c, s.lane);                     /* behind the frame's kernel, no event needed */
-            cudaError_t er = cudaSuccess;
-            if (head) er = cudaMemcpyAsync(c->h_edge, s.d_tight, head, cudaMemcpyDeviceToHost, ds);
+            cudaStream_t ds = delivery_stream(c);
+            cudaError_t er = cudaEventSynchronize(c->ring[s.conv_slot >= 0 ? s.conv_slot : c->cur].converted);   /* launch done: the copies never wait on the device */
+            if (er == cudaSuccess && head) er = cudaMemcpyAsync(c->h_edge, s.d_tight, head, cudaMemcpyDeviceToHost, ds);
             if (er == cudaSuccess) er = cudaMemcpyAsync(blo, s.d_tight + head, body, cudaMemcpyDeviceToHost, ds);
             if (er == cudaSuccess && tail) er = cudaMemcpyAsync(c->h_edge + 4096, s.d_tight + head + body, tail, cudaMemcpyDeviceToHost, ds);
             if (er == cudaSuccess) er = cudaEventRecord(s.direct, ds);
@@ -1186,14 +1259,21 @@ int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec han
             /* pinned / registered out_buf: only the tight frame crosses PCIe, by DMA straight into the caller's
              * buffer (a device out_buf gets a device-to-device copy: the frame never leaves HBM) */
             c->staged = false;
-            cudaStream_t ds = lane_stream(c, s.lane);                     /* behind the frame's kernel, no event needed */
+            c->to_prefetch.clear();                                       /* this caller takes its frames by direct DMA */
+            cudaStream_t ds = delivery_stream(c);
+            if (cudaEventSynchronize(c->ring[s.conv_slot >= 0 ? s.conv_slot : c->cur].converted) != cudaSuccess) { cudaGetLastError(); return -1; }   /* launch done: the copy never waits on the device */
             if (cudaMemcpyAsync(out_buf, s.d_tight, s.total, kind == MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ds) != cudaSuccess) { cudaGetLastError(); return -1; }
             if (cudaEventRecord(s.direct, ds) != cudaSuccess || cudaEventSynchronize(s.direct) != cudaSuccess) { cudaGetLastError(); return -1; }
         } else {
             /* pageable out_buf (what the reference's callers pass): the frame is (being) prefetched into the pinned
              * ring; copy chunk i out while chunk i+1 is still in flight */
             c->staged = true;
-            if (!prefetch_slot(c, s)) return -1;
+            if (!s.prefetched) {
+                bool queued = false;
+                for (int q : c->to_prefetch) queued = queued || q == c->cur;
+                if (!queued) c->to_prefetch.push_back(c->cur);
+                if (!flush_prefetch(c, c->cur)) return -1;
+            }
             const size_t unit = 4096, rows = s.total / unit;
             bool failed = false;
             auto wait_chunk = [&](int i) { if (cudaEventSynchronize(s.delivered[i]) != cudaSuccess) { cudaGetLastError(); failed = true; } };
@@ -1208,6 +1288,7 @@ int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec han
                 memcpy(out_buf + rows * unit, s.h_tight + rows * unit, s.total % unit);
             }
             if (failed) return -1;
+            flush_prefetch(c, -1);                             /* this frame's delivery is done: let the next one start */
         }
     }
     *out_len = need;                                           /* :824 */
@@ -1222,7 +1303,12 @@ int jm_nvdec_output_frame_ref(const unsigned char **frame, int *frame_len, handl
     if (guard.err) return -1;
     ring_slot &s = c->ring[c->cur];
     c->staged = true;
-    if (!prefetch_slot(c, s)) return -1;
+    if (!s.prefetched) {
+        bool queued = false;
+        for (int q : c->to_prefetch) queued = queued || q == c->cur;
+        if (!queued) c->to_prefetch.push_back(c->cur);
+        if (!flush_prefetch(c, c->cur)) return -1;
+    }
     for (int i = 0; i < s.n_chunks; i++)
         if (cudaEventSynchronize(s.delivered[i]) != cudaSuccess) { cudaGetLastError(); return -1; }
     *frame = s.h_tight;

@@ -60,7 +60,7 @@ static const Variant VARIANTS[] = {
     { "device_surface_ref_delay2_4_handles_fps", true, "ref", 2, -1, 4 },
 };
 
-struct Options { int device = 0, frames = 400, width = 1920, height = 1080, pitch = 2048; std::string only; };
+struct Options { int device = 0, frames = 400, width = 1920, height = 1080, pitch = 2048; std::string only, custom; bool verbose = false; };
 
 static void fill(unsigned char *p, size_t n, unsigned seed)
 {
@@ -171,10 +171,22 @@ int main(int argc, char **argv)
         else if (a == "--height") o.height = atoi(val());
         else if (a == "--pitch") o.pitch = atoi(val());
         else if (a == "--only") o.only = val();
+        else if (a == "--custom") o.custom = val();        /* in,out,delay,threads,handles  e.g. device,ref,2,-1,4 */
+        else if (a == "--verbose") o.verbose = true;
+    }
+    std::vector<Variant> variants(VARIANTS, VARIANTS + sizeof(VARIANTS) / sizeof(VARIANTS[0]));
+    static char c_in[32], c_out[32], c_name[128];
+    if (!o.custom.empty()) {
+        int d = 0, t = -1, hn = 1;
+        if (sscanf(o.custom.c_str(), "%31[^,],%31[^,],%d,%d,%d", c_in, c_out, &d, &t, &hn) != 5) { fprintf(stderr, "bad --custom\n"); return 2; }
+        snprintf(c_name, sizeof(c_name), "custom_%s_%s_delay%d_threads%d_handles%d", c_in, c_out, d, t, hn);
+        variants.clear();
+        variants.push_back(Variant{ c_name, !strcmp(c_in, "device"), c_out, d, t, hn });
+        o.only.clear();
     }
     printf("{");
     bool first = true;
-    for (const Variant &v : VARIANTS) {
+    for (const Variant &v : variants) {
         if (!o.only.empty() && o.only != v.name) continue;
         std::vector<Result> res((size_t)v.handles);
         std::vector<std::thread> th;
@@ -185,7 +197,10 @@ int main(int argc, char **argv)
         long long frames = 0;
         double secs = 0;
         std::string err;
-        for (auto &r : res) { frames += r.frames; if (r.seconds > secs) secs = r.seconds; if (!r.error.empty()) err = r.error; }
+        for (auto &r : res) {
+            frames += r.frames; if (r.seconds > secs) secs = r.seconds; if (!r.error.empty()) err = r.error;
+            if (o.verbose) fprintf(stderr, "%s: handle %ld: %lld frames in %.4f s = %.0f fps\n", v.name, (long)(&r - &res[0]), r.frames, r.seconds, r.seconds > 0 ? r.frames / r.seconds : 0.0);
+        }
         printf("%s\"%s\": ", first ? "" : ", ", v.name);
         if (!err.empty()) printf("\"error: %s\"", err.c_str());
         else printf("%.1f", secs > 0 ? (double)frames / secs : 0.0);
