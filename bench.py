@@ -63,15 +63,46 @@ def peaks():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+KERNEL_SOURCES = ("jmc_k_common.cuh", "jmc_k_planes.cuh", "jmc_k_rows.cuh", "jmc_k_rgb.cuh", "jmc_kernels.cu")
+
+
+def kernel_sources_sha256():
+    """Hash of the kernel sources + launch logic: ties a recorded ncu DRAM-traffic figure to the code it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "jmcodec_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def recorded_traffic(workload):
-    """dram bytes per launch from the committed ncu --set full capture, or None."""
+    """(dram bytes per launch, provenance dict) from the committed ncu --set full capture (profiles/traffic.json, written by
+    tools/record_traffic.py).  A figure captured from other kernel sources than the ones in this tree is STALE: it is
+    reported as null, with the reason."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get(workload)
-        except Exception:
-            return None
-    return None
+    try:
+        e = json.load(open(p)).get(workload)
+    except Exception:
+        e = None
+    if not isinstance(e, dict):
+        return None, {"status": "no ncu capture recorded for this workload"}
+    prov = {k: e.get(k) for k in ("kernel", "capture", "git", "when", "sources_sha256")}
+    if e.get("sources_sha256") != kernel_sources_sha256():
+        prov["status"] = "stale: kernel sources changed since the capture"
+        return None, prov
+    prov["status"] = "current"
+    return e.get("traffic"), prov
+
+
+def run_config(name, n_gpus):
+    """The `config` object, identical in both arms (b200 / reference) for the same command line."""
+    op, w, h, pitch, n = WORKLOADS[name]
+    in_b, out_b, out2_b = io_bytes(op, w, h, pitch)
+    return {"workload": name, "width": w, "height": h, "pitch": pitch, "frames_per_step_per_gpu": n,
+            "distinct_surfaces": N_DISTINCT,
+            "l2": f"batch {in_b * n / 1e6:.0f} MB in + {(out_b + out2_b) * n / 1e6:.0f} MB out per step > 126 MB L2 / host LLC, no flush needed",
+            "parallelism": f"frames sharded over {n_gpus} GPU(s), no collective"}
 
 
 def dist_env():
@@ -231,7 +262,7 @@ def run_reference_arm(args, name):
         "impl": "reference", "metric": "NV12->I420 frames/s", "value": fps, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": name, "width": w, "height": h, "pitch": pitch, "frames_per_step": n},
+        "config": run_config(name, args.gpus),
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": chk.kind,
                          "sample": f"{args.steps} steps x {n} frames, jm_nvdec_output_frame out_fmt=1, one handle per thread, "
                                    f"{N_DISTINCT} distinct surfaces"},
@@ -472,8 +503,25 @@ def main():
         decode_path = {"value": dp_units / (dp_ms_max * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": 0,
                        "d2h_bytes_per_step": int((pipe.d2h_bytes - d1) // args.steps), "ms_per_step": dp_ms_max / args.steps,
                        "note": "surfaces resident in HBM as after NVDEC; kernel + pinned D2H of the tight frames only"}
-    sampler.stop()
     pipe.close()
+    # ---- the host link's ceiling, measured NOW on every rank at once (barrier-synchronised): both directions
+    #      concurrently (what e2e does) and D2H alone (what the device-resident flow does); whole-job = sum over ranks
+    ceiling = None
+    try:
+        barrier()
+        up, down = ctx.link_probe(256 << 20, 6, 3)
+        barrier()
+        _, down_only = ctx.link_probe(256 << 20, 6, 2)
+        barrier()
+        sums = []
+        for v in (up, down, down_only):
+            tot, _ = aggregate(int(v * 1e6), 1.0, dev)
+            sums.append(tot / 1e6)
+        ceiling = {"bidirectional_h2d_gbs": sums[0], "bidirectional_d2h_gbs": sums[1], "d2h_only_gbs": sums[2],
+                   "how": "jmc_link_probe: 6 x 256 MiB pinned copies per direction on every rank at once, between barriers, device-timed"}
+    except Exception as e:      # noqa: BLE001
+        ceiling = {"error": repr(e)}
+    sampler.stop()
 
     # ---- extras on rank 0, N=1: per-kernel device table + CPU baseline ------------------------------
     kernels, cpu, batch_sweep, dropin = None, None, None, None
@@ -510,7 +558,9 @@ def main():
             for k in list(WORKLOADS):
                 r = device_only(ctx, k, rank, 10, 3)
                 kernels[k] = {"frames_per_s": round(r["frames_per_s"], 1), "gbs": round(r["gbs"], 1),
-                              "frac_of_peak": round(r["gbs"] / peak, 4), "ms_per_launch": round(r["ms_per_launch"], 4)}
+                              "frac_of_peak": round(r["gbs"] / peak, 4), "ms_per_launch": round(r["ms_per_launch"], 4),
+                              # the reference has no RGB code: those oracles are builder-defined
+                              "parity": "unpinned" if WORKLOADS[k][0] in ("rgb", "fused", "argb", "rgb2nv12") else "pinned"}
         except Exception as e:          # noqa: BLE001
             extras_errors.append("kernels: " + repr(e))
         try:
@@ -529,24 +579,40 @@ def main():
             extras_errors.append("dropin_api: " + repr(e))
 
     if rank == 0:
+        traffic, traffic_prov = recorded_traffic(name)
+        step_s = e2e_ms_max / args.steps * 1e-3
+        # whole-job bytes per second each way (h2d_step / d2h_step are this rank's bytes per step; ranks are identical)
+        gbs_up, gbs_down = h2d_step * world / step_s / 1e9, d2h_step * world / step_s / 1e9
+        e2e_obj = {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
+                   "ms_per_step": e2e_ms_max / args.steps, "frames_per_pipeline_batch": sub, "pipeline_depth": args.e2e_depth,
+                   "pcie_gbs_each_way_whole_job": [gbs_up, gbs_down]}
+        if ceiling and "error" not in ceiling:
+            lim = min(ceiling["bidirectional_h2d_gbs"], ceiling["bidirectional_d2h_gbs"])
+            e2e_obj["host_ceiling_gbs"] = lim
+            e2e_obj["frac_of_host_ceiling"] = max(gbs_up, gbs_down) / lim if lim > 0 else None
+            e2e_obj["host_ceiling"] = ceiling
+            if decode_path:
+                decode_path["host_ceiling_gbs"] = ceiling["d2h_only_gbs"]
+                dp_gbs = decode_path["d2h_bytes_per_step"] * world / (decode_path["ms_per_step"] * 1e-3) / 1e9
+                decode_path["frac_of_host_ceiling"] = dp_gbs / ceiling["d2h_only_gbs"] if ceiling["d2h_only_gbs"] > 0 else None
+        elif ceiling:
+            e2e_obj["host_ceiling"] = ceiling
         line = {
             "metric": "NV12->I420 frames/s" if op == "i420" else f"{name} frames/s",
             "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": name, "width": w, "height": h, "pitch": pitch, "frames_per_step_per_gpu": n,
-                       "launches_per_step": 1, "l2": f"batch {in_b * n / 1e6:.0f} MB in + {out_b * n / 1e6:.0f} MB out per step > 126 MB L2, no flush needed",
-                       "parallelism": f"frames sharded over {world} GPU(s), no collective"},
+            "config": run_config(name, world),
+            "launches_per_step": 1,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": recorded_traffic(name), "peak_source": peak_src,
+                         "traffic": traffic, "traffic_provenance": traffic_prov, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_launch},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
-                    "ms_per_step": e2e_ms_max / args.steps, "frames_per_pipeline_batch": sub, "pipeline_depth": args.e2e_depth,
-                    "pcie_gbs_each_way": [h2d_step / (e2e_ms_max / args.steps * 1e-3) / 1e9, d2h_step / (e2e_ms_max / args.steps * 1e-3) / 1e9]},
+            "e2e": e2e_obj,
             "e2e_device_resident_input": decode_path,
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "verified_bit_exact": verified,
+            "parity": "unpinned" if op in ("rgb", "fused", "argb", "rgb2nv12") else "pinned",
         }
         if cpu:
             line["cpu_baseline"] = cpu

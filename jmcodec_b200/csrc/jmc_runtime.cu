@@ -364,6 +364,49 @@ int jmc_convert_timed(jmc_ctx *c, const jmc_job *job, int iters, float *ms_per_l
     return JMC_OK;
 }
 
+/* ---- host link probe ------------------------------------------------------------------------- */
+int jmc_link_probe(jmc_ctx *c, size_t bytes_per_copy, int copies, int mode, jmc_link_rates *out)
+{
+    JMC_BIND(c);
+    if (!out || bytes_per_copy == 0 || copies < 1 || mode < 1 || mode > 3) { jmc_set_error("jmc_link_probe: bad arguments"); return JMC_ERR_INVALID; }
+    out->h2d_gbs = out->d2h_gbs = 0.0;
+    void *h_up = nullptr, *h_down = nullptr, *d_up = nullptr, *d_down = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaError_t e = cudaSuccess;
+    if (mode & 1) { e = cudaHostAlloc(&h_up, bytes_per_copy, cudaHostAllocDefault); if (e == cudaSuccess) e = cudaMalloc(&d_up, bytes_per_copy); }
+    if (e == cudaSuccess && (mode & 2)) { e = cudaHostAlloc(&h_down, bytes_per_copy, cudaHostAllocDefault); if (e == cudaSuccess) e = cudaMalloc(&d_down, bytes_per_copy); }
+    for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
+    if (e == cudaSuccess && h_up) memset(h_up, 0x5A, bytes_per_copy);
+    if (e == cudaSuccess && d_down) e = cudaMemset(d_down, 0xA5, bytes_per_copy);
+    /* one warm-up copy each way, then `copies` timed ones; the two directions run on the upload and the delivery stream */
+    for (int rep = 0; rep < 2 && e == cudaSuccess; rep++) {
+        const int n = rep == 0 ? 1 : copies;
+        if (mode & 1) e = cudaEventRecord(ev[0], c->stream[1]);
+        if (e == cudaSuccess && (mode & 2)) e = cudaEventRecord(ev[2], c->stream[2]);
+        for (int i = 0; i < n && e == cudaSuccess; i++) {
+            if (mode & 1) e = cudaMemcpyAsync(d_up, h_up, bytes_per_copy, cudaMemcpyHostToDevice, c->stream[1]);
+            if (e == cudaSuccess && (mode & 2)) e = cudaMemcpyAsync(h_down, d_down, bytes_per_copy, cudaMemcpyDeviceToHost, c->stream[2]);
+        }
+        if (e == cudaSuccess && (mode & 1)) e = cudaEventRecord(ev[1], c->stream[1]);
+        if (e == cudaSuccess && (mode & 2)) e = cudaEventRecord(ev[3], c->stream[2]);
+        if (e == cudaSuccess && (mode & 1)) e = cudaEventSynchronize(ev[1]);
+        if (e == cudaSuccess && (mode & 2)) e = cudaEventSynchronize(ev[3]);
+    }
+    if (e == cudaSuccess) {
+        float ms = 0.f;
+        const double total = (double)bytes_per_copy * copies;
+        if (mode & 1) { e = cudaEventElapsedTime(&ms, ev[0], ev[1]); if (e == cudaSuccess && ms > 0) out->h2d_gbs = total / (ms * 1e-3) / 1e9; }
+        if (e == cudaSuccess && (mode & 2)) { e = cudaEventElapsedTime(&ms, ev[2], ev[3]); if (e == cudaSuccess && ms > 0) out->d2h_gbs = total / (ms * 1e-3) / 1e9; }
+    }
+    for (int i = 0; i < 4; i++) if (ev[i]) cudaEventDestroy(ev[i]);
+    if (h_up) cudaFreeHost(h_up);
+    if (h_down) cudaFreeHost(h_down);
+    if (d_up) cudaFree(d_up);
+    if (d_down) cudaFree(d_down);
+    if (e != cudaSuccess) return jmc_cuda_fail(e, "jmc_link_probe");
+    return JMC_OK;
+}
+
 /* ---- events ---------------------------------------------------------------------------------- */
 int jmc_event_create(jmc_ctx *c, jmc_event **out)
 {

@@ -109,6 +109,7 @@ _SIGS = {
     "jmc_job_algorithmic_bytes": (C.c_int64, [C.POINTER(Job)]),
     "jmc_convert": (C.c_int, [C.c_void_p, C.POINTER(Job), C.c_void_p]),
     "jmc_convert_timed": (C.c_int, [C.c_void_p, C.POINTER(Job), C.c_int, C.POINTER(C.c_float)]),
+    "jmc_link_probe": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double * 2)]),
     "jmc_event_create": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "jmc_event_destroy": (C.c_int, [C.c_void_p, C.c_void_p]),
     "jmc_event_record": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
@@ -331,6 +332,12 @@ class Ctx:
         j = Job()
         _ck(self.L.jmc_job_rgb_to_nv12(C.byref(j), w, h, rgb_pitch, stride), "jmc_job_rgb_to_nv12")
         return j
+
+    def link_probe(self, bytes_per_copy: int, copies: int, mode: int):
+        """(h2d GB/s, d2h GB/s) of the PCIe link right now; mode 1 = H2D, 2 = D2H, 3 = both at once."""
+        r = (C.c_double * 2)()
+        _ck(self.L.jmc_link_probe(self.h, bytes_per_copy, copies, mode, C.byref(r)), "jmc_link_probe")
+        return r[0], r[1]
 
     def algorithmic_bytes(self, job: Job) -> int:
         return int(self.L.jmc_job_algorithmic_bytes(C.byref(job)))
