@@ -44,7 +44,7 @@ private:
 /* The JMC_* environment switches (kernel-variant A/B, pipeline upload shape), read ONCE per process --
  * not per launch -- and again only when jmc_reload_env() is called (tests flip them in-process). */
 struct jmc_env_flags {
-    bool no_bulk, no_rows, rows_single, rows_always, rgb_bulk_always, pipeline_h2d_2d, no_tensor_map;
+    bool no_bulk, no_rows, rows_single, rows_always, rgb_bulk_always, pipeline_h2d_2d;
     int rgb_flat;             /* -1 unset (heuristic), 0 off, 1 on */
     int rgb2_flat;            /* same, for the RGB24 -> NV12 kernel */
 };

@@ -121,7 +121,6 @@ static void env_load()
     f.rows_single = env_on("JMC_ROWS_SINGLE");
     f.rows_always = env_on("JMC_ROWS_ALWAYS");
     f.rgb_bulk_always = env_on("JMC_RGB_BULK_ALWAYS");
-    f.no_tensor_map = env_on("JMC_NO_TENSOR_MAP");
     f.pipeline_h2d_2d = env_tri("JMC_PIPELINE_H2D_2D") != 0;
     f.rgb_flat = env_tri("JMC_RGB_FLAT");
     f.rgb2_flat = env_tri("JMC_RGB2_FLAT");

@@ -418,3 +418,33 @@ def test_any_alignment_kernel_still_matches(ctx, c, monkeypatch):
     monkeypatch.setenv("JMC_NO_ROWS", "1")
     out = G.run_case_gpu(ctx, c)
     assert K.sha(out) == GOLD[K.case_id(c)]["sha256"]
+
+
+@pytest.mark.parametrize("geom", [(854, 480, 1024), (1366, 768, 1536), (1080, 1920, 1088), (427, 241, 512), (2562, 38, 2688), (255, 17, 256), (257, 16, 272)])
+def test_pack_batches_of_odd_widths(ctx, geom):
+    """Encode direction, widths that are not multiples of 16, several frames per launch in stride mode, tight frames at
+    aligned and skewed addresses: intel_enc.cpp:291-307,366-380 / nv_enc.cpp:1029-1081 reproduced, padding left alone."""
+    w, h, pitch = geom
+    n = 5
+    tight_bytes = w * h * 3 // 2
+    tstride = (tight_bytes + 15 + 48) & ~15                 # frames a multiple of 16 bytes apart, with slack between them
+    nsurf = pitch * (h * 3 // 2 + 1)
+    for code in (0x1, 0x10):
+        for skew in (0, 5):
+            frames = [synth.i420_frame(w, h, 25, f * 7 + w) for f in range(n)]
+            hin = np.full(n * tstride + 64, 0x77, np.uint8)
+            for f in range(n):
+                hin[skew + f * tstride: skew + f * tstride + tight_bytes] = frames[f]
+            dt = ctx.upload(hin)
+            ds = ctx.alloc(n * nsurf)
+            ctx.memset(ds, synth.PAD_BYTE, n * nsurf)
+            j = ctx.job_nvenc(w, h, pitch, code)
+            j.n_frames, j.surf.base, j.surf.stride, j.tight.base, j.tight.stride = n, ds, nsurf, dt + skew, tstride
+            ctx.convert(j)
+            got = np.empty(n * nsurf, np.uint8)
+            ctx.d2h(got, ds)
+            for f in range(n):
+                want = np.full(nsurf, synth.PAD_BYTE, np.uint8)
+                oracle.nvenc_upload(frames[f], code, w, h, want, pitch)
+                assert np.array_equal(got[f * nsurf:(f + 1) * nsurf], want), (geom, hex(code), skew, f)
+            ctx.free(dt), ctx.free(ds)
