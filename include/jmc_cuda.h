@@ -143,6 +143,11 @@ typedef struct jmc_job {
  * they are passed to the kernel as arguments, nothing is uploaded first (how jm_nvdec_* feeds the few decoder
  * surfaces it has mapped into one launch).  Alignment is then checked on the host; ALIGNED16 is not needed. */
 #define JMC_JOB_LIST_ON_HOST 2u
+/* encode ops (tight / RGB frame -> pitched surface): the caller does not care about the surface's pitch padding -- true for
+ * encoder input surfaces, whose padding nobody reads -- so the kernel may ZERO the padding of every row up to the next
+ * 16-byte boundary instead of preserving it.  Default (flag clear): every padding byte keeps its value, as after the
+ * reference's cuMemcpy2D / row memcpy (nv_enc.cpp:1029-1040, intel_enc.cpp:291-307). */
+#define JMC_JOB_PAD_ZERO 4u
 #define JMC_INLINE_LIST_MAX 8
 
 /* Geometry fillers: set width/height/pitch and every offset exactly as the named reference

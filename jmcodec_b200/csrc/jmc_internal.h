@@ -47,6 +47,8 @@ struct jmc_env_flags {
     bool no_bulk, no_rows, rows_single, rows_always, rgb_bulk_always, pipeline_h2d_2d;
     int rgb_flat;             /* -1 unset (heuristic), 0 off, 1 on */
     int rgb2_flat;            /* same, for the RGB24 -> NV12 kernel */
+    bool pad_zero;            /* JMC_PAD_ZERO=1: as if every job carried JMC_JOB_PAD_ZERO (measurements) */
+    int brows_rows;           /* > 0: rows per tile of the bulk-loaded row kernels (tuning) */
 };
 const jmc_env_flags &jmc_env();
 

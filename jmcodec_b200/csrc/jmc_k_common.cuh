@@ -156,11 +156,34 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+/* JMC_MBAR_POLL: 0 = every thread of the CTA polls the mbarrier (round 1); 1 = the first warp polls, with the
+ * hardware suspend-time hint, and the other warps sleep in the CTA barrier.  Polling warps execute instructions:
+ * ncu counted ~1500 warp-instructions per CTA of pure try_wait / branch in the row kernels, competing for issue
+ * slots with the CTAs that have data (profiles/README.md, round 2). */
+#ifndef JMC_MBAR_POLL
+#define JMC_MBAR_POLL 1
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+#if JMC_MBAR_POLL
+    asm volatile(
+        "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680) : "memory");
+#else
     asm volatile(
         "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(smem_u32(bar)),
         "r"(parity) : "memory");
+#endif
+}
+/* the whole CTA waits for the barrier's phase: one warp observes it, the CTA barrier hands the observation on */
+__device__ __forceinline__ void mbar_wait_cta(uint64_t *bar, uint32_t parity)
+{
+#if JMC_MBAR_POLL
+    if (threadIdx.x < 32) mbar_wait(bar, parity);
+    __syncthreads();
+#else
+    mbar_wait(bar, parity);
+#endif
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar)
 {

@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(BULK_THREADS) bulk_planes_kernel(const __grid_
                 mbar_expect_tx(&bar, nr * 2 * re);
                 for (uint32_t i = 0; i < nr; i++) bulk_g2s(s_uv + (size_t)i * 2 * re, pp + (size_t)(r0 + i) * pitch, 2 * re, &bar);
             }
-            mbar_wait(&bar, 0);
+            mbar_wait_cta(&bar, 0);
             for (uint32_t v = threadIdx.x; v < nvec; v += BULK_THREADS) {
                 const uint4 a = *(const uint4 *)(s_uv + (size_t)v * 32), b = *(const uint4 *)(s_uv + (size_t)v * 32 + 16);
                 uint4 u, w;
@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(BULK_THREADS) bulk_planes_kernel(const __grid_
                 bulk_g2s(s_u, tu, nr * re, &bar);
                 bulk_g2s(s_v, tv, nr * re, &bar);
             }
-            mbar_wait(&bar, 0);
+            mbar_wait_cta(&bar, 0);
             for (uint32_t v = threadIdx.x; v < nvec; v += BULK_THREADS) {
                 const uint4 u = *(const uint4 *)(s_u + (size_t)v * 16), w = *(const uint4 *)(s_v + (size_t)v * 16);
                 uint4 a, b;

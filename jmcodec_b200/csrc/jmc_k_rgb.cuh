@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid
         bulk_g2s(s_uv, sp + p.uv_off + (size_t)cy * p.pitch + x0, lw, &bar);
     }
     __syncthreads();
-    mbar_wait(&bar, 0);
+    mbar_wait_cta(&bar, 0);
     const bool do_uv = p.fused && rp < ch;
     for (uint32_t unit = threadIdx.x; unit < (lw >> 4); unit += RGB_BULK_THREADS) {
         const uint4 uv = *(const uint4 *)(s_uv + unit * 16);
@@ -531,7 +531,18 @@ struct Rgb2Params {
     int64_t y_off, uv_off;
     uint32_t row_pairs, segs_per_row, tasks_per_frame, total_tasks;
     FastDiv tpf_div, seg_div;  /* division by tasks_per_frame / segs_per_row */
+    uint32_t pad_zero;         /* the padding behind a row may be zeroed up to the next 16-byte boundary (JMC_JOB_PAD_ZERO) */
 };
+
+/* the first n (0..16) bytes of a 16-byte lane result, zeros behind them */
+__device__ __forceinline__ void keep_prefix(uint32_t (&w)[4], uint32_t n)
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t have = n > 4u * k ? min(n - 4u * k, 4u) : 0u;
+        w[k] &= have >= 4 ? 0xffffffffu : ((1u << (8 * have)) - 1u);
+    }
+}
 
 constexpr uint32_t FWD_Y = 66u | (129u << 8) | (25u << 16);                 /* R,G,B -> Y, unsigned bytes */
 constexpr uint32_t FWD_U = 0xDAu | (0xB6u << 8) | (0x70u << 16);            /* -38, -74, 112 as signed bytes */
@@ -617,6 +628,23 @@ __global__ void __launch_bounds__(RGB2_THREADS, 8) rgb_to_nv12_kernel(const __gr
         uvw[g] = __byte_perm(__byte_perm(c[0], c[1], 0x0040), __byte_perm(c[2], c[3], 0x0040), 0x5410);
     }
     uint8_t *yrow = sp + p.y_off + (size_t)y0 * p.pitch + x0 + px0;
+    if (p.pad_zero) {
+        /* whole 16-byte chunks everywhere (the host has checked 16-byte alignment and pitch >= width rounded up to 16): a
+         * row end written as a sub-16-byte fragment makes the L2 fetch the padding's sector from DRAM to merge it, which
+         * costs 10 % of the roofline on 1366-wide frames (profiles/r2_partial_sector_probe.txt) */
+        if (npx < 16) { keep_prefix(ya, npx); keep_prefix(yb, npx); }
+        *(uint4 *)yrow = make_uint4(ya[0], ya[1], ya[2], ya[3]);
+        if (two) *(uint4 *)(yrow + p.pitch) = make_uint4(yb[0], yb[1], yb[2], yb[3]);
+        if (do_uv) {
+            const uint32_t pair0 = (x0 + px0) >> 1;
+            if (pair0 < cw) {
+                const uint32_t nuv = 2 * min(8u, cw - pair0);
+                if (nuv < 16) keep_prefix(uvw, nuv);
+                *(uint4 *)(sp + p.uv_off + (size_t)rp * p.pitch + x0 + px0) = make_uint4(uvw[0], uvw[1], uvw[2], uvw[3]);
+            }
+        }
+        return;
+    }
     store_prefix<4>(yrow, ya, npx);
     if (two) store_prefix<4>(yrow + p.pitch, yb, npx);
     if (do_uv) {

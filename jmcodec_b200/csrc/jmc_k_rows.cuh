@@ -331,6 +331,7 @@ struct BulkRowsParams {
     uint32_t tiles[2];        /* tiles per frame of part 0 / part 1 */
     uint32_t rstride[2];      /* shared-memory stride of a staged row (surface bytes; multiple of 16, of 32 for chroma pairs) */
     uint32_t ldbytes[2];      /* bytes per bulk row load: row bytes rounded up to 16 */
+    uint32_t pad_zero;        /* encode direction: the padding behind a row may be zeroed up to the next 16-byte boundary (JMC_JOB_PAD_ZERO) */
     Part part[2];
 };
 
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(BROWS_THREADS) bulk_rows_kernel(const __grid_c
         mbar_expect_tx(&bar, nr * ld);
         for (uint32_t i = 0; i < nr; i++) bulk_g2s(A + (size_t)i * rs, pp + (size_t)(r0 + i) * pitch, ld, &bar);
     }
-    mbar_wait(&bar, 0);
+    mbar_wait_cta(&bar, 0);
 
     if (!second || KIND1 == PART_COPY) {
         uint8_t *t = tp + pt.a_off + (size_t)r0 * re;
@@ -423,6 +424,70 @@ __device__ __forceinline__ uint4 staged16(const uint8_t *S, uint32_t off)
     return shift_pair(q[0], q[1], (off & 15) >> 2, 8 * (off & 3));
 }
 
+/* 16 bytes at chunk q (aligned) or at a row-uniform byte shift behind it; WS < 0: the row starts on a chunk boundary */
+template <int WS> __device__ __forceinline__ uint4 staged16_ws(const uint4 *q, uint32_t sh)
+{
+    if (WS < 0) return q[0];
+    return shift_pair_ws<(WS < 0 ? 0 : WS)>(q[0], q[1], sh);
+}
+/* word shift of a row that starts `off` bytes into the staging buffer: -1 when it starts on a 16-byte chunk boundary */
+__device__ __forceinline__ int row_ws(uint32_t off) { return (off & 15u) == 0 ? -1 : (int)((off & 15u) >> 2); }
+
+/* The first n (0..16) bytes of `data`, the rest from `old` */
+__device__ __forceinline__ uint4 blend16(const uint4 &data, const uint4 &old, uint32_t n)
+{
+    const uint32_t dw[4] = {data.x, data.y, data.z, data.w}, ow[4] = {old.x, old.y, old.z, old.w};
+    uint32_t r[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const uint32_t have = n > 4u * k ? min(n - 4u * k, 4u) : 0u;          /* data bytes in word k */
+        const uint32_t mask = have >= 4 ? 0xffffffffu : ((1u << (8 * have)) - 1u);
+        r[k] = (dw[k] & mask) | (ow[k] & ~mask);
+    }
+    return make_uint4(r[0], r[1], r[2], r[3]);
+}
+/* plain (coherent) 16-byte global load / store: for bytes this kernel reads and then writes back */
+__device__ __forceinline__ uint4 ld16_plain(const void *p)
+{
+    uint4 r;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p) : "memory");
+    return r;
+}
+
+/* One surface chroma row from its U and V rows (re pairs each, staged at byte offsets offu / offv): whole 32-byte
+ * outputs in the loop -- the two row shifts are template parameters, so the loop body is 4 LDS.128, 8 SHF, 8 PRMT,
+ * 2 STG.128 and nothing else; the < 32 bytes at the row end are the kernel's row-end pass.
+ * Round 1 took the shifts as run-time values per chunk and ended every row with two store_prefix() calls under
+ * divergence: ncu counted ~80 warp instructions per 512 output bytes (profiles/README.md, round 2). */
+template <int WSU, int WSV>
+__device__ __forceinline__ void merge_row_ws(uint8_t *d, const uint8_t *Su, uint32_t offu, const uint8_t *Sv, uint32_t offv, uint32_t re, uint32_t lane)
+{
+    const uint4 *qu = (const uint4 *)Su + (offu >> 4), *qv = (const uint4 *)Sv + (offv >> 4);
+    const uint32_t shu = 8 * (offu & 3), shv = 8 * (offv & 3);
+    const uint32_t nfull = re >> 4;
+    for (uint32_t j = lane; j < nfull; j += 32) {
+        const uint4 u = staged16_ws<WSU>(qu + j, shu), w = staged16_ws<WSV>(qv + j, shv);
+        uint4 lo, hi;
+        lo.x = __byte_perm(u.x, w.x, 0x5140); lo.y = __byte_perm(u.x, w.x, 0x7362);
+        lo.z = __byte_perm(u.y, w.y, 0x5140); lo.w = __byte_perm(u.y, w.y, 0x7362);
+        hi.x = __byte_perm(u.z, w.z, 0x5140); hi.y = __byte_perm(u.z, w.z, 0x7362);
+        hi.z = __byte_perm(u.w, w.w, 0x5140); hi.w = __byte_perm(u.w, w.w, 0x7362);
+        *(uint4 *)(d + 32 * (size_t)j) = lo;
+        *(uint4 *)(d + 32 * (size_t)j + 16) = hi;
+    }
+}
+template <int WSU>
+__device__ __forceinline__ void merge_row_v(int wsv, uint8_t *d, const uint8_t *Su, uint32_t offu, const uint8_t *Sv, uint32_t offv, uint32_t re, uint32_t lane)
+{
+    switch (wsv) {                                                /* warp-uniform, once per row */
+    case -1: merge_row_ws<WSU, -1>(d, Su, offu, Sv, offv, re, lane); break;
+    case 0: merge_row_ws<WSU, 0>(d, Su, offu, Sv, offv, re, lane); break;
+    case 1: merge_row_ws<WSU, 1>(d, Su, offu, Sv, offv, re, lane); break;
+    case 2: merge_row_ws<WSU, 2>(d, Su, offu, Sv, offv, re, lane); break;
+    default: merge_row_ws<WSU, 3>(d, Su, offu, Sv, offv, re, lane); break;
+    }
+}
+
 template <int KIND1>
 __global__ void __launch_bounds__(BROWS_THREADS) bulk_rows_pack_kernel(const __grid_constant__ BulkRowsParams p)
 {
@@ -453,28 +518,44 @@ __global__ void __launch_bounds__(BROWS_THREADS) bulk_rows_pack_kernel(const __g
             bulk_g2s(S + run.a + run.head, src + run.head, run.body, &bar);
         }
         run_edges(S, src, run, lane, warp);
+        /* Row ends.  A row of re bytes ends re & 15 bytes into a 16-byte chunk of the surface; the rest of that chunk is
+         * pitch padding, which must keep its value.  Writing just the re & 15 bytes costs far more than its share: rows
+         * that end on a sub-16-byte store run at 0.87 of the roofline where rows ending on a chunk boundary reach 0.98
+         * (profiles/r2_partial_sector_probe.txt) -- the L2 has to merge every such fragment.  So lane k of each warp
+         * fetches the old chunk of the warp's k-th row NOW (the latency hides behind the bulk load), and after the
+         * copy writes the chunk back whole: the row's last bytes blended over the padding's own bytes. */
+        const uint32_t nfull = re >> 4, tail = re & 15u;
+        const uint32_t my_row = warp + (BROWS_THREADS / 32) * lane;            /* the row whose end this lane owns */
+        uint4 old = make_uint4(0, 0, 0, 0);
+        if (tail && my_row < nr && !p.pad_zero) old = ld16_plain(pp + (size_t)(r0 + my_row) * pitch + 16 * (size_t)nfull);
+#if JMC_MBAR_POLL
+        if (run.body && warp == 0) mbar_wait(&bar, 0);
+        __syncthreads();
+#else
         __syncthreads();
         if (run.body) mbar_wait(&bar, 0);
+#endif
         for (uint32_t i = warp; i < nr; i += BROWS_THREADS / 32) {
             uint8_t *d = pp + (size_t)(r0 + i) * pitch;
             const uint32_t off = run.a + i * re;
             const uint4 *q0 = (const uint4 *)S + (off >> 4);                  /* the row starts off & 15 bytes into this chunk */
             const uint32_t sh = 8 * (off & 3);
-#define JMC_PACK_ROW(EXPR)                                                                                     \
-            for (uint32_t c = 16 * lane; c < re; c += 512) {                                                   \
-                const uint4 *q = q0 + (c >> 4);                                                                \
-                const uint4 o = EXPR;                                                                          \
-                if (c + 16 <= re) *(uint4 *)(d + c) = o;                                                       \
-                else { const uint32_t wd[4] = {o.x, o.y, o.z, o.w}; store_prefix<4>(d + c, wd, re - c); }     \
-            }
-            if ((off & 15) == 0) { JMC_PACK_ROW(q[0]) }
-            else switch ((off & 15) >> 2) {                                    /* warp-uniform, once per row */
-            case 0: JMC_PACK_ROW(shift_pair_ws<0>(q[0], q[1], sh)) break;
-            case 1: JMC_PACK_ROW(shift_pair_ws<1>(q[0], q[1], sh)) break;
-            case 2: JMC_PACK_ROW(shift_pair_ws<2>(q[0], q[1], sh)) break;
-            default: JMC_PACK_ROW(shift_pair_ws<3>(q[0], q[1], sh)) break;
+#define JMC_PACK_ROW(WS)                                                                                       \
+            for (uint32_t j = lane; j < nfull; j += 32) *(uint4 *)(d + 16 * (size_t)j) = staged16_ws<WS>(q0 + j, sh);
+            switch (row_ws(off)) {                                             /* warp-uniform, once per row */
+            case -1: JMC_PACK_ROW(-1) break;
+            case 0: JMC_PACK_ROW(0) break;
+            case 1: JMC_PACK_ROW(1) break;
+            case 2: JMC_PACK_ROW(2) break;
+            default: JMC_PACK_ROW(3) break;
             }
 #undef JMC_PACK_ROW
+        }
+        if (tail && my_row < nr) {
+            const uint32_t off = run.a + my_row * re + 16 * nfull;           /* the row's last bytes in the staging buffer */
+            const uint4 *q = (const uint4 *)S + (off >> 4);
+            const uint4 data = (off & 15) ? shift_pair(q[0], q[1], (off & 15) >> 2, 8 * (off & 3)) : q[0];
+            *(uint4 *)(pp + (size_t)(r0 + my_row) * pitch + 16 * (size_t)nfull) = blend16(data, old, tail);
         }
     } else {
         /* MERGE: re = pairs per row; U run and V run staged separately */
@@ -489,29 +570,45 @@ __global__ void __launch_bounds__(BROWS_THREADS) bulk_rows_pack_kernel(const __g
         }
         run_edges(Su, su, ru, lane, warp);
         run_edges(Sv, sv, rv, lane, warp ^ 2);               /* warps 2 and 3 */
+        /* row ends as above: 2*(re & 15) interleaved bytes behind the last whole 32; the chunk they end in is read now
+         * and written back whole after the merge */
+        const uint32_t nfull = re >> 4, tail = 2 * (re & 15u);
+        const uint32_t my_row = warp + (BROWS_THREADS / 32) * lane;
+        const uint32_t mixed = tail > 16 ? 16u : 0u;          /* offset of the chunk that holds the row end */
+        uint4 old = make_uint4(0, 0, 0, 0);
+        if (tail && tail != 16 && my_row < nr && !p.pad_zero) old = ld16_plain(pp + (size_t)(r0 + my_row) * pitch + 32 * (size_t)nfull + mixed);
+#if JMC_MBAR_POLL
+        if ((ru.body | rv.body) && warp == 0) mbar_wait(&bar, 0);
+        __syncthreads();
+#else
         __syncthreads();
         if (ru.body | rv.body) mbar_wait(&bar, 0);
-        const uint32_t nbytes = 2 * re;
+#endif
         for (uint32_t i = warp; i < nr; i += BROWS_THREADS / 32) {
             uint8_t *d = pp + (size_t)(r0 + i) * pitch;
             const uint32_t offu = ru.a + i * re, offv = rv.a + i * re;
-            for (uint32_t c = 16 * lane; c < re; c += 512) {          /* 16 pairs -> 32 interleaved bytes at 2c */
-                const uint4 u = staged16(Su, offu + c), w = staged16(Sv, offv + c);
-                uint32_t lo[4], hi[4];
-                lo[0] = __byte_perm(u.x, w.x, 0x5140); lo[1] = __byte_perm(u.x, w.x, 0x7362);
-                lo[2] = __byte_perm(u.y, w.y, 0x5140); lo[3] = __byte_perm(u.y, w.y, 0x7362);
-                hi[0] = __byte_perm(u.z, w.z, 0x5140); hi[1] = __byte_perm(u.z, w.z, 0x7362);
-                hi[2] = __byte_perm(u.w, w.w, 0x5140); hi[3] = __byte_perm(u.w, w.w, 0x7362);
-                const uint32_t rem = nbytes - 2 * c;                  /* > 0 */
-                if (rem >= 32) {
-                    *(uint4 *)(d + 2 * c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    *(uint4 *)(d + 2 * c + 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                } else if (rem >= 16) {
-                    *(uint4 *)(d + 2 * c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-                    if (rem > 16) store_prefix<4>(d + 2 * c + 16, hi, rem - 16);
-                } else {
-                    store_prefix<4>(d + 2 * c, lo, rem);
-                }
+            const int wsv = row_ws(offv);
+            switch (row_ws(offu)) {                                            /* warp-uniform, once per row */
+            case -1: merge_row_v<-1>(wsv, d, Su, offu, Sv, offv, re, lane); break;
+            case 0: merge_row_v<0>(wsv, d, Su, offu, Sv, offv, re, lane); break;
+            case 1: merge_row_v<1>(wsv, d, Su, offu, Sv, offv, re, lane); break;
+            case 2: merge_row_v<2>(wsv, d, Su, offu, Sv, offv, re, lane); break;
+            default: merge_row_v<3>(wsv, d, Su, offu, Sv, offv, re, lane); break;
+            }
+        }
+        if (tail && my_row < nr) {
+            const uint32_t offu = ru.a + my_row * re + 16 * nfull, offv = rv.a + my_row * re + 16 * nfull;
+            const uint4 u = staged16(Su, offu), w = staged16(Sv, offv);
+            uint4 lo, hi;
+            lo.x = __byte_perm(u.x, w.x, 0x5140); lo.y = __byte_perm(u.x, w.x, 0x7362);
+            lo.z = __byte_perm(u.y, w.y, 0x5140); lo.w = __byte_perm(u.y, w.y, 0x7362);
+            hi.x = __byte_perm(u.z, w.z, 0x5140); hi.y = __byte_perm(u.z, w.z, 0x7362);
+            hi.z = __byte_perm(u.w, w.w, 0x5140); hi.w = __byte_perm(u.w, w.w, 0x7362);
+            uint8_t *d = pp + (size_t)(r0 + my_row) * pitch + 32 * (size_t)nfull;
+            if (tail < 16) *(uint4 *)d = blend16(lo, old, tail);
+            else {
+                *(uint4 *)d = lo;
+                if (tail > 16) *(uint4 *)(d + 16) = blend16(hi, old, tail - 16);
             }
         }
     }

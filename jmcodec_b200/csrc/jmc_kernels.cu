@@ -225,6 +225,7 @@ static int launch_bulk_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &p
     b.pitched = pp.pitched;
     b.tight = pp.tight;
     b.n_frames = pp.n_frames;
+    b.pad_zero = (!pp.to_tight && ((j->flags & JMC_JOB_PAD_ZERO) || jmc_env().pad_zero)) ? 1u : 0u;
     uint32_t per_row = 0, widest = 16;                 /* shared memory per staged row (worst part); surface bytes per row */
     for (int i = 0; i < 2; i++) {
         const Part &pt = pp.part[i];
@@ -243,6 +244,7 @@ static int launch_bulk_rows(jmc_ctx *ctx, const jmc_job *j, const PlaneParams &p
     if (per_row == 0) return JMC_OK;
     /* ~12 KB of surface data per tile, a multiple of the four warps that store the rows */
     uint32_t rows = std::min<uint32_t>(32, std::max<uint32_t>(4, (12288 / widest) & ~3u));
+    if (jmc_env().brows_rows > 0) rows = (uint32_t)jmc_env().brows_rows;
     const size_t slack = 192;                          /* spare chunks behind each staging area, run alignment */
     while (rows > 1 && (size_t)rows * per_row + slack > 96 * 1024) rows >>= 1;
     if ((size_t)rows * per_row + slack > 96 * 1024) return 1;
@@ -494,6 +496,12 @@ static int launch_rgb_to_nv12(jmc_ctx *ctx, const jmc_job *j, cudaStream_t strea
     if (total == 0) return JMC_OK;
     if (total > 0x7fffffffull) { jmc_set_error("jmc_convert: batch too large for one launch"); return JMC_ERR_INVALID; }
     p.total_tasks = (uint32_t)total;
+    {
+        /* JMC_JOB_PAD_ZERO is honoured when every surface row is 16-byte aligned and long enough for whole chunks */
+        bool known = true;
+        const uint64_t bits = frames_bits(j, j->surf, &known) | (uint64_t)j->surf_y_off | (uint64_t)j->surf_uv_off | (uint32_t)j->pitch;
+        p.pad_zero = (((j->flags & JMC_JOB_PAD_ZERO) || jmc_env().pad_zero) && known && (bits & 15) == 0 && j->pitch >= ((j->width + 15) & ~15)) ? 1u : 0u;
+    }
     constexpr uint32_t WARPS = RGB2_THREADS / 32;
     rgb_to_nv12_kernel<<<(p.total_tasks + WARPS - 1) / WARPS, RGB2_THREADS, 0, stream>>>(p);
     JMC_CUDA(cudaGetLastError());

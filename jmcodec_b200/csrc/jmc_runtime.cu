@@ -124,6 +124,8 @@ static void env_load()
     f.pipeline_h2d_2d = env_tri("JMC_PIPELINE_H2D_2D") != 0;
     f.rgb_flat = env_tri("JMC_RGB_FLAT");
     f.rgb2_flat = env_tri("JMC_RGB2_FLAT");
+    f.pad_zero = env_on("JMC_PAD_ZERO");
+    f.brows_rows = getenv("JMC_BROWS_ROWS") ? atoi(getenv("JMC_BROWS_ROWS")) : 0;
     g_env = f;
     g_env_loaded = true;
 }

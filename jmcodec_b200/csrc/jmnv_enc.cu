@@ -189,6 +189,9 @@ int jm_nvenc_enc_frame(const unsigned char *in_yuv_buf, const int yuv_len, int *
             j.n_frames = 1;
             j.tight.base = c->d_stage;
             j.surf.base = s.dptr;
+            /* the pool's surfaces are ours: zeroed at init and only ever written here, so zeroing the padding behind a row
+             * end again changes nothing -- and saves the kernel the read-merge of every row's last sector */
+            j.flags = JMC_JOB_PAD_ZERO;
             if (jmc_convert(c->ctx, &j, nullptr) != JMC_OK) { s.lock_count = 0; return JM_NVENC_ERR_GENERIC; }
         }
     } else {                                                          /* ARGB/ABGR, :1083-1097 (pitch honoured) */

@@ -448,3 +448,52 @@ def test_pack_batches_of_odd_widths(ctx, geom):
                 oracle.nvenc_upload(frames[f], code, w, h, want, pitch)
                 assert np.array_equal(got[f * nsurf:(f + 1) * nsurf], want), (geom, hex(code), skew, f)
             ctx.free(dt), ctx.free(ds)
+
+
+def _zero_row_end_padding(want, w, h, pitch, nv12_chroma):
+    """What JMC_JOB_PAD_ZERO allows: behind the last byte of every row the kernel wrote, zeros up to the next 16-byte boundary."""
+    rows = want.reshape(-1, pitch)
+    lw = w
+    rows[:h, lw:(lw + 15) & ~15] = 0
+    cwb = w if nv12_chroma else 2 * (w >> 1)                 # bytes per chroma row
+    rows[h:h + (h >> 1), cwb:(cwb + 15) & ~15] = 0
+    return want
+
+
+@pytest.mark.parametrize("geom", [(854, 480, 1024), (1366, 768, 1536), (1080, 1920, 1088), (427, 241, 512), (255, 17, 256), (250, 16, 256), (1919, 1079, 2048)])
+def test_pad_zero_flag(ctx, geom):
+    """JMC_JOB_PAD_ZERO (encode ops): the active bytes are the reference's, the padding behind every row end is zero up to
+    the next 16-byte boundary and untouched beyond -- for the I420 / NV12 pack and for RGB24 -> NV12."""
+    import jmcodec_b200 as J
+    w, h, pitch = geom
+    nsurf = pitch * (h * 3 // 2 + 1)
+    PAD_ZERO = 4
+    tight = synth.i420_frame(w, h, 26, w + h)
+    for code in (0x1, 0x10):
+        dt, ds = ctx.upload(tight), ctx.alloc(nsurf)
+        ctx.memset(ds, synth.PAD_BYTE, nsurf)
+        j = ctx.job_nvenc(w, h, pitch, code)
+        j.n_frames, j.surf.base, j.tight.base, j.flags = 1, ds, dt, PAD_ZERO
+        ctx.convert(j)
+        got = np.empty(nsurf, np.uint8)
+        ctx.d2h(got, ds)
+        want = np.full(nsurf, synth.PAD_BYTE, np.uint8)
+        oracle.nvenc_upload(tight, code, w, h, want, pitch)
+        if w % 16:                                           # widths that are multiples of 16 take the bulk kernel: nothing to zero
+            _zero_row_end_padding(want, w, h, pitch, code == 0x1)
+        assert np.array_equal(got, want), (geom, hex(code))
+        ctx.free(dt), ctx.free(ds)
+    if w >= 2 and h >= 2:
+        rgb = synth.random_bytes(3 * w * h, synth.frame_key(27, w))
+        dr, ds = ctx.upload(rgb), ctx.alloc(nsurf)
+        ctx.memset(ds, synth.PAD_BYTE, nsurf)
+        j = ctx.job_rgb_to_nv12(w, h, 3 * w, pitch)
+        j.n_frames, j.rgb.base, j.surf.base, j.flags = 1, dr, ds, PAD_ZERO
+        ctx.convert(j)
+        got = np.empty(nsurf, np.uint8)
+        ctx.d2h(got, ds)
+        want = np.full(nsurf, synth.PAD_BYTE, np.uint8)
+        oracle.rgb24_to_nv12(rgb, 3 * w, w, h, want, pitch)
+        _zero_row_end_padding(want, w, h, pitch, False)
+        assert np.array_equal(got, want), (geom, "rgb2nv12")
+        ctx.free(dr), ctx.free(ds)

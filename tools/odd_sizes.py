@@ -4,6 +4,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, jmcodec_b200 as J
 ctx = J.Ctx(0)
 peak, _ = bench.peaks()
+if len(sys.argv) > 2 and sys.argv[1] == "--spec":          # --spec op,w,h,pitch,frames [more specs ...]
+    for sp in sys.argv[2:]:
+        op, w, h, pitch, n = sp.split(",")
+        bench.WORKLOADS["_x"] = (op, int(w), int(h), int(pitch), int(n))
+        r = bench.device_only(ctx, "_x", 0, 10, 3)
+        print(f"{sp:28s} {r['frames_per_s']:12.0f} fps {r['gbs']:8.1f} GB/s  {r['gbs']/peak:.3f} of peak")
+    sys.exit(0)
 for name, spec in {
     "1080x1920 portrait p1088": ("i420", 1080, 1920, 1088, 150), "1080x1920 portrait p1280": ("i420", 1080, 1920, 1280, 150),
     "1366x768 p1536": ("i420", 1366, 768, 1536, 300), "854x480 p1024": ("i420", 854, 480, 1024, 600),
