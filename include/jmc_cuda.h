@@ -186,7 +186,8 @@ JMC_API int jmc_convert_timed(jmc_ctx *ctx, const jmc_job *job, int iters, float
 /* ---- host link probe ------------------------------------------------------------------------
  * What the PCIe link between this context's device and pinned host memory delivers right now: `copies` copies of
  * bytes_per_copy bytes, device-timed (CUDA events on the upload / delivery stream).  mode 1: host -> device only,
- * 2: device -> host only, 3: both directions at once (what the host-delivery pipeline does).  Run it on every GPU
+ * 2: device -> host only, 3: both directions at once (what the host-delivery pipeline does); +4: the upload reads a
+ * write-combined host buffer (cuMemHostAlloc(WRITECOMBINED), what nv_enc.cpp:1305 hands its callers).  Run it on every GPU
  * of a box between two barriers to measure the whole-box host ceiling the e2e leg is bounded by (bench.py). */
 typedef struct jmc_link_rates { double h2d_gbs, d2h_gbs; } jmc_link_rates;
 JMC_API int jmc_link_probe(jmc_ctx *ctx, size_t bytes_per_copy, int copies, int mode, jmc_link_rates *out);

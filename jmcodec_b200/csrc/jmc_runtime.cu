@@ -369,12 +369,14 @@ int jmc_convert_timed(jmc_ctx *c, const jmc_job *job, int iters, float *ms_per_l
 int jmc_link_probe(jmc_ctx *c, size_t bytes_per_copy, int copies, int mode, jmc_link_rates *out)
 {
     JMC_BIND(c);
-    if (!out || bytes_per_copy == 0 || copies < 1 || mode < 1 || mode > 3) { jmc_set_error("jmc_link_probe: bad arguments"); return JMC_ERR_INVALID; }
+    const bool wc = (mode & 4) != 0;                       /* write-combined (uncached, unsnooped) host source for the upload */
+    mode &= 3;
+    if (!out || bytes_per_copy == 0 || copies < 1 || mode < 1) { jmc_set_error("jmc_link_probe: bad arguments"); return JMC_ERR_INVALID; }
     out->h2d_gbs = out->d2h_gbs = 0.0;
     void *h_up = nullptr, *h_down = nullptr, *d_up = nullptr, *d_down = nullptr;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     cudaError_t e = cudaSuccess;
-    if (mode & 1) { e = cudaHostAlloc(&h_up, bytes_per_copy, cudaHostAllocDefault); if (e == cudaSuccess) e = cudaMalloc(&d_up, bytes_per_copy); }
+    if (mode & 1) { e = cudaHostAlloc(&h_up, bytes_per_copy, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault); if (e == cudaSuccess) e = cudaMalloc(&d_up, bytes_per_copy); }
     if (e == cudaSuccess && (mode & 2)) { e = cudaHostAlloc(&h_down, bytes_per_copy, cudaHostAllocDefault); if (e == cudaSuccess) e = cudaMalloc(&d_down, bytes_per_copy); }
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
     if (e == cudaSuccess && h_up) memset(h_up, 0x5A, bytes_per_copy);

@@ -13,8 +13,12 @@
  *              (jmc_pipeline_*, what a decoder-less caller of the library pays)
  * mode device: the surfaces of a stream are resident in HBM (what NVDEC would have produced);
  *              one launch per batch, tight frames stay on the device
+ * mode d2h   : surfaces resident in HBM, tight frames delivered to pinned host memory (the reference's real data flow)
+ * Every GPU thread enters its timed region through a barrier, so whole-box rates are concurrent rates.
  * Prints one JSON line with whole-box frames/s (wall clock over all GPU threads) and per-GPU rates.
  */
+#include <pthread.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -27,8 +31,10 @@
 
 struct Options {
     int gpus = 0, streams = 32, frames = 300, batch = 30, width = 1920, height = 1080, pitch = 2048;
-    bool e2e = true;
+    bool e2e = true;          /* host buffers both ways */
+    bool d2h = false;         /* surfaces resident in HBM (as after NVDEC), tight frames delivered to pinned host memory */
 };
+static pthread_barrier_t g_start;   /* every GPU enters its timed region together: whole-box rates are then concurrent rates */
 
 struct GpuResult {
     int device = 0, streams = 0;
@@ -49,7 +55,7 @@ static void fill_surface(unsigned char *p, size_t n, unsigned seed)
         if (r_ < 0) { res->error = std::string(#call) + ": " + jmc_last_error(); return; }          \
     } while (0)
 
-static void gpu_worker(const Options &o, int device, int n_gpus, GpuResult *res)
+static void gpu_worker_body(const Options &o, int device, int n_gpus, GpuResult *res, bool *at_barrier)
 {
     res->device = device;
     jmc_ctx *ctx = nullptr;
@@ -69,10 +75,14 @@ static void gpu_worker(const Options &o, int device, int n_gpus, GpuResult *res)
     CHECK(jmc_alloc_host(ctx, surf * o.frames, 0, &h_in));
     fill_surface((unsigned char *)h_in, surf * (size_t)(o.frames < 8 ? o.frames : 8), (unsigned)device);
     for (int f = 8; f < o.frames; f++) memcpy((unsigned char *)h_in + f * surf, (unsigned char *)h_in + (f % 8) * surf, surf);
-    if (o.e2e) {
+    if (o.e2e || o.d2h) {
         CHECK(jmc_alloc_host(ctx, tight * o.frames, 0, &h_out));
         CHECK(jmc_pipeline_create(ctx, &shape, surf, 3, &pipe));
-    } else {
+    }
+    if (o.d2h) {
+        CHECK(jmc_alloc_device(ctx, surf * o.frames, &d_in));
+        CHECK(jmc_memcpy_h2d(ctx, d_in, h_in, surf * o.frames));
+    } else if (!o.e2e) {
         CHECK(jmc_alloc_device(ctx, surf * o.frames, &d_in));
         CHECK(jmc_alloc_device(ctx, tight * o.frames, &d_out));
         CHECK(jmc_memcpy_h2d(ctx, d_in, h_in, surf * o.frames));
@@ -81,8 +91,9 @@ static void gpu_worker(const Options &o, int device, int n_gpus, GpuResult *res)
     auto run_stream = [&](bool timed) {
         for (int f0 = 0; f0 < o.frames; f0 += o.batch) {
             const int n = o.frames - f0 < o.batch ? o.frames - f0 : o.batch;
-            if (o.e2e) {
-                int slot = jmc_pipeline_submit(pipe, (unsigned char *)h_in + f0 * surf, nullptr, (unsigned char *)h_out + f0 * tight, nullptr, n);
+            if (o.e2e || o.d2h) {
+                int slot = jmc_pipeline_submit(pipe, o.d2h ? nullptr : (unsigned char *)h_in + f0 * surf, o.d2h ? (unsigned char *)d_in + f0 * surf : nullptr,
+                                               (unsigned char *)h_out + f0 * tight, nullptr, n);
                 if (slot < 0) { res->error = jmc_last_error(); return; }
             } else {
                 jmc_job j = shape;
@@ -98,13 +109,15 @@ static void gpu_worker(const Options &o, int device, int n_gpus, GpuResult *res)
     if (pipe) CHECK(jmc_pipeline_drain(pipe));
     CHECK(jmc_ctx_sync(ctx));
 
+    *at_barrier = true;
+    pthread_barrier_wait(&g_start);
     const auto t0 = std::chrono::steady_clock::now();
     CHECK(jmc_event_record(ctx, ev0, o.e2e ? 1 : 0));
     for (int s = device; s < o.streams && res->error.empty(); s += n_gpus) {      /* stream s lives on GPU s % N */
         run_stream(true);
         res->streams++;
     }
-    CHECK(jmc_event_record(ctx, ev1, o.e2e ? 2 : 0));
+    CHECK(jmc_event_record(ctx, ev1, (o.e2e || o.d2h) ? 2 : 0));
     float ms = 0;
     CHECK(jmc_event_elapsed_ms(ctx, ev0, ev1, &ms));
     if (pipe) CHECK(jmc_pipeline_drain(pipe));
@@ -122,6 +135,14 @@ static void gpu_worker(const Options &o, int device, int n_gpus, GpuResult *res)
     jmc_ctx_destroy(ctx);
 }
 
+/* a GPU whose set-up failed must still show up at the start barrier, or the others would wait for ever */
+static void gpu_worker(const Options &o, int device, int n_gpus, GpuResult *res)
+{
+    bool at_barrier = false;
+    gpu_worker_body(o, device, n_gpus, res, &at_barrier);
+    if (!at_barrier) pthread_barrier_wait(&g_start);
+}
+
 int main(int argc, char **argv)
 {
     Options o;
@@ -134,7 +155,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--width")) val(o.width);
         else if (!strcmp(argv[i], "--height")) val(o.height);
         else if (!strcmp(argv[i], "--pitch")) val(o.pitch);
-        else if (!strcmp(argv[i], "--mode") && i + 1 < argc) o.e2e = strcmp(argv[++i], "device") != 0;
+        else if (!strcmp(argv[i], "--mode") && i + 1 < argc) { const char *m = argv[++i]; o.e2e = !strcmp(m, "e2e"); o.d2h = !strcmp(m, "d2h"); }
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
     const int have = jmc_device_count();
@@ -142,6 +163,7 @@ int main(int argc, char **argv)
     if (o.gpus <= 0 || o.gpus > have) o.gpus = have;
     if (o.batch < 1 || o.frames < 1 || o.streams < 1 || o.pitch < o.width) { fprintf(stderr, "bad geometry\n"); return 2; }
 
+    pthread_barrier_init(&g_start, nullptr, (unsigned)o.gpus);
     std::vector<GpuResult> res(o.gpus);
     std::vector<std::thread> th;
     const auto t0 = std::chrono::steady_clock::now();
@@ -157,7 +179,7 @@ int main(int argc, char **argv)
     }
     printf("{\"tool\": \"jm_streams\", \"mode\": \"%s\", \"n_gpus\": %d, \"streams\": %d, \"frames_per_stream\": %d, \"batch\": %d, "
            "\"width\": %d, \"height\": %d, \"pitch\": %d, \"frames\": %lld, \"seconds_slowest_gpu\": %.6f, \"frames_per_s\": %.1f, \"per_gpu\": [",
-           o.e2e ? "e2e" : "device", o.gpus, o.streams, o.frames, o.batch, o.width, o.height, o.pitch, frames, slowest, frames / slowest);
+           o.e2e ? "e2e" : (o.d2h ? "d2h" : "device"), o.gpus, o.streams, o.frames, o.batch, o.width, o.height, o.pitch, frames, slowest, frames / slowest);
     for (size_t i = 0; i < res.size(); i++)
         printf("%s{\"device\": %d, \"streams\": %d, \"frames\": %lld, \"wall_s\": %.6f, \"device_ms\": %.3f, \"frames_per_s\": %.1f}", i ? ", " : "",
                res[i].device, res[i].streams, res[i].frames, res[i].seconds, res[i].device_ms, res[i].frames / (res[i].device_ms * 1e-3));
