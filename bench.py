@@ -509,16 +509,16 @@ def main():
     ceiling = None
     try:
         barrier()
-        up, down = ctx.link_probe(256 << 20, 6, 3)
+        up, down = ctx.link_probe(64 << 20, -300, 3)         # every rank copies for the same 300 ms window
         barrier()
-        _, down_only = ctx.link_probe(256 << 20, 6, 2)
+        _, down_only = ctx.link_probe(64 << 20, -300, 2)
         barrier()
         sums = []
         for v in (up, down, down_only):
             tot, _ = aggregate(int(v * 1e6), 1.0, dev)
             sums.append(tot / 1e6)
         ceiling = {"bidirectional_h2d_gbs": sums[0], "bidirectional_d2h_gbs": sums[1], "d2h_only_gbs": sums[2],
-                   "how": "jmc_link_probe: 6 x 256 MiB pinned copies per direction on every rank at once, between barriers, device-timed"}
+                   "how": "jmc_link_probe: 64 MiB pinned copies for a 300 ms window on every rank at once, between barriers, device-timed; whole-job = sum over ranks"}
     except Exception as e:      # noqa: BLE001
         ceiling = {"error": repr(e)}
     sampler.stop()

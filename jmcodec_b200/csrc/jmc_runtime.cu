@@ -4,6 +4,7 @@
  */
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 
@@ -371,7 +372,7 @@ int jmc_link_probe(jmc_ctx *c, size_t bytes_per_copy, int copies, int mode, jmc_
     JMC_BIND(c);
     const bool wc = (mode & 4) != 0;                       /* write-combined (uncached, unsnooped) host source for the upload */
     mode &= 3;
-    if (!out || bytes_per_copy == 0 || copies < 1 || mode < 1) { jmc_set_error("jmc_link_probe: bad arguments"); return JMC_ERR_INVALID; }
+    if (!out || bytes_per_copy == 0 || copies == 0 || mode < 1) { jmc_set_error("jmc_link_probe: bad arguments"); return JMC_ERR_INVALID; }
     out->h2d_gbs = out->d2h_gbs = 0.0;
     void *h_up = nullptr, *h_down = nullptr, *d_up = nullptr, *d_down = nullptr;
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
@@ -381,14 +382,34 @@ int jmc_link_probe(jmc_ctx *c, size_t bytes_per_copy, int copies, int mode, jmc_
     for (int i = 0; i < 4 && e == cudaSuccess; i++) e = cudaEventCreate(&ev[i]);
     if (e == cudaSuccess && h_up) memset(h_up, 0x5A, bytes_per_copy);
     if (e == cudaSuccess && d_down) e = cudaMemset(d_down, 0xA5, bytes_per_copy);
-    /* one warm-up copy each way, then `copies` timed ones; the two directions run on the upload and the delivery stream */
+    /* one warm-up copy each way, then the timed ones; the two directions run on the upload and the delivery stream.
+     * copies > 0: that many copies per direction.  copies < 0: keep copying for -copies milliseconds of host time (at most
+     * two copies queued per direction), so that several GPUs probed together are measured over the SAME window -- with a
+     * fixed number of copies the faster GPUs finish early and the slower ones then run alone, which overstates what the
+     * box delivers concurrently. */
+    const bool timed = copies < 0;
+    const double window_s = timed ? -copies * 1e-3 : 0.0;
+    long long done_up = 0, done_down = 0;
+    cudaEvent_t mark[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } };
+    for (int d = 0; d < 2 && e == cudaSuccess; d++) for (int k = 0; k < 2 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&mark[d][k], cudaEventDisableTiming);
     for (int rep = 0; rep < 2 && e == cudaSuccess; rep++) {
-        const int n = rep == 0 ? 1 : copies;
+        const int n = rep == 0 ? 1 : (timed ? 0x7fffffff : copies);
         if (mode & 1) e = cudaEventRecord(ev[0], c->stream[1]);
         if (e == cudaSuccess && (mode & 2)) e = cudaEventRecord(ev[2], c->stream[2]);
+        struct timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
         for (int i = 0; i < n && e == cudaSuccess; i++) {
-            if (mode & 1) e = cudaMemcpyAsync(d_up, h_up, bytes_per_copy, cudaMemcpyHostToDevice, c->stream[1]);
-            if (e == cudaSuccess && (mode & 2)) e = cudaMemcpyAsync(h_down, d_down, bytes_per_copy, cudaMemcpyDeviceToHost, c->stream[2]);
+            if (timed && rep == 1) {
+                clock_gettime(CLOCK_MONOTONIC, &t1);
+                if ((t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec) >= window_s) break;
+                if (i >= 2) {                                              /* at most two copies queued per direction */
+                    if (mode & 1) e = cudaEventSynchronize(mark[0][i & 1]);
+                    if (e == cudaSuccess && (mode & 2)) e = cudaEventSynchronize(mark[1][i & 1]);
+                }
+            }
+            if (e == cudaSuccess && (mode & 1)) { e = cudaMemcpyAsync(d_up, h_up, bytes_per_copy, cudaMemcpyHostToDevice, c->stream[1]); if (e == cudaSuccess) e = cudaEventRecord(mark[0][i & 1], c->stream[1]); }
+            if (e == cudaSuccess && (mode & 2)) { e = cudaMemcpyAsync(h_down, d_down, bytes_per_copy, cudaMemcpyDeviceToHost, c->stream[2]); if (e == cudaSuccess) e = cudaEventRecord(mark[1][i & 1], c->stream[2]); }
+            if (rep == 1) { done_up += (mode & 1) ? 1 : 0; done_down += (mode & 2) ? 1 : 0; }
         }
         if (e == cudaSuccess && (mode & 1)) e = cudaEventRecord(ev[1], c->stream[1]);
         if (e == cudaSuccess && (mode & 2)) e = cudaEventRecord(ev[3], c->stream[2]);
@@ -397,10 +418,10 @@ int jmc_link_probe(jmc_ctx *c, size_t bytes_per_copy, int copies, int mode, jmc_
     }
     if (e == cudaSuccess) {
         float ms = 0.f;
-        const double total = (double)bytes_per_copy * copies;
-        if (mode & 1) { e = cudaEventElapsedTime(&ms, ev[0], ev[1]); if (e == cudaSuccess && ms > 0) out->h2d_gbs = total / (ms * 1e-3) / 1e9; }
-        if (e == cudaSuccess && (mode & 2)) { e = cudaEventElapsedTime(&ms, ev[2], ev[3]); if (e == cudaSuccess && ms > 0) out->d2h_gbs = total / (ms * 1e-3) / 1e9; }
+        if (mode & 1) { e = cudaEventElapsedTime(&ms, ev[0], ev[1]); if (e == cudaSuccess && ms > 0) out->h2d_gbs = (double)bytes_per_copy * done_up / (ms * 1e-3) / 1e9; }
+        if (e == cudaSuccess && (mode & 2)) { e = cudaEventElapsedTime(&ms, ev[2], ev[3]); if (e == cudaSuccess && ms > 0) out->d2h_gbs = (double)bytes_per_copy * done_down / (ms * 1e-3) / 1e9; }
     }
+    for (int d = 0; d < 2; d++) for (int k = 0; k < 2; k++) if (mark[d][k]) cudaEventDestroy(mark[d][k]);
     for (int i = 0; i < 4; i++) if (ev[i]) cudaEventDestroy(ev[i]);
     if (h_up) cudaFreeHost(h_up);
     if (h_down) cudaFreeHost(h_down);

@@ -772,3 +772,31 @@ def test_job_with_host_side_pointer_list(J, ctx):
             ctx.convert(j)                                             # more than JMC_INLINE_LIST_MAX frames
         for d in dsurf + dout:
             ctx.free(d)
+
+
+def test_link_probe_and_tools(J, ctx):
+    """jmc_link_probe (fixed number of copies and fixed window), tools/jm_link and tools/jm_dropin run and report sane numbers."""
+    import json
+    import os
+    import subprocess
+    up, down = ctx.link_probe(8 << 20, 3, 3)
+    assert up > 0.5 and down > 0.5
+    up, down = ctx.link_probe(8 << 20, -30, 2)              # 30 ms window, device -> host only
+    assert up == 0 and down > 0.5
+    up, down = ctx.link_probe(8 << 20, 2, 5)                # host -> device from write-combined memory
+    assert up > 0.5 and down == 0
+    with pytest.raises(J.JmcError):
+        ctx.link_probe(0, 1, 3)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tools", "jm_link")
+    if os.path.exists(exe):
+        d = json.loads(subprocess.run([exe, "--gpus", "1", "--mb", "8", "--ms", "30"], capture_output=True, text=True, timeout=120).stdout)
+        assert d["n_gpus"] == 1 and d["bidirectional"]["box_h2d_gbs"] > 0.5 and d["d2h_only"]["box_d2h_gbs"] > 0.5
+    exe = os.path.join(root, "tools", "jm_dropin")
+    if os.path.exists(exe):
+        # every variant of the drop-in loop (pageable / pinned / registered / lazy / zero-copy, delays, threads, 4 handles) on
+        # small frames: each checks its first frame against a CPU restatement of nv_dec.cpp:798-820
+        p = subprocess.run([exe, "--frames", "12", "--width", "640", "--height", "360", "--pitch", "768"], capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr
+        d = json.loads(p.stdout)
+        assert len(d) >= 20 and all(isinstance(v, float) and v > 0 for v in d.values()), d

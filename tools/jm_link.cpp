@@ -3,7 +3,9 @@
  * (H2D only / D2H only / both at once, optionally from write-combined host memory) starts on all GPUs together and is
  * device-timed per GPU (jmc_link_probe).  Plain C++ on include/jmc_cuda.h.
  *
- *   tools/jm_link [--gpus N] [--mb 256] [--copies 6]      one JSON line: per-GPU and whole-box GB/s per phase
+ *   tools/jm_link [--gpus N] [--mb 64] [--ms 400 | --copies K]      one JSON line: per-GPU and whole-box GB/s per phase
+ * Default: every GPU copies for the same 400 ms window (with a fixed number of copies the faster GPUs finish early and
+ * the slower ones then run alone, which overstates the concurrent rate).
  */
 #include <pthread.h>
 
@@ -22,12 +24,13 @@ constexpr int NPH = sizeof(PHASES) / sizeof(PHASES[0]);
 
 int main(int argc, char **argv)
 {
-    int gpus = jmc_device_count(), mb = 256, copies = 6;
+    int gpus = jmc_device_count(), mb = 64, copies = -400;       /* copies < 0: a window of that many milliseconds */
     for (int i = 1; i < argc; i++) {
         std::string a = argv[i];
         if (a == "--gpus" && i + 1 < argc) gpus = atoi(argv[++i]);
         else if (a == "--mb" && i + 1 < argc) mb = atoi(argv[++i]);
         else if (a == "--copies" && i + 1 < argc) copies = atoi(argv[++i]);
+        else if (a == "--ms" && i + 1 < argc) copies = -atoi(argv[++i]);
     }
     if (gpus < 1) { fprintf(stderr, "no CUDA device\n"); return 1; }
     pthread_barrier_t bar;

@@ -19,6 +19,7 @@
  */
 #include <pthread.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -33,7 +34,9 @@ struct Options {
     int gpus = 0, streams = 32, frames = 300, batch = 30, width = 1920, height = 1080, pitch = 2048;
     bool e2e = true;          /* host buffers both ways */
     bool d2h = false;         /* surfaces resident in HBM (as after NVDEC), tight frames delivered to pinned host memory */
+    bool dynamic = false;     /* --assign dynamic: a GPU takes the next unprocessed stream when it is free, instead of s % nGPU */
 };
+static std::atomic<int> g_next_stream{0};
 static pthread_barrier_t g_start;   /* every GPU enters its timed region together: whole-box rates are then concurrent rates */
 
 struct GpuResult {
@@ -113,9 +116,19 @@ static void gpu_worker_body(const Options &o, int device, int n_gpus, GpuResult 
     pthread_barrier_wait(&g_start);
     const auto t0 = std::chrono::steady_clock::now();
     CHECK(jmc_event_record(ctx, ev0, o.e2e ? 1 : 0));
-    for (int s = device; s < o.streams && res->error.empty(); s += n_gpus) {      /* stream s lives on GPU s % N */
-        run_stream(true);
-        res->streams++;
+    if (o.dynamic) {
+        /* the GPUs of one box do not all reach host memory at the same rate (this pool: GPUs 4-7 deliver 1.5x what GPUs 0-3
+         * do, profiles/r2_host_link_8gpu.txt); with s % nGPU the box waits for its slowest GPU, with a shared queue of
+         * streams every GPU works until the queue is empty */
+        for (int s; (s = g_next_stream.fetch_add(1)) < o.streams && res->error.empty();) {
+            run_stream(true);
+            res->streams++;
+        }
+    } else {
+        for (int s = device; s < o.streams && res->error.empty(); s += n_gpus) {      /* stream s lives on GPU s % N */
+            run_stream(true);
+            res->streams++;
+        }
     }
     CHECK(jmc_event_record(ctx, ev1, (o.e2e || o.d2h) ? 2 : 0));
     float ms = 0;
@@ -155,6 +168,7 @@ int main(int argc, char **argv)
         else if (!strcmp(argv[i], "--width")) val(o.width);
         else if (!strcmp(argv[i], "--height")) val(o.height);
         else if (!strcmp(argv[i], "--pitch")) val(o.pitch);
+        else if (!strcmp(argv[i], "--assign") && i + 1 < argc) o.dynamic = !strcmp(argv[++i], "dynamic");
         else if (!strcmp(argv[i], "--mode") && i + 1 < argc) { const char *m = argv[++i]; o.e2e = !strcmp(m, "e2e"); o.d2h = !strcmp(m, "d2h"); }
         else { fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
     }
@@ -178,8 +192,8 @@ int main(int argc, char **argv)
         if (r.seconds > slowest) slowest = r.seconds;
     }
     printf("{\"tool\": \"jm_streams\", \"mode\": \"%s\", \"n_gpus\": %d, \"streams\": %d, \"frames_per_stream\": %d, \"batch\": %d, "
-           "\"width\": %d, \"height\": %d, \"pitch\": %d, \"frames\": %lld, \"seconds_slowest_gpu\": %.6f, \"frames_per_s\": %.1f, \"per_gpu\": [",
-           o.e2e ? "e2e" : (o.d2h ? "d2h" : "device"), o.gpus, o.streams, o.frames, o.batch, o.width, o.height, o.pitch, frames, slowest, frames / slowest);
+           "\"assign\": \"%s\", \"width\": %d, \"height\": %d, \"pitch\": %d, \"frames\": %lld, \"seconds_slowest_gpu\": %.6f, \"frames_per_s\": %.1f, \"per_gpu\": [",
+           o.e2e ? "e2e" : (o.d2h ? "d2h" : "device"), o.gpus, o.streams, o.frames, o.batch, o.dynamic ? "dynamic" : "stream % n_gpus", o.width, o.height, o.pitch, frames, slowest, frames / slowest);
     for (size_t i = 0; i < res.size(); i++)
         printf("%s{\"device\": %d, \"streams\": %d, \"frames\": %lld, \"wall_s\": %.6f, \"device_ms\": %.3f, \"frames_per_s\": %.1f}", i ? ", " : "",
                res[i].device, res[i].streams, res[i].frames, res[i].seconds, res[i].device_ms, res[i].frames / (res[i].device_ms * 1e-3));
