@@ -143,8 +143,9 @@ JMDLL_FUNC int jm_nvdec_memory_release_host(void *buf, handle_nvdec handle);
 /** page-lock a buffer the caller already owns (malloc'ed out_buf / packet buffer) so that it is reached by direct
  *  DMA; unregister it BEFORE freeing it.  Only the whole pages INSIDE the buffer are locked (its partial first / last
  *  page may hold other allocations of the caller); those < 4 KB edges are copied through a pinned bounce buffer.
- *  Buffers with less than 64 KB of whole pages are left pageable (returns -1).  (JMC_NVDEC_LAZY_PIN=1 / option "lazy_pin" does this automatically for a
- *  buffer it sees for the second time -- opt-in, because the library cannot see the caller free it.) */
+ *  Buffers with less than 64 KB of whole pages are left pageable (returns -1).  (JMC_NVDEC_LAZY_PIN=1 / option "lazy_pin" does this automatically for an
+ *  OUT_BUF it sees for the second time -- opt-in, because the library cannot see the caller free it: a buffer that is
+ *  freed while registered and whose address is handed out again would receive its frames in the old pages.) */
 JMDLL_FUNC int jm_nvdec_memory_register_host(void *buf, int buf_len, handle_nvdec handle);
 JMDLL_FUNC int jm_nvdec_memory_unregister_host(void *buf, handle_nvdec handle);
 /** frames held back before they are announced (0..20, default 0 or env JMC_NVDEC_DISPLAY_DELAY): with n >= 1 the

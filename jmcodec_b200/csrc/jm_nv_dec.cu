@@ -560,9 +560,10 @@ bool ensure_edges(nvdec_b200 *c)
     return true;
 }
 
-/* Opt-in (JMC_NVDEC_LAZY_PIN=1 / jm_nvdec_set_option): a pageable caller buffer seen for the second time is
- * page-locked in place so that it receives / supplies frames by direct DMA.  Off by default: the registration
- * outlives a free() of the buffer by the caller, which the library cannot observe. */
+/* Opt-in (JMC_NVDEC_LAZY_PIN=1 / jm_nvdec_set_option): a pageable out_buf seen for the second time is page-locked in
+ * place so that it receives frames by direct DMA (test_nv_dec.cpp:207 mallocs one buffer for the whole run).  Off by
+ * default, and never applied to packet buffers: the registration outlives a free() of the buffer by the caller, which
+ * the library cannot observe -- the virtual range then maps new pages while the DMA still targets the old ones. */
 bool maybe_lazy_pin(nvdec_b200 *c, const void *p, size_t len)
 {
     if (!c->lazy_pin) return false;
@@ -848,8 +849,9 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
             uint8_t *blo = nullptr, *bhi = nullptr;
             bool split = false;
             if (!pinned) {
+                /* only buffers the caller registered explicitly (jm_nvdec_memory_register_host): packet buffers are
+                 * typically transient, and a registration that outlives its buffer makes the DMA read stale pages */
                 split = registered_interior(c, src, bytes, &blo, &bhi);
-                if (!split && maybe_lazy_pin(c, src, bytes)) split = registered_interior(c, src, bytes, &blo, &bhi);
                 if (split && !ensure_edges(c)) split = false;
             }
             if (split) {

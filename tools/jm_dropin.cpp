@@ -39,8 +39,8 @@ static const Variant VARIANTS[] = {
     { "host_packet_pageable_out_1thread_fps", false, "pageable", 0, 0, 1 },
     { "host_packet_pageable_out_delay2_fps", false, "pageable", 2, -1, 1 },
     { "host_packet_pageable_out_delay2_1thread_fps", false, "pageable", 2, 0, 1 },
-    { "host_packet_lazy_pin_fps", false, "lazy", 0, -1, 1 },
-    { "host_packet_lazy_pin_delay2_fps", false, "lazy", 2, -1, 1 },
+    { "host_packet_registered_fps", false, "registered", 0, -1, 1 },      /* packet buffers and out_buf registered explicitly */
+    { "host_packet_registered_delay2_fps", false, "registered", 2, -1, 1 },
     /* behind NVDEC: device-resident surface in */
     { "device_surface_pageable_out_fps", true, "pageable", 0, -1, 1 },
     { "device_surface_pageable_out_1thread_fps", true, "pageable", 0, 0, 1 },
@@ -116,6 +116,7 @@ static void run_handle(const Options &o, const Variant &v, int tid, int warm, in
             pkts[i].resize(sizeof(hd) + surf);
             memcpy(pkts[i].data(), &hd, sizeof(hd));
             memcpy(pkts[i].data() + sizeof(hd), host_surf.data(), surf);
+            if (!strcmp(v.out, "registered")) jm_nvdec_memory_register_host(pkts[i].data(), (int)pkts[i].size(), dec);
         }
     }
     unsigned char *out = nullptr;
@@ -151,7 +152,10 @@ static void run_handle(const Options &o, const Variant &v, int tid, int warm, in
     res->frames = fetched - f0;
     res->seconds = std::chrono::duration<double>(t1 - t0).count();
     while (!jm_nvdec_is_exit(dec)) step(nullptr, 0);                      /* flush, test_nv_dec.cpp:232-246 */
-    if (!strcmp(v.out, "registered")) jm_nvdec_memory_unregister_host(out, dec);
+    if (!strcmp(v.out, "registered")) {
+        jm_nvdec_memory_unregister_host(out, dec);
+        if (!v.device_in) for (int i = 0; i < NS; i++) jm_nvdec_memory_unregister_host(pkts[i].data(), dec);
+    }
     if (pinned) jm_nvdec_memory_release_host(pinned, dec);
     jm_nvdec_deinit(dec);
     if (!pinned) free(out);
