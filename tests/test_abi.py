@@ -179,3 +179,29 @@ def test_headers_are_valid_c99_and_cxx(tmp_path):
         assert p.returncode == 1 and "no CUDA device" in p.stderr       # fails loudly, no CPU fallback
     else:
         assert p.returncode == 0 and "decoded 8 of 8 frames, exit=1" in p.stdout
+
+
+def test_nvdec_handle_options_without_a_device(lib):
+    """Host-side logic of the jm_nvdec_* extensions that needs no CUDA: option names and ranges, defaults from the
+    environment, calls on a handle that was never initialised."""
+    h = lib.jm_nvdec_create_handle()
+    assert h
+    assert lib.jm_nvdec_set_display_delay(0, h) == 0 and lib.jm_nvdec_set_display_delay(20, h) == 0
+    assert lib.jm_nvdec_set_display_delay(-1, h) == -1 and lib.jm_nvdec_set_display_delay(21, h) == -1
+    for name, good, bad in ((b"display_delay", 3, 99), (b"copy_threads", 2, 17), (b"map_limit", 8, 9), (b"map_limit", 1, 0)):
+        assert lib.jm_nvdec_set_option(name, good, h) == 0, name
+        assert lib.jm_nvdec_set_option(name, bad, h) == -1, name
+    assert lib.jm_nvdec_set_option(b"lazy_pin", 1, h) == 0
+    assert lib.jm_nvdec_set_option(b"no_such_option", 1, h) == -1
+    assert lib.jm_nvdec_set_option(None, 1, h) == -1
+    got = C.c_int(5)
+    assert lib.jm_nvdec_decode_frame(None, 0, C.byref(got), h) == 0 and got.value == 0      # never initialised: swallowed like nv_dec.cpp:491-493
+    n = C.c_int(16)
+    buf = (C.c_uint8 * 16)()
+    assert lib.jm_nvdec_output_frame(buf, C.byref(n), h) == -1 and n.value == 16             # no frame: -1, *out_len untouched
+    p = C.c_void_p()
+    assert lib.jm_nvdec_output_frame_ref(C.byref(p), C.byref(n), h) == -1
+    assert lib.jm_nvdec_memory_register_host(buf, 16, h) == -1                               # no context yet
+    assert lib.jm_nvdec_dropped_frames(h) == 0 and lib.jm_nvdec_launch_count(h) == 0
+    assert lib.jm_nvdec_deinit(h) == 0
+    lib.jmc_reload_env()                                                                     # harmless without a device

@@ -56,3 +56,30 @@ def test_product_arm_line():
     c = d["clocks"]
     assert c["sm_max_mhz"] and not ({"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(c["reasons"]))
     assert d["verified_bit_exact"] is True
+
+
+def test_both_arms_carry_the_same_config_and_traffic_is_tied_to_the_sources(tmp_path, monkeypatch):
+    """`config` comes from one function for both arms (the driver compares the two objects), and roofline.traffic is
+    reported only while the recorded ncu capture belongs to the kernel sources in the tree."""
+    sys.path.insert(0, ROOT)
+    import bench
+    a = bench.run_config("nv12_to_i420_1080p_x300_pitch2048", 4)
+    assert a == bench.run_config("nv12_to_i420_1080p_x300_pitch2048", 4)
+    assert a["workload"] == "nv12_to_i420_1080p_x300_pitch2048" and a["frames_per_step_per_gpu"] == 300 and "L2" in a["l2"]
+    assert "4 GPU" in a["parallelism"] and "model" not in a
+    h = bench.kernel_sources_sha256()
+    assert len(h) == 64
+    t, prov = bench.recorded_traffic("nv12_to_i420_1080p_x300_pitch2048")
+    assert prov["status"] in ("current", "stale: kernel sources changed since the capture", "no ncu capture recorded for this workload")
+    assert (t is not None) == (prov["status"] == "current")
+    # a capture taken from other sources is never reported
+    fake = {"nv12_to_i420_1080p_x300_pitch2048": {"traffic": 123, "kernel": "k", "capture": "c", "git": "g", "when": "w", "sources_sha256": "0" * 64}}
+    (tmp_path / "profiles").mkdir()
+    (tmp_path / "profiles" / "traffic.json").write_text(json.dumps(fake))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "kernel_sources_sha256", lambda: h)
+    t, prov = bench.recorded_traffic("nv12_to_i420_1080p_x300_pitch2048")
+    assert t is None and prov["status"].startswith("stale")
+    fake["nv12_to_i420_1080p_x300_pitch2048"]["sources_sha256"] = h
+    (tmp_path / "profiles" / "traffic.json").write_text(json.dumps(fake))
+    assert bench.recorded_traffic("nv12_to_i420_1080p_x300_pitch2048")[0] == 123
