@@ -147,7 +147,11 @@ struct copy_pool {
 
     void ensure_started()
     {
-        for (int i = (int)workers.size(); i < want_threads; i++) workers.emplace_back([this] { worker(); });
+        try {
+            for (int i = (int)workers.size(); i < want_threads; i++) workers.emplace_back([this] { worker(); });
+        } catch (...) {
+            want_threads = (int)workers.size();            /* no more threads to be had: copy with the ones we have */
+        }
     }
 
     void shutdown()
@@ -280,6 +284,7 @@ struct nvdec_b200 {
     uint8_t *h_edge = nullptr;      /* pinned bounce buffer for the unregistered < 4 KB edges of such buffers: 2 x 4 KB out, 2 x 4 KB in */
     copy_pool copier;
     int copy_threads = 0;
+    bool stage_linear = false;      /* pageable payloads: compact staging rows + 2-D H2D (JMC_NVDEC_STAGE_LINEAR=1: pitched staging + one linear H2D) */
 
     int disp_w = 0, disp_h = 0;     /* dec_create_info.ulTargetWidth/Height */
     uint32_t num_frames = 0, dropped = 0;
@@ -873,7 +878,12 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
             } else {
                 /* pageable payload: compact the rows into this surface's pinned staging buffer (the call returns when
                  * in_buf has been read) and let the H2D run behind us */
-                const size_t need = wbytes * rows;
+                /* default: compact rows in the staging buffer + a 2-D H2D that adds the pitch (6 % fewer bytes on the link).
+                 * JMC_NVDEC_STAGE_LINEAR=1: staging in the surface's pitch + one linear H2D -- measured the same within the
+                 * run-to-run noise (profiles/r2_stage_linear_ab.txt): enqueueing the 2-D copy is not what this path waits for */
+                const bool linear = c->stage_linear;
+                const size_t spitch = linear ? (size_t)h.pitch : wbytes;
+                const size_t need = spitch * rows;
                 if (need > c->stage_bytes) {
                     jmc_ctx_sync(c->ctx);
                     for (int i = 0; i < NVDEC_MAX_FRAMES; i++) if (c->h_stage[i]) { cudaFreeHost(c->h_stage[i]); c->h_stage[i] = nullptr; }
@@ -882,15 +892,17 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
                 if (!c->h_stage[slot] && cudaHostAlloc((void **)&c->h_stage[slot], c->stage_bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return -1; }
                 if (!c->stage_done[slot] && cudaEventCreateWithFlags(&c->stage_done[slot], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
                 if (c->stage_used[slot]) cudaEventSynchronize(c->stage_done[slot]);        /* ten uploads ago: long done */
-                /* rows are compacted by the copy threads in a few pieces; each piece's H2D starts while the next is
-                 * being compacted */
+                /* rows are copied into the staging buffer by the copy threads in a few pieces; each piece's H2D starts while the
+                 * next is being copied */
                 const size_t pieces = (need >= (2u << 20) && c->delay == 0) ? 4 : 1, prow = (rows + pieces - 1) / pieces;
                 for (size_t r0 = 0; r0 < rows; r0 += prow) {
                     const size_t nr = rows - r0 < prow ? rows - r0 : prow;
-                    copy_job cj = { c->h_stage[slot] + r0 * wbytes, wbytes, src + r0 * (size_t)h.pitch, (size_t)h.pitch, wbytes, nr, nr, 1 };
+                    copy_job cj = { c->h_stage[slot] + r0 * spitch, spitch, src + r0 * (size_t)h.pitch, (size_t)h.pitch, wbytes, nr, nr, 1 };
                     c->copier.copy(cj);
-                    if (cudaMemcpy2DAsync(c->pool[slot] + r0 * (size_t)h.pitch, (size_t)h.pitch, c->h_stage[slot] + r0 * wbytes, wbytes, wbytes, nr,
-                                          cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return -1; }
+                    cudaError_t e2 = linear
+                        ? cudaMemcpyAsync(c->pool[slot] + r0 * (size_t)h.pitch, c->h_stage[slot] + r0 * spitch, (nr - 1) * spitch + wbytes, cudaMemcpyHostToDevice, st)
+                        : cudaMemcpy2DAsync(c->pool[slot] + r0 * (size_t)h.pitch, (size_t)h.pitch, c->h_stage[slot] + r0 * wbytes, wbytes, wbytes, nr, cudaMemcpyHostToDevice, st);
+                    if (e2 != cudaSuccess) { cudaGetLastError(); return -1; }
                 }
                 cudaEventRecord(c->stage_done[slot], st);
                 c->stage_used[slot] = true;
@@ -1082,8 +1094,8 @@ extern "C" {
 
 handle_nvdec jm_nvdec_create_handle(void)
 {
-    nvdec_b200 *c = new (std::nothrow) nvdec_b200();                   /* new + memset, nv_dec.cpp:54-60 */
-    if (!c) return nullptr;
+    nvdec_b200 *c = nullptr;
+    try { c = new nvdec_b200(); } catch (...) { return nullptr; }    /* new + memset, nv_dec.cpp:54-60; nothing may throw across the C ABI */
     c->device = env_int("JMC_DEVICE", 0, 0, 1023);
     c->delay = env_int("JMC_NVDEC_DISPLAY_DELAY", 0, 0, DELAY_MAX);
     /* helper threads for copies from / to PAGEABLE caller buffers (started only when such a copy happens):
@@ -1092,6 +1104,7 @@ handle_nvdec jm_nvdec_create_handle(void)
     c->lazy_pin = env_int("JMC_NVDEC_LAZY_PIN", 0, 0, 1);
     c->map_limit = env_int("JMC_NVDEC_MAP_LIMIT", MAP_LIMIT_MAX, 1, MAP_LIMIT_MAX);
     c->max_inflight = env_int("JMC_NVDEC_MAX_INFLIGHT", 2, 1, 16);
+    c->stage_linear = env_int("JMC_NVDEC_STAGE_LINEAR", 0, 0, 1) != 0;
     if (g_dev_inflight_max < 0) g_dev_inflight_max = env_int("JMC_NVDEC_DEVICE_INFLIGHT", 4, 1, 64);
     g_live_handles.fetch_add(1);
     return c;
@@ -1177,7 +1190,22 @@ int jm_nvdec_deinit(handle_nvdec handle)
     return 0;
 }
 
+static int decode_frame_impl(unsigned char *in_buf, int in_data_len, int *got_frame, handle_nvdec handle);
+static int output_frame_impl(unsigned char *out_buf, int *out_len, handle_nvdec handle);
+
 int jm_nvdec_decode_frame(unsigned char *in_buf, int in_data_len, int *got_frame, handle_nvdec handle)
+{
+    try { return decode_frame_impl(in_buf, in_data_len, got_frame, handle); }
+    catch (...) { jmc_set_error("jm_nvdec_decode_frame: out of host memory"); if (got_frame) *got_frame = 0; return -1; }
+}
+
+int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec handle)
+{
+    try { return output_frame_impl(out_buf, out_len, handle); }
+    catch (...) { jmc_set_error("jm_nvdec_output_frame: out of host memory"); return -1; }
+}
+
+static int decode_frame_impl(unsigned char *in_buf, int in_data_len, int *got_frame, handle_nvdec handle)
 {
     nvdec_b200 *c = (nvdec_b200 *)handle;
     if (got_frame) *got_frame = 0;
@@ -1221,7 +1249,7 @@ int jm_nvdec_decode_frame(unsigned char *in_buf, int in_data_len, int *got_frame
     return 0;
 }
 
-int jm_nvdec_output_frame(unsigned char *out_buf, int *out_len, handle_nvdec handle)
+static int output_frame_impl(unsigned char *out_buf, int *out_len, handle_nvdec handle)
 {
     nvdec_b200 *c = (nvdec_b200 *)handle;
     if (!c || c->cur < 0) return -1;                           /* nv_dec.cpp:757-758 */
