@@ -48,6 +48,7 @@ struct jmc_env_flags {
     int rgb_flat;             /* -1 unset (heuristic), 0 off, 1 on */
     int rgb2_flat;            /* same, for the RGB24 -> NV12 kernel */
     bool pad_zero;            /* JMC_PAD_ZERO=1: as if every job carried JMC_JOB_PAD_ZERO (measurements) */
+    int rgb_bulk_pairs;       /* JMC_RGB_BULK_PAIRS: row pairs per CTA of the re-aligning bulk colour kernel (0: two for the fused op, RGB alone stays on the warp-per-task kernel) */
     int brows_rows;           /* > 0: rows per tile of the bulk-loaded row kernels (tuning) */
 };
 const jmc_env_flags &jmc_env();

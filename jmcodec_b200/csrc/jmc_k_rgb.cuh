@@ -403,6 +403,10 @@ struct RgbBulkParams {
     uint32_t row_pairs;
     uint32_t segs;            /* column segments per row pair */
     uint32_t seg_w;           /* pixels per segment (multiple of 32); the last one takes the remainder */
+    /* rgb_bulk_pairs_kernel only */
+    uint32_t pairs;           /* row pairs per CTA (segs == 1) */
+    uint32_t groups;          /* ceil(row_pairs / pairs) */
+    FastDiv upr_div;          /* division by the 16-pixel units per row */
 };
 
 constexpr int RGB_BULK_THREADS = 128;
@@ -510,6 +514,108 @@ __global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_kernel(const __grid
             const uint32_t half = ((3 * w) >> 1) & ~15u;               /* each RGB row is shared by two warps */
             const uint32_t b0 = warp < 2 ? 0u : half, b1 = warp < 2 ? half : 3 * w;
             warp_store_shifted(rgbp + (size_t)row * p.rgb_pitch + b0, s_rgb + (size_t)row * 3 * sw + b0, b1 - b0, lane);
+        }
+    }
+}
+
+/* The re-aligning variant (!ALIGNED above) with `pairs` consecutive row pairs of whole rows per CTA: every row of the
+ * tile arrives on one barrier, the units of all pairs are dealt out to the threads as one flat range, and each warp
+ * writes whole rows. */
+__global__ void __launch_bounds__(RGB_BULK_THREADS) rgb_bulk_pairs_kernel(const __grid_constant__ RgbBulkParams p)
+{
+    extern __shared__ __align__(128) uint8_t rs[];
+    __shared__ __align__(8) uint64_t bar;
+    const uint32_t per_frame = p.groups * p.segs;
+    const uint32_t f = blockIdx.x / per_frame;
+    const uint32_t t = blockIdx.x - f * per_frame;
+    const uint32_t grp = t / p.segs, seg = t - grp * p.segs;
+    const uint32_t W = (uint32_t)p.width, h = (uint32_t)p.height, cw = W >> 1, ch = h >> 1;
+    const uint32_t x0 = seg * p.seg_w;                     /* first pixel of this segment */
+    const uint32_t w = min(p.seg_w, W - x0);               /* pixels in this segment (even) */
+    const uint32_t lw = (w + 15) & ~15u;                   /* bytes loaded per row */
+    const uint32_t pairs = p.pairs;
+    const uint32_t rp0 = grp * pairs;                      /* first row pair of this CTA */
+    const uint32_t np = min(pairs, p.row_pairs - rp0);     /* row pairs of this CTA */
+    const uint8_t *sp = frame_ptr(p.surf, f);
+    uint8_t *rgb0 = frame_ptr(p.rgb, f) + 3 * (size_t)x0;
+    const uint32_t sw = p.seg_w;                           /* shared-memory row stride */
+    const size_t pair_bytes = 10 * (size_t)sw;             /* per row pair: 2*sw luma, sw chroma, 6*sw RGB, sw U + V (fused) */
+    if (threadIdx.x == 0) {
+        mbar_init(&bar, 1);
+        uint32_t rows = 0;
+        for (uint32_t i = 0; i < np; i++) rows += (2 * (rp0 + i) + 1 < h) ? 3u : 2u;
+        mbar_expect_tx(&bar, rows * lw);
+        for (uint32_t i = 0; i < np; i++) {
+            const uint32_t rp = rp0 + i, y0 = 2 * rp, cy = min(rp, ch - 1);
+            uint8_t *s_y = rs + i * pair_bytes;
+            const uint8_t *yrow = sp + p.y_off + (size_t)y0 * p.pitch + x0;
+            bulk_g2s(s_y, yrow, lw, &bar);
+            if (y0 + 1 < h) bulk_g2s(s_y + sw, yrow + p.pitch, lw, &bar);
+            bulk_g2s(s_y + 2 * (size_t)sw, sp + p.uv_off + (size_t)cy * p.pitch + x0, lw, &bar);
+        }
+    }
+    __syncthreads();
+    mbar_wait_cta(&bar, 0);
+    const uint32_t upr = lw >> 4;
+    for (uint32_t u = threadIdx.x; u < np * upr; u += RGB_BULK_THREADS) {
+        const uint32_t i = pairs > 1 ? fast_div(u, p.upr_div) : 0u;
+        const uint32_t unit = u - i * upr;
+        const uint32_t rp = rp0 + i;
+        const bool two = 2 * rp + 1 < h, do_uv = p.fused && rp < ch;
+        uint8_t *s_y = rs + i * pair_bytes, *s_uv = s_y + 2 * (size_t)sw, *s_rgb = s_y + 3 * (size_t)sw;
+        uint8_t *s_u = s_y + 9 * (size_t)sw, *s_v = s_u + (sw >> 1);
+        const uint4 uv = *(const uint4 *)(s_uv + unit * 16);
+        const uint32_t uvw[4] = {uv.x, uv.y, uv.z, uv.w};
+        int cr[8], cg[8], cb[8];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            cr[2 * j] = dp2a_lo(COEF_RV, uvw[j], RGB_CR);  cr[2 * j + 1] = dp2a_hi(COEF_RV, uvw[j], RGB_CR);
+            cg[2 * j] = dp2a_lo(COEF_GUV, uvw[j], RGB_CG); cg[2 * j + 1] = dp2a_hi(COEF_GUV, uvw[j], RGB_CG);
+            cb[2 * j] = dp2a_lo(COEF_BU, uvw[j], RGB_CB);  cb[2 * j + 1] = dp2a_hi(COEF_BU, uvw[j], RGB_CB);
+        }
+        if (do_uv) {
+            uint2 uu, vv;
+            uu.x = __byte_perm(uv.x, uv.y, 0x6420); vv.x = __byte_perm(uv.x, uv.y, 0x7531);
+            uu.y = __byte_perm(uv.z, uv.w, 0x6420); vv.y = __byte_perm(uv.z, uv.w, 0x7531);
+            *(uint2 *)(s_u + unit * 8) = uu;
+            *(uint2 *)(s_v + unit * 8) = vv;
+        }
+#pragma unroll
+        for (int row = 0; row < 2; row++) {
+            if (row == 1 && !two) break;
+            const uint4 yy = *(const uint4 *)(s_y + (size_t)row * sw + unit * 16);
+            const uint32_t yw[4] = {yy.x, yy.y, yy.z, yy.w};
+            uint32_t o[12];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                rgb4(yw[j], cr[2 * j], cg[2 * j], cb[2 * j], cr[2 * j + 1], cg[2 * j + 1], cb[2 * j + 1], o + 3 * j);
+            uint4 *d = (uint4 *)(s_rgb + (size_t)row * 3 * sw + unit * 48);
+            d[0] = make_uint4(o[0], o[1], o[2], o[3]);
+            d[1] = make_uint4(o[4], o[5], o[6], o[7]);
+            d[2] = make_uint4(o[8], o[9], o[10], o[11]);
+        }
+    }
+    {
+        /* whole rows are dealt out to the warps.  Jobs per row pair: RGB row 0, RGB row 1 and, fused, luma row 0, luma
+         * row 1, U row, V row.  Two row pairs give the four warps one RGB row each (RGB alone) or 4.5 w bytes each
+         * (fused: 3w + w/2 + w twice, w + 3w + w/2 twice); splitting rows between warps only adds partial head / tail
+         * stores (profiles/r2_rgb_tile_shape_sweep.txt). */
+        __syncthreads();
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t jobs_per_pair = p.fused ? 6u : 2u;
+        uint8_t *tp = p.fused ? frame_ptr(p.tight, f) : nullptr;
+        for (uint32_t j = warp; j < np * jobs_per_pair; j += RGB_BULK_THREADS / 32) {
+            const uint32_t i = j / jobs_per_pair, kind = j - i * jobs_per_pair;
+            const uint32_t rp = rp0 + i, y0 = 2 * rp;
+            const bool two = y0 + 1 < h, do_uv = rp < ch;
+            uint8_t *s_y = rs + i * pair_bytes, *s_rgb = s_y + 3 * (size_t)sw, *s_u = s_y + 9 * (size_t)sw, *s_v = s_u + (sw >> 1);
+            uint8_t *rgbp = rgb0 + (size_t)y0 * p.rgb_pitch;
+            if (kind == 0) warp_store_shifted(rgbp, s_rgb, 3 * w, lane);
+            else if (kind == 1) { if (two) warp_store_shifted(rgbp + p.rgb_pitch, s_rgb + 3 * (size_t)sw, 3 * w, lane); }
+            else if (kind == 2) warp_store_shifted(tp + (size_t)y0 * W + x0, s_y, w, lane);
+            else if (kind == 3) { if (two) warp_store_shifted(tp + (size_t)(y0 + 1) * W + x0, s_y + sw, w, lane); }
+            else if (kind == 4) { if (do_uv) warp_store_shifted(tp + p.u_off + (size_t)rp * cw + (x0 >> 1), s_u, w >> 1, lane); }
+            else { if (do_uv) warp_store_shifted(tp + p.v_off + (size_t)rp * cw + (x0 >> 1), s_v, w >> 1, lane); }
         }
     }
 }

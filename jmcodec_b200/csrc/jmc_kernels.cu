@@ -400,8 +400,13 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
         /* ... and for RGB alone on narrow frames the warp-per-task kernel is ahead even when everything is aligned
          * (profiles/r1c_rgb_bulk_vs_vector.txt: 1536 wide 1.03 vs 0.99, 1376 wide 0.95 vs 0.92; from 1920 wide on the
          * bulk kernel wins, 1.02 vs 1.00) */
+        /* row pairs per CTA of the re-aligning variant (!aligned).  Measured (profiles/r2_rgb_tile_shape_sweep.txt): two
+         * pairs - one whole-row store job per warp - lift the fused op on 1366 / 1080 / 854-wide frames from 0.75 / 0.68 /
+         * 0.59 to 0.88 / 0.85 / 0.75 of peak; three and more lose it again to occupancy.  RGB alone stays on the
+         * warp-per-task kernel (0.85 / 0.91 / 0.78 vs 0.83 / 0.82 / 0.74) unless JMC_RGB_BULK_PAIRS=n asks (A/B). */
+        const int want_pairs = jmc_env().rgb_bulk_pairs;
         const bool bulk_pays = fused || j->width >= 1664 || jmc_env().rgb_bulk_always;
-        if (ok && ((aligned && bulk_pays) || (surf_ok && (fused || jmc_env().rgb_bulk_always)))) {
+        if (ok && ((aligned && bulk_pays) || (surf_ok && (fused || jmc_env().rgb_bulk_always || (!aligned && want_pairs > 0))))) {
             RgbBulkParams b;
             b.surf = p.surf; b.tight = p.tight; b.rgb = p.rgb;
             b.n_frames = p.n_frames; b.width = p.width; b.height = p.height; b.pitch = p.pitch;
@@ -414,15 +419,29 @@ static int launch_rgb(jmc_ctx *ctx, const jmc_job *j, cudaStream_t stream)
             b.segs = ((uint32_t)j->width + seg_max - 1) / seg_max;
             b.seg_w = ((((uint32_t)j->width + b.segs - 1) / b.segs) + 31) & ~31u;
             b.segs = ((uint32_t)j->width + b.seg_w - 1) / b.seg_w;
-            const uint64_t ctas = (uint64_t)b.row_pairs * b.segs * b.n_frames;
-            const size_t smem = (size_t)b.seg_w * 10 + 64;           /* + spare chunks read by the re-aligning stores */
+            /* whole unaligned rows: two row pairs per CTA (rgb_bulk_pairs_kernel), while they fit ~56 KB (4 CTAs per SM) */
+            b.pairs = 1;
+            if (!aligned && b.segs == 1 && want_pairs != 1) {
+                b.pairs = want_pairs > 1 ? (uint32_t)want_pairs : 2u;
+                while (b.pairs > 1 && (size_t)b.pairs * b.seg_w * 10 + 64 > 56 * 1024) b.pairs--;
+                if (b.pairs > b.row_pairs) b.pairs = b.row_pairs;
+            }
+            b.groups = (b.row_pairs + b.pairs - 1) / b.pairs;
+            b.upr_div = make_fastdiv(((std::min<uint32_t>(b.seg_w, (uint32_t)j->width) + 15) & ~15u) >> 4);
+            const uint64_t ctas = (uint64_t)b.groups * b.segs * b.n_frames;
+            const size_t smem = (size_t)b.pairs * b.seg_w * 10 + 64; /* + spare chunks read by the re-aligning stores */
             if (ctas <= 0x7fffffffull && smem <= 100 * 1024) {
 #define JMC_RGB_BULK(AL)                                                                                          \
     do {                                                                                                          \
         JMC_SMEM_ONCE(100 * 1024, rgb_bulk_kernel<AL>);                                                           \
         rgb_bulk_kernel<AL><<<(uint32_t)ctas, RGB_BULK_THREADS, smem, stream>>>(b);                               \
     } while (0)
-                if (aligned) JMC_RGB_BULK(true); else JMC_RGB_BULK(false);
+                if (aligned) JMC_RGB_BULK(true);
+                else if (b.pairs == 1) JMC_RGB_BULK(false);
+                else {
+                    JMC_SMEM_ONCE(100 * 1024, rgb_bulk_pairs_kernel);
+                    rgb_bulk_pairs_kernel<<<(uint32_t)ctas, RGB_BULK_THREADS, smem, stream>>>(b);
+                }
 #undef JMC_RGB_BULK
                 JMC_CUDA(cudaGetLastError());
                 ctx->launches++;

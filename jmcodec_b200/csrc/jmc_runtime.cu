@@ -126,6 +126,7 @@ static void env_load()
     f.rgb_flat = env_tri("JMC_RGB_FLAT");
     f.rgb2_flat = env_tri("JMC_RGB2_FLAT");
     f.pad_zero = env_on("JMC_PAD_ZERO");
+    f.rgb_bulk_pairs = getenv("JMC_RGB_BULK_PAIRS") ? atoi(getenv("JMC_RGB_BULK_PAIRS")) : 0;
     f.brows_rows = getenv("JMC_BROWS_ROWS") ? atoi(getenv("JMC_BROWS_ROWS")) : 0;
     g_env = f;
     g_env_loaded = true;

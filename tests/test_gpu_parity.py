@@ -286,13 +286,28 @@ def test_random_widths_rgb_on_aligned_surfaces(ctx, seed, always, flat, monkeypa
         monkeypatch.setenv("JMC_RGB_BULK_ALWAYS", "1")
     if flat != "default":
         monkeypatch.setenv("JMC_RGB_FLAT", flat)
+    _random_widths_rgb(ctx, 4000 + seed)
+
+
+@pytest.mark.parametrize("pairs", ["0", "1", "2", "3", "4", "7"])
+@pytest.mark.parametrize("seed", range(2))
+def test_rgb_bulk_tiles_of_several_row_pairs(ctx, seed, pairs, monkeypatch):
+    """JMC_RGB_BULK_PAIRS=n: the re-aligning bulk-loaded kernel takes n row pairs per CTA (frames whose rows are not
+    16-byte multiples; 0 = the library's choice: two for the fused op, RGB24 alone on the warp-per-task kernel; 1 =
+    the one-pair kernel).  Heights that are not a multiple of 2n, odd heights, widths up to the point where n pairs
+    no longer fit and the launch falls back to fewer; RGB24 alone and fused."""
+    monkeypatch.setenv("JMC_RGB_BULK_PAIRS", pairs)
+    _random_widths_rgb(ctx, 4100 + seed, hmax=70)
+
+
+def _random_widths_rgb(ctx, seed, hmax=40):
     chk = oracle.best()
-    rng = np.random.default_rng(4000 + seed)
+    rng = np.random.default_rng(seed)
     for it in range(24):
         w = int(rng.integers(2, 2600))
         if it % 4:
             w &= ~1
-        h = int(rng.integers(2, 40))
+        h = int(rng.integers(2, hmax))
         pitch = ((w + 15) & ~15) + 16 * int(rng.integers(0, 3))
         kt, kr = int(rng.integers(0, 16)), int(rng.integers(0, 16))
         surf = synth.nv12_surface(w, h, pitch, 29, w * 7 + h)
