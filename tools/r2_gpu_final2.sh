@@ -2,7 +2,7 @@
 # (recorded before the bench so that its line carries roofline.traffic), bench, the odd sizes, the pairs sweep
 python -m pytest tests -m gpu -q > gpurun_out/r2_final_pytest_gpu.log 2>&1; tail -3 gpurun_out/r2_final_pytest_gpu.log
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_final_smoke.log 2>&1; tail -1 gpurun_out/r2_final_smoke.log
-timeout 200 compute-sanitizer --tool racecheck --log-file gpurun_out/r2_sanitizer_racecheck_pairs.log python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "several_row_pairs and (0-0 or 2-0 or 3-1)" 2>&1 | tail -2
+timeout 200 compute-sanitizer --tool racecheck --log-file gpurun_out/r2_sanitizer_racecheck_pairs.log python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "several_row_pairs and (0-0 or 0-2 or 1-3)" 2>&1 | tail -2
 grep -c "RACECHECK SUMMARY: 0 hazards" gpurun_out/r2_sanitizer_racecheck_pairs.log
 for wl in nv12_to_i420_1080p_x300_pitch2048:bulk_planes nv12_to_i420_4k_x64_pitch4096:bulk_planes i420_to_nv12_1080p_x300_pitch2048:bulk_planes nv12_to_rgb24_4k_x64_pitch4096:rgb nv12_to_i420_rgb24_4k_x64_pitch4096:rgb nv12_to_argb32_4k_x64_pitch4096:rgb; do
   w="${wl%%:*}"; k="${wl##*:}"

@@ -35,7 +35,7 @@ def main():
         "traffic": int(round(sum(vals) / len(vals))), "launches_averaged": len(vals), "kernel": sorted(names)[0] if len(names) == 1 else sorted(names),
         "capture": os.path.relpath(path, ROOT),
         "git": subprocess.run(["git", "-C", ROOT, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip(),
-        "when": datetime.datetime.utcnow().strftime("%Y-%m-%dT%H:%MZ"),
+        "when": datetime.datetime.now(datetime.timezone.utc).strftime("%Y-%m-%dT%H:%MZ"),
         "sources_sha256": bench.kernel_sources_sha256(),
     }
     p = os.path.join(ROOT, "profiles", "traffic.json")
