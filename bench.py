@@ -341,6 +341,22 @@ def device_only(ctx, name, rank, iters, warmup):
     return res
 
 
+def ratios_vs_cpu(cpu, value, e2e_value, decode_path):
+    """This run's GPU figures over this run's CPU baseline (the reference's loop on all host cores of the same box).
+    `e2e` is the honest headline: host buffers both ways on both sides.  The driver's own e2e ratio uses the separate
+    `--impl reference` run; this is the same comparison inside one process.  Never raises (it decorates the line)."""
+    try:
+        base = float(cpu["value"])
+        if not base > 0:
+            return None
+        return {"e2e": e2e_value / base,
+                "e2e_device_resident_input": decode_path["value"] / base if decode_path else None,
+                "device_only": value / base,
+                "basis": "cpu_baseline.value of this run: %s threads, kind %s" % (cpu.get("cores"), cpu.get("kind"))}
+    except Exception:                   # noqa: BLE001
+        return None
+
+
 def dropin_api_fps(device, w=1920, h=1080, pitch=2048, frames=400):
     """Frames/s of the per-frame drop-in API, called as test_nv_dec.cpp:215-218 calls it (jm_nvdec_decode_frame
     then jm_nvdec_output_frame, one frame at a time, one handle per thread), measured by tools/jm_dropin -- plain
@@ -614,6 +630,7 @@ def main():
         }
         if cpu:
             line["cpu_baseline"] = cpu
+            line["vs_cpu_baseline_all_cores"] = ratios_vs_cpu(cpu, value, e2e_value, decode_path)
         if kernels:
             line["kernels"] = kernels
         if batch_sweep:

@@ -389,12 +389,17 @@ int acquire_slot(nvdec_b200 *c, int w, int h)
         idx = n;
     }
     ring_slot &s = c->ring[idx];
-    if (!s.converted) {
-        if (cudaEventCreateWithFlags(&s.converted, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
-        if (cudaEventCreateWithFlags(&s.direct, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
-        for (int i = 0; i < MAX_CHUNKS; i++)
-            if (cudaEventCreateWithFlags(&s.delivered[i], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); return -1; }
-    }
+    /* each event is created once; a slot whose events could not all be created is retried on its next use */
+    auto have = [](cudaEvent_t &e) {
+        if (e) return true;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess) return true;
+        cudaGetLastError();
+        e = nullptr;
+        return false;
+    };
+    if (!have(s.converted) || !have(s.direct)) return -1;
+    for (int i = 0; i < MAX_CHUNKS; i++)
+        if (!have(s.delivered[i])) return -1;
     if (s.d_bytes < need) {                                   /* replaces cuMemAllocHost(pitch*h*3/2), nv_dec.cpp:569 */
         if (s.d_tight) { cudaFree(s.d_tight); s.d_tight = nullptr; s.d_bytes = 0; }   /* cudaFree waits for the device */
         if (cudaMalloc((void **)&s.d_tight, need) != cudaSuccess) { cudaGetLastError(); jmc_set_error("out of device memory for a %dx%d frame", w, h); return -1; }

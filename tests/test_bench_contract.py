@@ -83,3 +83,13 @@ def test_both_arms_carry_the_same_config_and_traffic_is_tied_to_the_sources(tmp_
     fake["nv12_to_i420_1080p_x300_pitch2048"]["sources_sha256"] = h
     (tmp_path / "profiles" / "traffic.json").write_text(json.dumps(fake))
     assert bench.recorded_traffic("nv12_to_i420_1080p_x300_pitch2048")[0] == 123
+
+
+def test_ratios_against_the_cpu_baseline_of_the_same_run():
+    sys.path.insert(0, ROOT)
+    import bench
+    r = bench.ratios_vs_cpu({"value": 20000.0, "cores": 16, "kind": "reference"}, 1.1e6, 15500.0, {"value": 17400.0})
+    assert abs(r["e2e"] - 0.775) < 1e-9 and abs(r["e2e_device_resident_input"] - 0.87) < 1e-9 and abs(r["device_only"] - 55.0) < 1e-9
+    assert "16 threads" in r["basis"]
+    assert bench.ratios_vs_cpu({"value": 20000.0}, 1.0, 1.0, None)["e2e_device_resident_input"] is None
+    assert bench.ratios_vs_cpu({"value": 0}, 1.0, 1.0, None) is None and bench.ratios_vs_cpu({}, 1.0, 1.0, None) is None
