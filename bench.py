@@ -401,6 +401,12 @@ def main():
 
     op, w, h, pitch, n = WORKLOADS[name]
     in_b, out_b, out2_b = io_bytes(op, w, h, pitch)
+    # weak scaling: the job is n frames per GPU, and a rank owns one contiguous slice of the job's frames -- no rank ever
+    # needs another rank's bytes (the same split the world-2 gloo test checks)
+    from jmcodec_b200.shard import frames_for_rank
+    my_frames = frames_for_rank(n * world, rank, world)
+    if len(my_frames) != n:
+        raise SystemExit("bench.py: frame split is not even")
     ctx = J.Ctx(local)
     sampler = ClockSampler(local)
     sampler.start()
