@@ -1235,6 +1235,9 @@ static int decode_frame_impl(unsigned char *in_buf, int in_data_len, int *got_fr
     while (!c->pending.empty()) {
         if (convert_stage(c, false) <= 0) break;
     }
+    /* nothing to announce while pictures wait for a map slot (every mapped surface still belongs to a launch in
+     * flight): wait for those launches rather than hand the caller an empty call it can only repeat */
+    if (c->ready.empty() && !c->pending.empty()) convert_stage(c, true);
     flush_prefetch(c, -1);                                     /* whatever has finished converting meanwhile (uploads take longer than kernels) */
     /* announce at most one frame per call (:455); frames beyond the display delay wait in `ready` */
     if (!c->ready.empty() && ((int)c->ready.size() > c->delay || c->is_eof)) {

@@ -1,0 +1,561 @@
+/*
+ * The library's host layer (jm_nv_dec.cu, jmnv_enc.cu, jmc_runtime.cu -- compiled unchanged) driven through its public
+ * C API on top of the CUDA runtime simulator (fake_cuda/) and an oracle-backed stand-in for the kernels
+ * (fake_launch.cpp).  What this checks that the GPU tests cannot: the stream / event protocol of the delivery code
+ * under the LEAST helpful legal timing (work that runs only when somebody waits for it, or at random moments), every
+ * frame against the oracle, frees and unregistrations under pending work, leaks after deinit, allocation failures at
+ * every allocation site, the caller's current device after every call.  Built with AddressSanitizer + UBSan by
+ * tests/test_host_logic.py.  usage: delivery_sim_test <path of the fake nvcuvid .so> [scenario-filter]
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <random>
+#include <string>
+#include <vector>
+
+#include "cuda_runtime.h"
+#include "jm_nv_dec.h"
+#include "jmc_cuda.h"
+#include "jmnv_enc.h"
+#include "../../oracle/jm_oracle.h"
+
+extern int g_fake_launches, g_fake_frames, g_fake_max_batch;
+static int g_arm_kind = -1, g_arm_k = 0;      /* allocation failure to arm right after the simulator reset */
+
+static int g_fail = 0, g_checks = 0;
+static std::string g_ctx;
+#define CHECK(cond, ...)                                                                                         \
+    do {                                                                                                         \
+        g_checks++;                                                                                              \
+        if (!(cond)) { if (g_fail < 40) { printf("FAIL [%s] line %d: ", g_ctx.c_str(), __LINE__); printf(__VA_ARGS__); printf("\n"); } g_fail++; } \
+    } while (0)
+
+struct geom { int w, h, pitch; };
+
+static void random_bytes(uint8_t *p, size_t n, uint32_t seed)
+{
+    uint64_t x = seed * 0x9E3779B97F4A7C15ull + 0x1234567ull;
+    for (size_t i = 0; i < n; i++) {
+        if ((i & 7) == 0) { x ^= x << 13; x ^= x >> 7; x ^= x << 17; }
+        p[i] = (uint8_t)(x >> (8 * (i & 7)));
+    }
+}
+
+static std::vector<uint8_t> surface(const geom &g, uint32_t seed)
+{
+    const size_t bytes = (size_t)g.pitch * g.h * 3 / 2;                   /* nv_dec.cpp:453 */
+    std::vector<uint8_t> s(bytes, 0xCD);
+    const size_t rows = g.pitch ? bytes / (size_t)g.pitch : 0;
+    for (size_t y = 0; y < rows; y++) random_bytes(&s[y * g.pitch], (size_t)g.w, seed * 4099u + (uint32_t)y);
+    return s;
+}
+
+static size_t written(int fmt, int w, int h) { return fmt == 0 ? (size_t)w * h + (size_t)(h >> 1) * w : (size_t)w * h + 2 * (size_t)(w >> 1) * (h >> 1); }
+
+static std::vector<uint8_t> expected(const std::vector<uint8_t> &surf, const geom &g, int fmt)
+{
+    std::vector<uint8_t> out((size_t)g.w * g.h * 3 / 2 + 8, 0xA5);
+    int len = g.w * g.h * 3 / 2;
+    if (len > 0) jmo_nvdec_output_frame(surf.data(), g.pitch, g.w, g.h, fmt, 1, out.data(), &len);
+    return out;
+}
+
+static void sim_clean(const fake_cuda_counts &base, bool streams_may_grow)
+{
+    for (auto &e : fake_cuda_take_errors()) CHECK(false, "simulator: %s", e.c_str());
+    const fake_cuda_counts now = fake_cuda_live();
+    CHECK(now.device == base.device, "device allocations leaked: %zu -> %zu", base.device, now.device);
+    CHECK(now.pinned == base.pinned, "pinned allocations leaked: %zu -> %zu", base.pinned, now.pinned);
+    CHECK(now.registered == base.registered, "host registrations leaked: %zu -> %zu", base.registered, now.registered);
+    CHECK(now.events == base.events, "events leaked: %zu -> %zu", base.events, now.events);
+    CHECK(now.streams == base.streams || (streams_may_grow && now.streams == base.streams + 1), "streams leaked: %zu -> %zu", base.streams, now.streams);
+}
+
+enum { IN_PAGEABLE, IN_PINNED, IN_REGISTERED, IN_DEVICE, IN_DEVICE_SYNC, IN_DEVICE_EVENT };
+enum { OUT_PAGEABLE, OUT_PINNED, OUT_REGISTERED, OUT_LAZY_PIN, OUT_DEVICE, OUT_REF };
+
+struct raw_cfg {
+    geom g; int fmt, delay, in_kind, out_kind, threads, frames, device;
+    bool tolerate_errors;           /* allocation-failure runs: frames may be missing, calls may fail */
+};
+
+/* One RAW-front-end session, the reference's calling loop (test_nv_dec.cpp:207-258): decode, fetch if a frame is
+ * announced, flush at the end.  Returns the number of frames delivered. */
+static int run_raw(const raw_cfg &c, unsigned seed, int laziness)
+{
+    const int n_dev = c.device + 1 > 2 ? c.device + 1 : 2;
+    fake_cuda_reset(seed, laziness, n_dev);
+    cudaSetDevice(0);
+    const fake_cuda_counts base = fake_cuda_live();
+    if (g_arm_kind >= 0) fake_cuda_fail_alloc(g_arm_kind, g_arm_k);
+    const geom &g = c.g;
+    const size_t surf_bytes = (size_t)g.pitch * g.h * 3 / 2, tight = (size_t)g.w * g.h * 3 / 2, wr = written(c.fmt, g.w, g.h);
+    handle_nvdec h = jm_nvdec_create_handle();
+    CHECK(h != nullptr, "create_handle");
+    if (!h) return 0;
+    jm_nvdec_set_device(c.device, h);
+    jm_nvdec_set_option("display_delay", c.delay, h);
+    jm_nvdec_set_option("copy_threads", c.threads, h);
+    if (c.out_kind == OUT_LAZY_PIN) jm_nvdec_set_option("lazy_pin", 1, h);
+    int r = jm_nvdec_init(JM_NVDEC_CODEC_RAW_NV12, c.fmt, nullptr, 0, h);
+    if (r != 0) {
+        CHECK(c.tolerate_errors, "init failed: %d (%s)", r, jmc_last_error());
+        jm_nvdec_deinit(h);
+        sim_clean(base, false);
+        return 0;
+    }
+    /* caller-side buffers */
+    const size_t pkt_bytes = sizeof(jm_nvdec_raw_packet_ex) + surf_bytes;
+    uint8_t *pkt = nullptr, *pkt_base = nullptr;
+    if (c.in_kind == IN_PINNED) { void *p = nullptr; jm_nvdec_memory_alloc_host(&p, (int)pkt_bytes, h); pkt = pkt_base = (uint8_t *)p; }
+    else { pkt_base = (uint8_t *)malloc(pkt_bytes + 8192); pkt = pkt_base + 1234; }           /* unaligned inside the malloc block */
+    if (c.in_kind == IN_REGISTERED) jm_nvdec_memory_register_host(pkt, (int)pkt_bytes, h);
+    const size_t out_cap = tight + 8;
+    uint8_t *out = nullptr, *out_base = nullptr;
+    if (c.out_kind == OUT_PINNED) { void *p = nullptr; jm_nvdec_memory_alloc_host(&p, (int)out_cap, h); out = out_base = (uint8_t *)p; }
+    else if (c.out_kind == OUT_DEVICE) { void *p = nullptr; cudaSetDevice(c.device); cudaMalloc(&p, out_cap); cudaSetDevice(0); out = out_base = (uint8_t *)p; }
+    else { out_base = (uint8_t *)malloc(out_cap + 8192); out = out_base + 777; }
+    /* buffers with less than 64 KB of whole pages inside are not worth a registration: the call says so (-1) */
+    const bool out_registered = c.out_kind == OUT_REGISTERED && out && jm_nvdec_memory_register_host(out, (int)out_cap, h) == 0;
+    if (c.out_kind == OUT_REGISTERED && !c.tolerate_errors) CHECK(out_registered == (out_cap >= (64u << 10) + 8192), "registration of a %zu-byte out_buf: %d", out_cap, (int)out_registered);
+    CHECK((pkt && out) || c.tolerate_errors, "caller buffers");
+    /* device-pointer inputs: a ring of surfaces, as a decoder has; a slot is rewritten only after the frame made from it was fetched */
+    const int n_dsurf = c.delay + 4;
+    std::vector<uint8_t *> dsurf;
+    cudaStream_t up = nullptr;
+    cudaEvent_t up_ev = nullptr;
+    uint8_t *up_stage = nullptr;
+    if (c.in_kind >= IN_DEVICE) {
+        cudaSetDevice(c.device);
+        for (int i = 0; i < n_dsurf; i++) { void *p = nullptr; cudaMalloc(&p, surf_bytes ? surf_bytes : 1); dsurf.push_back((uint8_t *)p); }
+        if (c.in_kind == IN_DEVICE_EVENT) {
+            cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking);
+            cudaEventCreateWithFlags(&up_ev, cudaEventDisableTiming);
+            void *p = nullptr; cudaHostAlloc(&p, (surf_bytes ? surf_bytes : 1) * n_dsurf, cudaHostAllocDefault); up_stage = (uint8_t *)p;
+        }
+        cudaSetDevice(0);
+    }
+    bool caller_ok = pkt && out && (c.in_kind != IN_DEVICE_EVENT || up_stage);
+    for (uint8_t *d : dsurf) caller_ok = caller_ok && d;
+    std::vector<std::vector<uint8_t>> want;
+    int delivered = 0, next_want = 0;
+    bool order_ok = true;
+    auto fetch = [&]() {
+        int len = (int)tight;
+        int rr;
+        const uint8_t *got = nullptr;
+        if (c.out_kind == OUT_REF) {
+            const unsigned char *f = nullptr;
+            rr = jm_nvdec_output_frame_ref(&f, &len, h);
+            got = f;
+        } else {
+            if (c.out_kind != OUT_DEVICE) memset(out, 0xA5, out_cap);
+            else cudaMemset(out, 0xA5, out_cap);
+            rr = jm_nvdec_output_frame(out, &len, h);
+            got = out;
+        }
+        int dev = -1; cudaGetDevice(&dev);
+        CHECK(dev == 0, "output_frame left device %d current", dev);
+        if (rr < 0) { CHECK(c.tolerate_errors, "output_frame returned %d (%s)", rr, jmc_last_error()); return; }
+        CHECK(rr == (int)tight && len == (int)tight, "output_frame returned %d, len %d, expected %zu", rr, len, tight);
+        /* which frame is it?  In order, but frames may be missing when errors are tolerated */
+        bool found = false;
+        while (next_want < (int)want.size()) {
+            const std::vector<uint8_t> &w = want[(size_t)next_want++];
+            const size_t n = c.out_kind == OUT_REF ? wr : out_cap;           /* a ring slot only promises the written bytes */
+            if (memcmp(got, w.data(), n) == 0) { found = true; break; }
+            if (!c.tolerate_errors) break;
+        }
+        CHECK(found, "frame %d: bytes differ from the oracle (or frames out of order)", delivered);
+        order_ok = order_ok && found;
+        delivered++;
+    };
+    for (int f = 0; f < c.frames && caller_ok; f++) {
+        const std::vector<uint8_t> s = surface(g, seed * 1000 + (unsigned)f);
+        want.push_back(expected(s, g, c.fmt));
+        jm_nvdec_raw_packet_ex x;
+        memset(&x, 0, sizeof(x));
+        x.base.magic = JM_NVDEC_RAW_MAGIC; x.base.width = g.w; x.base.height = g.h; x.base.pitch = g.pitch;
+        int len;
+        if (c.in_kind < IN_DEVICE) {
+            memcpy(pkt, &x.base, sizeof(x.base));
+            if (surf_bytes) memcpy(pkt + sizeof(x.base), s.data(), surf_bytes);
+            len = (int)(sizeof(x.base) + surf_bytes);
+        } else {
+            uint8_t *d = dsurf[(size_t)f % dsurf.size()];
+            x.base.flags = JM_NVDEC_RAW_DEVICE_PTR;
+            x.base.device_ptr = (uint64_t)(uintptr_t)d;
+            if (c.in_kind == IN_DEVICE_EVENT) {
+                /* the surface is still being produced on another stream when the packet is handed over */
+                uint8_t *st = up_stage + (size_t)(f % n_dsurf) * (surf_bytes ? surf_bytes : 1);
+                if (surf_bytes) memcpy(st, s.data(), surf_bytes);
+                cudaSetDevice(c.device);
+                if (surf_bytes) cudaMemcpyAsync(d, st, surf_bytes, cudaMemcpyHostToDevice, up);
+                cudaEventRecord(up_ev, up);
+                cudaSetDevice(0);
+                x.base.flags |= JM_NVDEC_RAW_WAIT_EVENT;
+                x.ready_event = (uint64_t)(uintptr_t)up_ev;
+            } else if (surf_bytes) {
+                cudaMemcpy2D(d, surf_bytes, s.data(), surf_bytes, surf_bytes, 1, cudaMemcpyHostToDevice);      /* written at once */
+            }
+            if (c.in_kind == IN_DEVICE_SYNC) x.base.flags |= JM_NVDEC_RAW_SYNC;
+            memcpy(pkt, &x, sizeof(x));
+            len = (int)sizeof(x);
+        }
+        int got_frame = -1;
+        r = jm_nvdec_decode_frame(pkt, len, &got_frame, h);
+        int dev = -1; cudaGetDevice(&dev);
+        CHECK(dev == 0, "decode_frame left device %d current", dev);
+        CHECK(r == 0 || c.tolerate_errors, "decode_frame returned %d (%s)", r, jmc_last_error());
+        memset(pkt, 0x77, (size_t)len);                                    /* in_buf is the caller's again */
+        if (c.in_kind == IN_DEVICE_SYNC && surf_bytes) cudaMemset(dsurf[(size_t)f % dsurf.size()], 0x33, surf_bytes);   /* ... and so is the surface */
+        if (got_frame == 1) fetch();
+    }
+    for (int guard = 0; guard < c.frames + 50 && !jm_nvdec_is_exit(h); guard++) {
+        int got_frame = 0;
+        r = jm_nvdec_decode_frame(nullptr, 0, &got_frame, h);
+        CHECK(r == 0 || c.tolerate_errors, "flush returned %d", r);
+        if (got_frame == 1) fetch();
+    }
+    CHECK(jm_nvdec_is_exit(h), "the handle never reported the end of the stream");
+    (void)order_ok;
+    if (!c.tolerate_errors) {
+        CHECK(delivered == c.frames, "%d of %d frames delivered", delivered, c.frames);
+        CHECK(jm_nvdec_dropped_frames(h) == 0, "%d frames dropped", jm_nvdec_dropped_frames(h));
+        CHECK(g_fake_max_batch >= 1, "no launch seen");
+    }
+    if (out_registered) CHECK(jm_nvdec_memory_unregister_host(out, h) == 0, "unregister out_buf");
+    if (c.in_kind == IN_PINNED && pkt) jm_nvdec_memory_release_host(pkt, h);
+    if (c.out_kind == OUT_PINNED && out) jm_nvdec_memory_release_host(out, h);
+    jm_nvdec_deinit(h);                                                    /* releases what is still registered (IN_REGISTERED, lazy pin) */
+    if (c.in_kind != IN_PINNED) free(pkt_base);
+    if (c.out_kind == OUT_DEVICE) { if (out_base) cudaFree(out_base); }
+    else if (c.out_kind != OUT_PINNED) free(out_base);
+    for (uint8_t *d : dsurf) if (d) cudaFree(d);
+    if (up) { cudaStreamDestroy(up); if (up_ev) cudaEventDestroy(up_ev); if (up_stage) cudaFreeHost(up_stage); }
+    sim_clean(base, false);
+    return delivered;
+}
+
+/* ---- NVDEC front-end against the fake library ------------------------------------------------------------------- */
+static void put_nal(std::vector<uint8_t> &s, int type, const uint8_t *rbsp, size_t n, bool long_start)
+{
+    if (long_start) s.push_back(0);
+    s.push_back(0); s.push_back(0); s.push_back(1);
+    s.push_back((uint8_t)type);
+    int zeros = 0;
+    for (size_t i = 0; i < n; i++) {                                        /* H.264 emulation prevention */
+        if (zeros >= 2 && rbsp[i] <= 3) { s.push_back(3); zeros = 0; }
+        s.push_back(rbsp[i]);
+        zeros = rbsp[i] == 0 ? zeros + 1 : 0;
+    }
+    s.push_back(0x80);
+}
+
+struct cuvid_cfg {
+    std::vector<geom> formats;      /* one sequence per entry (pitch unused) */
+    int pics_per_format, pics_per_packet, map_limit, parser_delay, delay, fmt, out_kind;
+    bool expect_drops;
+};
+
+static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const char *fake_lib)
+{
+    fake_cuda_reset(seed, laziness, 2);
+    cudaSetDevice(0);
+    const fake_cuda_counts base = fake_cuda_live();
+    setenv("JMC_NVCUVID_LIB", fake_lib, 1);
+    char num[16];
+    snprintf(num, sizeof(num), "%d", c.parser_delay);
+    setenv("JMC_NVDEC_PARSER_DELAY", num, 1);
+    g_fake_launches = g_fake_frames = g_fake_max_batch = 0;
+    handle_nvdec h = jm_nvdec_create_handle();
+    jm_nvdec_set_option("map_limit", c.map_limit, h);
+    jm_nvdec_set_option("display_delay", c.delay, h);
+    int r = jm_nvdec_init(JM_NVDEC_CODEC_AVC, c.fmt, nullptr, 0, h);
+    CHECK(r == 0, "init with the fake NVDEC library failed: %d (%s)", r, jmc_last_error());
+    if (r != 0) { jm_nvdec_deinit(h); return; }
+    /* the stream and what must come out of it */
+    std::vector<std::vector<uint8_t>> packets, want;
+    std::vector<geom> want_geom;
+    std::mt19937 rng(seed + 99);
+    for (const geom &g : c.formats) {
+        std::vector<uint8_t> cur;
+        uint32_t wh[2] = { (uint32_t)g.w, (uint32_t)g.h };
+        put_nal(cur, 0x67, (const uint8_t *)wh, 8, true);
+        int in_packet = 0;
+        for (int p = 0; p < c.pics_per_format; p++) {
+            const geom tg = { g.w, g.h, g.w };
+            std::vector<uint8_t> tight_nv12 = surface(tg, (uint32_t)rng());
+            if (p % 5 == 0 && tight_nv12.size() > 64) memset(tight_nv12.data() + 20, 0, 40);      /* runs of zeros: escapes */
+            want.push_back(expected(tight_nv12, tg, c.fmt));
+            want_geom.push_back(tg);
+            put_nal(cur, 0x65, tight_nv12.data(), tight_nv12.size(), (p & 1) == 0);
+            if (++in_packet == c.pics_per_packet) { packets.push_back(cur); cur.clear(); in_packet = 0; }
+        }
+        if (!cur.empty()) packets.push_back(cur);
+    }
+    std::vector<uint8_t> out_buf_pageable;
+    int delivered = 0, next_want = 0;
+    uint8_t *pinned = nullptr;
+    size_t pinned_cap = 0;
+    for (const geom &g : c.formats) pinned_cap = std::max(pinned_cap, (size_t)g.w * g.h * 3 / 2 + 8);
+    if (c.out_kind == OUT_PINNED) { void *p = nullptr; jm_nvdec_memory_alloc_host(&p, (int)pinned_cap, h); pinned = (uint8_t *)p; }
+    out_buf_pageable.resize(pinned_cap);
+    auto fetch = [&]() {
+        int w = 0, hh = 0;
+        jm_nvdec_stream_info(&w, &hh, h);
+        uint8_t *out = pinned ? pinned : out_buf_pageable.data();
+        memset(out, 0xA5, pinned_cap);
+        int len = (int)pinned_cap;
+        int rr = jm_nvdec_output_frame(out, &len, h);
+        CHECK(rr > 0, "output_frame returned %d (%s)", rr, jmc_last_error());
+        if (rr <= 0) return;
+        bool found = false;
+        while (next_want < (int)want.size()) {
+            const size_t i = (size_t)next_want++;
+            const size_t n = (size_t)want_geom[i].w * want_geom[i].h * 3 / 2;
+            if ((int)n == rr && memcmp(out, want[i].data(), n + 8 <= pinned_cap ? n + 8 : n) == 0) { found = true; break; }
+            if (!c.expect_drops) break;
+        }
+        CHECK(found, "picture %d: bytes differ from the oracle (or out of order)", delivered);
+        delivered++;
+    };
+    bool saw_drop_report = false;
+    for (auto &p : packets) {
+        int got_frame = 0;
+        std::vector<uint8_t> copy = p;                                      /* handed over, then scribbled on */
+        r = jm_nvdec_decode_frame(copy.data(), (int)copy.size(), &got_frame, h);
+        if (r != 0) saw_drop_report = true;
+        CHECK(r == 0 || c.expect_drops, "decode_frame returned %d (%s)", r, jmc_last_error());
+        memset(copy.data(), 0x77, copy.size());
+        int dev = -1; cudaGetDevice(&dev);
+        CHECK(dev == 0, "decode_frame left device %d current", dev);
+        if (got_frame == 1) fetch();
+    }
+    for (int guard = 0; guard < (int)want.size() + 50 && !jm_nvdec_is_exit(h); guard++) {
+        int got_frame = 0;
+        jm_nvdec_decode_frame(nullptr, 0, &got_frame, h);
+        if (got_frame == 1) fetch();
+    }
+    CHECK(jm_nvdec_is_exit(h), "the handle never reported the end of the stream");
+    const int dropped = jm_nvdec_dropped_frames(h);
+    if (!c.expect_drops) {
+        CHECK(delivered == (int)want.size(), "%d of %zu pictures delivered", delivered, want.size());
+        CHECK(dropped == 0, "%d pictures dropped", dropped);
+    } else {
+        CHECK(delivered + dropped == (int)want.size(), "delivered %d + dropped %d != %zu", delivered, dropped, want.size());
+        CHECK(dropped == 0 || saw_drop_report, "pictures were dropped but no call reported it");
+    }
+    if (c.pics_per_packet >= 2 && c.map_limit >= 2) CHECK(g_fake_max_batch >= 2, "several pictures per packet were never converted by one launch (max batch %d)", g_fake_max_batch);
+    CHECK(g_fake_max_batch <= c.map_limit, "a launch took %d pictures with a map limit of %d", g_fake_max_batch, c.map_limit);
+    if (pinned) jm_nvdec_memory_release_host(pinned, h);
+    jm_nvdec_deinit(h);
+    sim_clean(base, true);
+}
+
+/* ---- encoder input API ------------------------------------------------------------------------------------------- */
+static void run_nvenc(int fmt, const geom &g, unsigned seed, int laziness)
+{
+    fake_cuda_reset(seed, laziness, 2);
+    cudaSetDevice(0);
+    const fake_cuda_counts base = fake_cuda_live();
+    handle_nvenc h = jm_nvenc_create_handle();
+    jm_nvenc_set_device(1, h);
+    nv_enc_param p;
+    memset(&p, 0, sizeof(p));
+    p.codec_id = JM_NVENC_CODEC_SURFACE_ONLY;
+    p.src_width = g.w; p.src_height = g.h; p.in_fmt = fmt;
+    int r = jm_nvenc_init(&p, h);
+    CHECK(r == JM_NVENC_SUCCESS, "nvenc init %d (%s)", r, jmc_last_error());
+    r = jm_nvenc_init(&p, h);                                               /* again on the live handle: starts over, leaks nothing */
+    CHECK(r == JM_NVENC_SUCCESS, "nvenc re-init %d", r);
+    const bool rgb = fmt == JM_NVENC_FMT_ARGB || fmt == JM_NVENC_FMT_ABGR;
+    const size_t in_bytes = rgb ? (size_t)g.w * g.h * 4 : (size_t)g.w * g.h * 3 / 2;
+    for (int f = 0; f < JM_NVENC_NUM_SURFACES + 2; f++) {
+        std::vector<uint8_t> in(in_bytes);
+        random_bytes(in.data(), in.size(), seed * 100 + (unsigned)f);
+        const std::vector<uint8_t> in2 = in;                                /* enc_frame's buffer is scribbled on below */
+        int got = -1;
+        r = jm_nvenc_enc_frame(in.data(), (int)in.size(), &got, h);
+        int dev = -1; cudaGetDevice(&dev);
+        CHECK(dev == 0, "enc_frame left device %d current", dev);
+        if (f >= JM_NVENC_NUM_SURFACES) {                                   /* every surface locked: the reference returns -1 (nv_enc.cpp:90-93) */
+            CHECK(r == -1, "enc_frame with no free surface returned %d", r);
+            CHECK(jm_nvenc_release_surface(h) == 0, "release_surface");
+            r = jm_nvenc_enc_frame(in.data(), (int)in.size(), &got, h);     /* the oldest surface is free again */
+        }
+        CHECK(r == 0 && got == 0, "enc_frame returned %d got %d (%s)", r, got, jmc_last_error());
+        memset(in.data(), 0x77, in.size());                                 /* consumed before return */
+        void *d = nullptr; int pitch = 0, rows = 0;
+        CHECK(jm_nvenc_peek_surface(&d, &pitch, &rows, h) == 0, "peek_surface");
+        std::vector<uint8_t> want((size_t)pitch * rows, 0);
+        if (rgb) { for (int y = 0; y < g.h; y++) memcpy(&want[(size_t)y * pitch], &in2[(size_t)y * g.w * 4], (size_t)g.w * 4); }   /* pitch honoured (documented fix of nv_enc.cpp:1096) */
+        else jmo_nvenc_upload(in2.data(), fmt, g.w, g.h, want.data(), pitch);
+        CHECK(memcmp(d, want.data(), want.size()) == 0, "surface %d differs from the oracle (fmt 0x%x)", f, fmt);
+    }
+    if (!rgb || true) {
+        std::vector<uint8_t> small(in_bytes / 2 + 1, 1);
+        int got = 0;
+        r = jm_nvenc_enc_frame(small.data(), (int)small.size(), &got, h);
+        if (fmt != JM_NVENC_FMT_YV12) CHECK(r == JM_NVENC_ERR_INVALID_PARAM, "short buffer accepted: %d", r);
+    }
+    jm_nvenc_deinit(h);
+    sim_clean(base, false);
+}
+
+static const char *in_name[] = { "host-pageable", "host-pinned", "host-registered", "device", "device+sync", "device+event" };
+static const char *out_name[] = { "pageable", "pinned", "registered", "lazy-pin", "device", "ref" };
+
+int main(int argc, char **argv)
+{
+    if (argc < 2) { printf("usage: %s <fake nvcuvid .so> [filter]\n", argv[0]); return 2; }
+    const char *fake_lib = argv[1];
+    const char *filter = argc > 2 ? argv[2] : "";
+    auto want_run = [&](const char *name) { return strstr(name, filter) != nullptr; };
+    const geom geoms[] = { { 64, 36, 64 }, { 1366, 768, 1536 }, { 1280, 720, 1280 }, { 199, 77, 256 }, { 2, 2, 16 } };
+
+    if (want_run("raw")) {
+        for (int lazy = 0; lazy <= 2; lazy++)
+            for (int in = 0; in <= IN_DEVICE_EVENT; in++)
+                for (int out = 0; out <= OUT_REF; out++)
+                    for (int delay : { 0, 2 }) {
+                        const int gi = (in + out + delay) % 5;
+                        const int fmt = (in + out) & 1;
+                        char name[200];
+                        snprintf(name, sizeof(name), "raw lazy=%d in=%s out=%s delay=%d %dx%d fmt=%d", lazy, in_name[in], out_name[out], delay, geoms[gi].w, geoms[gi].h, fmt);
+                        g_ctx = name;
+                        raw_cfg c = { geoms[gi], fmt, delay, in, out, (in + out) % 3 == 0 ? 3 : 0, 14, (in + out) & 1, false };
+                        g_fake_max_batch = 0;
+                        run_raw(c, 100u + (unsigned)(lazy * 1000 + in * 100 + out * 10 + delay), lazy);
+                    }
+        /* a display delay longer than the ring of upload surfaces / staging buffers (10): their reuse must wait for
+         * uploads and launches that nobody has synchronised with yet */
+        for (int lazy = 0; lazy <= 2; lazy++)
+            for (int in : { (int)IN_PAGEABLE, (int)IN_PINNED, (int)IN_DEVICE }) {
+                char name[100];
+                snprintf(name, sizeof(name), "raw long delay lazy=%d in=%s", lazy, in_name[in]);
+                g_ctx = name;
+                raw_cfg c = { geoms[3], 1, 14, in, OUT_PAGEABLE, 0, 40, 0, false };
+                run_raw(c, 900u + (unsigned)lazy, lazy);
+            }
+        /* many seeds of the random-progress mode on the calling convention the reference uses */
+        for (unsigned seed = 1; seed <= 40; seed++) {
+            char name[100];
+            snprintf(name, sizeof(name), "raw random-progress seed %u", seed);
+            g_ctx = name;
+            raw_cfg c = { geoms[seed % 5], (int)(seed & 1), (int)(seed % 4), (int)(seed % 6), (int)((seed / 2) % 6), (int)(seed % 3), 20, 1, false };
+            run_raw(c, seed, 1);
+        }
+        /* a stream whose geometry grows: surfaces, staging buffers and ring slots are re-allocated under way */
+        g_ctx = "raw geometry change";
+        for (int lazy = 0; lazy <= 2; lazy++) {
+            fake_cuda_reset(7, lazy, 2);
+            const fake_cuda_counts base = fake_cuda_live();
+            handle_nvdec h = jm_nvdec_create_handle();
+            jm_nvdec_set_option("display_delay", 1, h);
+            CHECK(jm_nvdec_init(JM_NVDEC_CODEC_RAW_NV12, 1, nullptr, 0, h) == 0, "init");
+            std::vector<std::vector<uint8_t>> want;
+            std::vector<size_t> want_n;
+            size_t next = 0;
+            const geom seq[] = { { 64, 36, 64 }, { 64, 36, 64 }, { 640, 360, 640 }, { 640, 360, 768 }, { 64, 36, 128 }, { 1280, 720, 1280 }, { 1280, 720, 1280 }, { 64, 36, 64 } };
+            std::vector<uint8_t> out(1280 * 720 * 3 / 2 + 8);
+            auto fetch = [&]() {
+                memset(out.data(), 0xA5, out.size());
+                int len = (int)out.size();
+                int rr = jm_nvdec_output_frame(out.data(), &len, h);
+                CHECK(next < want.size() && rr == (int)want_n[next] && memcmp(out.data(), want[next].data(), want_n[next] + 8) == 0, "frame %zu after a geometry change", next);
+                next++;
+            };
+            for (size_t f = 0; f < sizeof(seq) / sizeof(seq[0]); f++) {
+                const std::vector<uint8_t> s = surface(seq[f], (uint32_t)f + 5);
+                want.push_back(expected(s, seq[f], 1));
+                want_n.push_back((size_t)seq[f].w * seq[f].h * 3 / 2);
+                std::vector<uint8_t> pkt(sizeof(jm_nvdec_raw_packet) + s.size());
+                jm_nvdec_raw_packet hd;
+                memset(&hd, 0, sizeof(hd));
+                hd.magic = JM_NVDEC_RAW_MAGIC; hd.width = seq[f].w; hd.height = seq[f].h; hd.pitch = seq[f].pitch;
+                memcpy(pkt.data(), &hd, sizeof(hd));
+                memcpy(pkt.data() + sizeof(hd), s.data(), s.size());
+                int got = 0;
+                CHECK(jm_nvdec_decode_frame(pkt.data(), (int)pkt.size(), &got, h) == 0, "decode");
+                if (got) fetch();
+            }
+            for (int k = 0; k < 8 && !jm_nvdec_is_exit(h); k++) { int got = 0; jm_nvdec_decode_frame(nullptr, 0, &got, h); if (got) fetch(); }
+            CHECK(next == want.size(), "%zu of %zu frames", next, want.size());
+            /* init on the live handle, then straight to deinit with frames still inside */
+            CHECK(jm_nvdec_init(JM_NVDEC_CODEC_RAW_NV12, 0, nullptr, 0, h) == 0, "re-init");
+            for (int f = 0; f < 3; f++) {
+                const std::vector<uint8_t> s = surface(seq[2], 77);
+                std::vector<uint8_t> pkt(sizeof(jm_nvdec_raw_packet) + s.size());
+                jm_nvdec_raw_packet hd;
+                memset(&hd, 0, sizeof(hd));
+                hd.magic = JM_NVDEC_RAW_MAGIC; hd.width = seq[2].w; hd.height = seq[2].h; hd.pitch = seq[2].pitch;
+                memcpy(pkt.data(), &hd, sizeof(hd));
+                memcpy(pkt.data() + sizeof(hd), s.data(), s.size());
+                int got = 0;
+                jm_nvdec_decode_frame(pkt.data(), (int)pkt.size(), &got, h);
+            }
+            jm_nvdec_deinit(h);
+            sim_clean(base, false);
+        }
+    }
+
+    if (want_run("alloc-failure")) {
+        /* every allocation site fails once: nothing crashes, nothing leaks, whatever is delivered is right */
+        for (int kind = 0; kind < 3; kind++)
+            for (int k = 0; k < 48; k++)
+                for (int variant = 0; variant < 3; variant++) {
+                    char name[100];
+                    snprintf(name, sizeof(name), "alloc-failure kind %d at %d variant %d", kind, k, variant);
+                    g_ctx = name;
+                    raw_cfg c = { geoms[variant == 2 ? 2 : 0], 1, variant, variant == 1 ? IN_DEVICE : IN_PAGEABLE, variant == 1 ? OUT_PINNED : OUT_PAGEABLE, variant == 2 ? 2 : 0, 6, 0, true };
+                    g_arm_kind = kind; g_arm_k = k;
+                    run_raw(c, 5, 1);
+                    g_arm_kind = -1;
+                }
+    }
+
+    if (want_run("cuvid")) {
+        struct { int ppp, map_limit, pdelay, delay; } v[] = { { 8, 8, 2, 0 }, { 8, 3, 2, 0 }, { 4, 8, 0, 2 }, { 1, 8, 2, 0 }, { 8, 1, 1, 1 }, { 3, 2, 4, 0 } };
+        for (int lazy = 0; lazy <= 2; lazy++)
+            for (size_t i = 0; i < sizeof(v) / sizeof(v[0]); i++) {
+                char name[160];
+                snprintf(name, sizeof(name), "cuvid lazy=%d pics/packet=%d map_limit=%d parser_delay=%d delay=%d", lazy, v[i].ppp, v[i].map_limit, v[i].pdelay, v[i].delay);
+                g_ctx = name;
+                cuvid_cfg c = { { { 320, 180, 0 } }, 48, v[i].ppp, v[i].map_limit, v[i].pdelay, v[i].delay, (int)(i & 1), i % 3 == 0 ? OUT_PINNED : OUT_PAGEABLE, false };
+                run_cuvid(c, 300u + (unsigned)i, lazy, fake_lib);
+                snprintf(name, sizeof(name), "cuvid format change lazy=%d pics/packet=%d map_limit=%d", lazy, v[i].ppp, v[i].map_limit);
+                g_ctx = name;
+                cuvid_cfg c2 = { { { 320, 180, 0 }, { 198, 102, 0 }, { 640, 360, 0 } }, 14, v[i].ppp, v[i].map_limit, v[i].pdelay, v[i].delay, 1, OUT_PAGEABLE, false };
+                run_cuvid(c2, 400u + (unsigned)i, lazy, fake_lib);
+            }
+        for (int lazy = 0; lazy <= 2; lazy++) {
+            g_ctx = "cuvid overflow";
+            cuvid_cfg c = { { { 128, 72, 0 } }, 110, 8, 8, 2, 0, 1, OUT_PAGEABLE, true };
+            run_cuvid(c, 500, lazy, fake_lib);
+        }
+        for (unsigned seed = 1; seed <= 25; seed++) {
+            char name[100];
+            snprintf(name, sizeof(name), "cuvid random-progress seed %u", seed);
+            g_ctx = name;
+            cuvid_cfg c = { { { 200, 120, 0 }, { 64, 48, 0 } }, 20, 1 + (int)(seed % 8), 1 + (int)(seed % 8), (int)(seed % 5), (int)(seed % 3), (int)(seed & 1), OUT_PAGEABLE, false };
+            run_cuvid(c, seed, 1, fake_lib);
+        }
+    }
+
+    if (want_run("nvenc")) {
+        for (int lazy = 0; lazy <= 2; lazy++)
+            for (int fmt : { JM_NVENC_FMT_NV12, JM_NVENC_FMT_YV12, JM_NVENC_FMT_ARGB })
+                for (const geom &g : { geom{ 64, 36, 0 }, geom{ 322, 180, 0 }, geom{ 1366, 768, 0 } }) {
+                    char name[100];
+                    snprintf(name, sizeof(name), "nvenc lazy=%d fmt=0x%x %dx%d", lazy, fmt, g.w, g.h);
+                    g_ctx = name;
+                    run_nvenc(fmt, g, 9, lazy);
+                }
+    }
+    printf("%d checks, %d failed\n", g_checks, g_fail);
+    printf(g_fail ? "FAILED\n" : "OK\n");
+    return g_fail ? 1 : 0;
+}

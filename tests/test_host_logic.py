@@ -64,3 +64,104 @@ int main()
     if "FATAL: ThreadSanitizer" in p.stderr and "unexpected memory mapping" in p.stderr:
         pytest.skip("thread sanitizer cannot map its shadow memory in this container")
     assert p.returncode == 0 and "OK" in p.stdout and "WARNING: ThreadSanitizer" not in p.stderr, p.stderr[-3000:]
+
+
+# ---- the whole host layer on a CUDA runtime simulator -----------------------------------------------------------------
+HL = os.path.join(ROOT, "tests", "host_logic")
+PRODUCT = ["jm_nv_dec.cu", "jmc_runtime.cu", "jmnv_enc.cu"]              # compiled unchanged, as C++, against fake_cuda/cuda_runtime.h
+HARNESS = [os.path.join(HL, "fake_cuda", "fake_cuda.cpp"), os.path.join(HL, "fake_launch.cpp"), os.path.join(HL, "delivery_sim_test.cpp")]
+INCLUDES = ["-I", os.path.join(HL, "fake_cuda"), "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+
+
+def _run(cmd, **kw):
+    p = subprocess.run(cmd, capture_output=True, text=True, **kw)
+    assert p.returncode == 0, " ".join(map(str, cmd)) + "\n" + p.stderr[-3000:]
+
+
+def _build_sim(out_dir, flags, nvdec_source=None):
+    """Objects + link of the simulation harness in out_dir; nvdec_source replaces jm_nv_dec.cu (mutation tests)."""
+    os.makedirs(out_dir, exist_ok=True)
+    objs = []
+    _run(["gcc"] + flags + ["-c", os.path.join(ROOT, "oracle", "jm_oracle.c"), "-o", os.path.join(out_dir, "jm_oracle.o")])
+    objs.append(os.path.join(out_dir, "jm_oracle.o"))
+    for f in PRODUCT:
+        src = nvdec_source if (nvdec_source and f == "jm_nv_dec.cu") else os.path.join(CSRC, f)
+        o = os.path.join(out_dir, f + ".o")
+        _run(["g++", "-std=c++17"] + flags + INCLUDES + ["-x", "c++", "-c", src, "-o", o])
+        objs.append(o)
+    for f in HARNESS:
+        o = os.path.join(out_dir, os.path.basename(f) + ".o")
+        _run(["g++", "-std=c++17"] + flags + INCLUDES + ["-c", f, "-o", o])
+        objs.append(o)
+    exe = os.path.join(out_dir, "delivery_sim_test")
+    _run(["g++"] + flags + objs + ["-rdynamic", "-ldl", "-lpthread", "-o", exe])
+    # the fake NVDEC library of the GPU tests, built against the simulator; its cuda* calls bind to the executable's
+    lib = os.path.join(out_dir, "libfake_nvcuvid_sim.so")
+    _run(["g++", "-std=c++17"] + flags + ["-shared", "-fPIC", "-I", os.path.join(HL, "fake_cuda"), "-I", CSRC, "-x", "c++",
+          os.path.join(ROOT, "tests", "fake_nvcuvid", "fake_nvcuvid.cu"), "-o", lib])
+    return exe, lib
+
+
+@pytest.fixture(scope="module")
+def sim_sanitized(tmp_path_factory):
+    flags = ["-g", "-O1", "-fno-omit-frame-pointer", "-fsanitize=address,undefined"]
+    probe = subprocess.run(["g++", "-fsanitize=address,undefined", "-x", "c++", "-", "-o", os.devnull], input="int main(){return 0;}", capture_output=True, text=True)
+    if probe.returncode != 0:
+        flags = ["-g", "-O1"]                                            # no sanitizer runtimes here: the checks still run
+    return _build_sim(str(tmp_path_factory.mktemp("sim_san")), flags)
+
+
+@pytest.mark.parametrize("scenario", ["raw", "cuvid", "nvenc", "alloc-failure"])
+def test_host_layer_on_the_cuda_simulator(sim_sanitized, scenario):
+    """jm_nv_dec.cu / jmnv_enc.cu / jmc_runtime.cu, unchanged, through the public C API on a CUDA runtime simulator whose
+    streams run work as late as CUDA allows (only when waited for / at random moments / at once): every frame against
+    the oracle for every input kind x out_buf kind x display delay, the NVDEC front-end against the fake library
+    (batch drain, map limit, format change, overflow), the encoder-input API, an allocation failure at every
+    allocation site; no leak, no free under pending work, caller's device restored -- under ASan + UBSan."""
+    exe, lib = sim_sanitized
+    p = subprocess.run([exe, lib, scenario], capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1"))
+    assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-3000:] + p.stderr[-3000:]
+
+
+MUTATIONS = {
+    # name: (text in jm_nv_dec.cu, replacement, scenario that must then fail)
+    "staging buffer reused before its upload ran": (
+        "if (c->stage_used[slot]) cudaEventSynchronize(c->stage_done[slot]);", ";", "raw"),
+    "decoder surfaces unmapped before the launch that reads them ran": (
+        "else if (cudaEventQuery(b.done) != cudaSuccess) { cudaGetLastError(); break; }", ";", "cuvid"),
+    "ready_event of a device-pointer packet ignored": (
+        "if (x.ready_event && cudaStreamWaitEvent(st, (cudaEvent_t)(uintptr_t)x.ready_event, 0) != cudaSuccess) { cudaGetLastError(); return -1; }", ";", "raw"),
+    "delivery chunks copied out without waiting for them": (
+        "auto wait_chunk = [&](int i) { if (cudaEventSynchronize(s.delivered[i]) != cudaSuccess) { cudaGetLastError(); failed = true; } };",
+        "auto wait_chunk = [&](int i) { (void)i; (void)failed; };", "raw"),
+    "direct delivery started before the launch finished and never waited for": (
+        "if (cudaEventRecord(s.direct, ds) != cudaSuccess || cudaEventSynchronize(s.direct) != cudaSuccess) { cudaGetLastError(); return -1; }", ";", "raw"),
+}
+
+
+@pytest.fixture(scope="module")
+def sim_plain(tmp_path_factory):
+    d = str(tmp_path_factory.mktemp("sim_plain"))
+    _, lib = _build_sim(d, ["-g", "-O1"])
+    return d, lib
+
+
+@pytest.mark.parametrize("name", sorted(MUTATIONS))
+def test_the_simulator_catches_injected_ordering_bugs(tmp_path, sim_plain, name):
+    """The harness above is only worth something if it fails when the protocol is broken: each of these one-line
+    removals of a synchronisation in jm_nv_dec.cu must make the named scenario fail."""
+    old, new, scenario = MUTATIONS[name]
+    text = open(os.path.join(CSRC, "jm_nv_dec.cu")).read()
+    assert text.count(old) == 1, "the mutation no longer applies: update MUTATIONS"
+    mutated = tmp_path / "jm_nv_dec_mutated.cu"
+    mutated.write_text(text.replace(old, new))
+    # everything but the mutated translation unit comes from the unsanitized build shared by these tests
+    base_dir, lib = sim_plain
+    o = str(tmp_path / "mutated.o")
+    _run(["g++", "-std=c++17", "-g", "-O1"] + INCLUDES + ["-x", "c++", "-c", str(mutated), "-o", o])
+    objs = [os.path.join(base_dir, f) for f in os.listdir(base_dir) if f.endswith(".o") and f != "jm_nv_dec.cu.o"] + [o]
+    exe = str(tmp_path / "mutant")
+    _run(["g++", "-g"] + objs + ["-rdynamic", "-ldl", "-lpthread", "-o", exe])
+    p = subprocess.run([exe, lib, scenario], capture_output=True, text=True, timeout=900)
+    assert p.returncode != 0 and "FAIL" in p.stdout, "mutation survived: " + name
