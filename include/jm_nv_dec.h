@@ -161,6 +161,9 @@ JMDLL_FUNC int jm_nvdec_output_frame_ref(const unsigned char **frame, int *frame
 JMDLL_FUNC int jm_nvdec_dropped_frames(handle_nvdec handle);
 /** conversion kernels this handle has launched (one per batch of surfaces, not one per frame) */
 JMDLL_FUNC long long jm_nvdec_launch_count(handle_nvdec handle);
+/** diagnostic: delivery copies (device-to-host copies of converted frames) that the handles of this process have queued on
+ *  `device` (0..63) and not yet seen complete -- the count the per-device cap works on; 0 once every handle is gone */
+JMDLL_FUNC int jm_nvdec_deliveries_in_flight(int device);
 
 #ifdef __cplusplus
 }

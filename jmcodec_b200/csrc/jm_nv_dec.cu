@@ -68,7 +68,7 @@ namespace {
  * (or when the caller is waiting for that very frame). */
 std::atomic<int> g_dev_inflight[64];
 std::atomic<int> g_live_handles{0};
-int g_dev_inflight_max = -1;
+std::atomic<int> g_dev_inflight_max{-1};
 
 int env_int(const char *name, int dflt, int lo, int hi)
 {
@@ -489,13 +489,13 @@ bool flush_prefetch(nvdec_b200 *c, int wanted)
         const int idx = c->to_prefetch.front();
         ring_slot &s = c->ring[idx];
         /* at most max_inflight deliveries queued per handle, DEVICE_INFLIGHT per device */
-        if ((int)c->inflight.size() >= c->max_inflight || (!c->inflight.empty() && dev.load(std::memory_order_relaxed) >= g_dev_inflight_max)) {
+        if ((int)c->inflight.size() >= c->max_inflight || (!c->inflight.empty() && dev.load(std::memory_order_relaxed) >= g_dev_inflight_max.load(std::memory_order_relaxed))) {
             if (wanted < 0) return true;                                  /* later: the link is busy enough and nobody waits for this frame */
             ring_slot &f = c->ring[c->inflight.front()];
             if (cudaEventSynchronize(f.delivered[f.n_chunks - 1]) != cudaSuccess) { cudaGetLastError(); return false; }
             c->inflight.pop_front();
             dev.fetch_sub(1, std::memory_order_relaxed);
-        } else if (c->inflight.empty() && dev.load(std::memory_order_relaxed) >= g_dev_inflight_max && wanted < 0 && c->delay > 0) {
+        } else if (c->inflight.empty() && dev.load(std::memory_order_relaxed) >= g_dev_inflight_max.load(std::memory_order_relaxed) && wanted < 0 && c->delay > 0) {
             return true;                                                  /* other handles fill the link; a display delay leaves slack */
         }
         cudaEvent_t ev = c->ring[s.conv_slot >= 0 ? s.conv_slot : idx].converted;
@@ -1110,7 +1110,7 @@ handle_nvdec jm_nvdec_create_handle(void)
     c->map_limit = env_int("JMC_NVDEC_MAP_LIMIT", MAP_LIMIT_MAX, 1, MAP_LIMIT_MAX);
     c->max_inflight = env_int("JMC_NVDEC_MAX_INFLIGHT", 2, 1, 16);
     c->stage_linear = env_int("JMC_NVDEC_STAGE_LINEAR", 0, 0, 1) != 0;
-    if (g_dev_inflight_max < 0) g_dev_inflight_max = env_int("JMC_NVDEC_DEVICE_INFLIGHT", 4, 1, 64);
+    if (g_dev_inflight_max.load() < 0) g_dev_inflight_max.store(env_int("JMC_NVDEC_DEVICE_INFLIGHT", 4, 1, 64));   /* racing handles store the same value */
     g_live_handles.fetch_add(1);
     return c;
 }
@@ -1438,6 +1438,11 @@ long long jm_nvdec_launch_count(handle_nvdec handle)
 {
     nvdec_b200 *c = (nvdec_b200 *)handle;
     return c && c->ctx ? (long long)jmc_ctx_launch_count(c->ctx) : 0;
+}
+
+int jm_nvdec_deliveries_in_flight(int device)
+{
+    return device >= 0 && device < 64 ? g_dev_inflight[device].load(std::memory_order_relaxed) : -1;
 }
 
 } /* extern "C" */

@@ -6,6 +6,8 @@
 #include <string.h>
 #include <time.h>
 
+#include <atomic>
+#include <mutex>
 #include <new>
 
 #include "jmc_internal.h"
@@ -111,10 +113,11 @@ jmc_device_guard::~jmc_device_guard()
 }
 
 static jmc_env_flags g_env;
-static bool g_env_loaded = false;
+static std::atomic<bool> g_env_loaded{false};
+static std::mutex g_env_mutex;
 static bool env_on(const char *name) { const char *e = getenv(name); return e && atoi(e) != 0; }
 static int env_tri(const char *name) { const char *e = getenv(name); return e ? (atoi(e) != 0 ? 1 : 0) : -1; }
-static void env_load()
+static void env_load_locked()
 {
     jmc_env_flags f;
     f.no_bulk = env_on("JMC_NO_BULK");
@@ -129,17 +132,20 @@ static void env_load()
     f.rgb_bulk_pairs = getenv("JMC_RGB_BULK_PAIRS") ? atoi(getenv("JMC_RGB_BULK_PAIRS")) : 0;
     f.brows_rows = getenv("JMC_BROWS_ROWS") ? atoi(getenv("JMC_BROWS_ROWS")) : 0;
     g_env = f;
-    g_env_loaded = true;
+    g_env_loaded.store(true, std::memory_order_release);
 }
 const jmc_env_flags &jmc_env()
 {
-    if (!g_env_loaded) env_load();                      /* racing first calls read the same environment: benign */
+    if (!g_env_loaded.load(std::memory_order_acquire)) {       /* first use, possibly from several threads at once */
+        std::lock_guard<std::mutex> lk(g_env_mutex);
+        if (!g_env_loaded.load(std::memory_order_relaxed)) env_load_locked();
+    }
     return g_env;
 }
 
 extern "C" {
 
-void jmc_reload_env(void) { env_load(); }
+void jmc_reload_env(void) { std::lock_guard<std::mutex> lk(g_env_mutex); env_load_locked(); }   /* tests; not while launches run on other threads */
 
 int jmc_ctx_destroy(jmc_ctx *c)
 {

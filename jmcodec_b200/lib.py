@@ -145,6 +145,7 @@ _SIGS = {
     "jm_nvdec_output_frame_ref": (C.c_int, [C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.c_void_p]),
     "jm_nvdec_dropped_frames": (C.c_int, [C.c_void_p]),
     "jm_nvdec_launch_count": (C.c_longlong, [C.c_void_p]),
+    "jm_nvdec_deliveries_in_flight": (C.c_int, [C.c_int]),
     # jmnv_enc.h
     "jm_nvenc_create_handle": (C.c_void_p, []),
     "jm_nvenc_init": (C.c_int, [C.POINTER(NvEncParam), C.c_void_p]),

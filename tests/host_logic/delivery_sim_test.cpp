@@ -11,8 +11,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <atomic>
 #include <random>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "cuda_runtime.h"
@@ -21,15 +23,15 @@
 #include "jmnv_enc.h"
 #include "../../oracle/jm_oracle.h"
 
-extern int g_fake_launches, g_fake_frames, g_fake_max_batch;
+extern std::atomic<int> g_fake_launches, g_fake_frames, g_fake_max_batch;
 static int g_arm_kind = -1, g_arm_k = 0;      /* allocation failure to arm right after the simulator reset */
 
-static int g_fail = 0, g_checks = 0;
-static std::string g_ctx;
+static std::atomic<int> g_fail{0}, g_checks{0};
+static thread_local std::string g_ctx;
 #define CHECK(cond, ...)                                                                                         \
     do {                                                                                                         \
         g_checks++;                                                                                              \
-        if (!(cond)) { if (g_fail < 40) { printf("FAIL [%s] line %d: ", g_ctx.c_str(), __LINE__); printf(__VA_ARGS__); printf("\n"); } g_fail++; } \
+        if (!(cond)) { if (g_fail.load() < 40) { printf("FAIL [%s] line %d: ", g_ctx.c_str(), __LINE__); printf(__VA_ARGS__); printf("\n"); } g_fail++; } \
     } while (0)
 
 struct geom { int w, h, pitch; };
@@ -71,6 +73,7 @@ static void sim_clean(const fake_cuda_counts &base, bool streams_may_grow)
     CHECK(now.registered == base.registered, "host registrations leaked: %zu -> %zu", base.registered, now.registered);
     CHECK(now.events == base.events, "events leaked: %zu -> %zu", base.events, now.events);
     CHECK(now.streams == base.streams || (streams_may_grow && now.streams == base.streams + 1), "streams leaked: %zu -> %zu", base.streams, now.streams);
+    for (int d = 0; d < 3; d++) CHECK(jm_nvdec_deliveries_in_flight(d) == 0, "device %d still counts %d deliveries in flight", d, jm_nvdec_deliveries_in_flight(d));
 }
 
 enum { IN_PAGEABLE, IN_PINNED, IN_REGISTERED, IN_DEVICE, IN_DEVICE_SYNC, IN_DEVICE_EVENT };
@@ -83,6 +86,8 @@ struct raw_cfg {
 
 /* One RAW-front-end session, the reference's calling loop (test_nv_dec.cpp:207-258): decode, fetch if a frame is
  * announced, flush at the end.  Returns the number of frames delivered. */
+static int raw_session(const raw_cfg &c, unsigned seed);
+
 static int run_raw(const raw_cfg &c, unsigned seed, int laziness)
 {
     const int n_dev = c.device + 1 > 2 ? c.device + 1 : 2;
@@ -90,6 +95,15 @@ static int run_raw(const raw_cfg &c, unsigned seed, int laziness)
     cudaSetDevice(0);
     const fake_cuda_counts base = fake_cuda_live();
     if (g_arm_kind >= 0) fake_cuda_fail_alloc(g_arm_kind, g_arm_k);
+    const int n = raw_session(c, seed);
+    sim_clean(base, false);
+    return n;
+}
+
+/* the session itself: usable from several threads at once (one handle each) */
+static int raw_session(const raw_cfg &c, unsigned seed)
+{
+    cudaSetDevice(0);
     const geom &g = c.g;
     const size_t surf_bytes = (size_t)g.pitch * g.h * 3 / 2, tight = (size_t)g.w * g.h * 3 / 2, wr = written(c.fmt, g.w, g.h);
     handle_nvdec h = jm_nvdec_create_handle();
@@ -103,7 +117,6 @@ static int run_raw(const raw_cfg &c, unsigned seed, int laziness)
     if (r != 0) {
         CHECK(c.tolerate_errors, "init failed: %d (%s)", r, jmc_last_error());
         jm_nvdec_deinit(h);
-        sim_clean(base, false);
         return 0;
     }
     /* caller-side buffers */
@@ -235,7 +248,6 @@ static int run_raw(const raw_cfg &c, unsigned seed, int laziness)
     else if (c.out_kind != OUT_PINNED) free(out_base);
     for (uint8_t *d : dsurf) if (d) cudaFree(d);
     if (up) { cudaStreamDestroy(up); if (up_ev) cudaEventDestroy(up_ev); if (up_stage) cudaFreeHost(up_stage); }
-    sim_clean(base, false);
     return delivered;
 }
 
@@ -348,8 +360,8 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
         CHECK(delivered + dropped == (int)want.size(), "delivered %d + dropped %d != %zu", delivered, dropped, want.size());
         CHECK(dropped == 0 || saw_drop_report, "pictures were dropped but no call reported it");
     }
-    if (c.pics_per_packet >= 2 && c.map_limit >= 2) CHECK(g_fake_max_batch >= 2, "several pictures per packet were never converted by one launch (max batch %d)", g_fake_max_batch);
-    CHECK(g_fake_max_batch <= c.map_limit, "a launch took %d pictures with a map limit of %d", g_fake_max_batch, c.map_limit);
+    if (c.pics_per_packet >= 2 && c.map_limit >= 2) CHECK(g_fake_max_batch >= 2, "several pictures per packet were never converted by one launch (max batch %d)", g_fake_max_batch.load());
+    CHECK(g_fake_max_batch <= c.map_limit, "a launch took %d pictures with a map limit of %d", g_fake_max_batch.load(), c.map_limit);
     if (pinned) jm_nvdec_memory_release_host(pinned, h);
     jm_nvdec_deinit(h);
     sim_clean(base, true);
@@ -402,6 +414,119 @@ static void run_nvenc(int fmt, const geom &g, unsigned seed, int laziness)
         if (fmt != JM_NVENC_FMT_YV12) CHECK(r == JM_NVENC_ERR_INVALID_PARAM, "short buffer accepted: %d", r);
     }
     jm_nvenc_deinit(h);
+    sim_clean(base, false);
+}
+
+/* ---- several handles on one device, calls interleaved (the per-device cap on queued deliveries) ------------------- */
+static void run_multi(unsigned seed, int laziness)
+{
+    fake_cuda_reset(seed, laziness, 2);
+    cudaSetDevice(0);
+    const fake_cuda_counts base = fake_cuda_live();
+    const int N = 5, FRAMES = 22;
+    const geom gs[N] = { { 640, 360, 640 }, { 64, 36, 64 }, { 1280, 720, 1280 }, { 199, 77, 256 }, { 640, 360, 768 } };
+    const int delays[N] = { 0, 2, 1, 3, 0 }, outs[N] = { OUT_PAGEABLE, OUT_PINNED, OUT_REF, OUT_PAGEABLE, OUT_PINNED };
+    handle_nvdec h[N];
+    std::vector<std::vector<uint8_t>> want[N];
+    size_t next[N] = {};
+    uint8_t *out[N] = {};
+    std::vector<uint8_t> pageable[N];
+    for (int i = 0; i < N; i++) {
+        h[i] = jm_nvdec_create_handle();
+        jm_nvdec_set_option("display_delay", delays[i], h[i]);
+        jm_nvdec_set_option("copy_threads", i == 0 ? 2 : 0, h[i]);
+        CHECK(jm_nvdec_init(JM_NVDEC_CODEC_RAW_NV12, i & 1, nullptr, 0, h[i]) == 0, "init handle %d", i);
+        const size_t cap = (size_t)gs[i].w * gs[i].h * 3 / 2 + 8;
+        if (outs[i] == OUT_PINNED) { void *p = nullptr; jm_nvdec_memory_alloc_host(&p, (int)cap, h[i]); out[i] = (uint8_t *)p; }
+        else { pageable[i].resize(cap); out[i] = pageable[i].data(); }
+    }
+    auto fetch = [&](int i) {
+        const size_t tight = (size_t)gs[i].w * gs[i].h * 3 / 2;
+        int len = (int)tight + 8, rr;
+        const uint8_t *got = out[i];
+        if (outs[i] == OUT_REF) { const unsigned char *f = nullptr; rr = jm_nvdec_output_frame_ref(&f, &len, h[i]); got = f; }
+        else { memset(out[i], 0xA5, tight + 8); rr = jm_nvdec_output_frame(out[i], &len, h[i]); }
+        CHECK(rr == (int)tight, "handle %d: output_frame returned %d", i, rr);
+        const size_t n = outs[i] == OUT_REF ? written(i & 1, gs[i].w, gs[i].h) : tight + 8;
+        CHECK(next[i] < want[i].size() && rr > 0 && memcmp(got, want[i][next[i]].data(), n) == 0, "handle %d frame %zu differs", i, next[i]);
+        next[i]++;
+    };
+    for (int f = 0; f < FRAMES; f++)
+        for (int i = 0; i < N; i++) {
+            const std::vector<uint8_t> s = surface(gs[i], seed * 77 + (unsigned)(f * N + i));
+            want[i].push_back(expected(s, gs[i], i & 1));
+            std::vector<uint8_t> pkt(sizeof(jm_nvdec_raw_packet) + s.size());
+            jm_nvdec_raw_packet hd;
+            memset(&hd, 0, sizeof(hd));
+            hd.magic = JM_NVDEC_RAW_MAGIC; hd.width = gs[i].w; hd.height = gs[i].h; hd.pitch = gs[i].pitch;
+            memcpy(pkt.data(), &hd, sizeof(hd));
+            memcpy(pkt.data() + sizeof(hd), s.data(), s.size());
+            int got = 0;
+            CHECK(jm_nvdec_decode_frame(pkt.data(), (int)pkt.size(), &got, h[i]) == 0, "handle %d decode", i);
+            if (got && (f + i) % 7 != 3) fetch(i);                          /* now and then a caller skips a frame: it is replaced, not leaked */
+            else if (got) next[i]++;
+        }
+    for (int i = 0; i < N; i++) {
+        for (int k = 0; k < FRAMES + 8 && !jm_nvdec_is_exit(h[i]); k++) { int got = 0; jm_nvdec_decode_frame(nullptr, 0, &got, h[i]); if (got) fetch(i); }
+        CHECK(next[i] == want[i].size() && jm_nvdec_dropped_frames(h[i]) == 0, "handle %d: %zu of %zu frames, %d dropped", i, next[i], want[i].size(), jm_nvdec_dropped_frames(h[i]));
+    }
+    /* deinit in an order that leaves deliveries of other handles queued */
+    for (int i : { 2, 0, 4, 1, 3 }) {
+        if (outs[i] == OUT_PINNED) jm_nvdec_memory_release_host(out[i], h[i]);
+        jm_nvdec_deinit(h[i]);
+    }
+    sim_clean(base, false);
+}
+
+/* ---- jmc_pipeline_*: the batch pipeline the bench's e2e leg uses --------------------------------------------------- */
+static void run_pipeline(const geom &g, int fmt, int sub, int depth, int batches, bool device_input, unsigned seed, int laziness)
+{
+    fake_cuda_reset(seed, laziness, 2);
+    cudaSetDevice(1);                                                       /* the caller sits on another device */
+    const fake_cuda_counts base = fake_cuda_live();
+    jmc_ctx *ctx = nullptr;
+    CHECK(jmc_ctx_create(0, &ctx) == JMC_OK, "ctx");
+    jmc_job shape;
+    memset(&shape, 0, sizeof(shape));
+    jmc_job_nvdec(&shape, g.w, g.h, g.pitch, fmt);
+    shape.n_frames = sub;
+    const size_t surf_bytes = (size_t)g.pitch * g.h * 3 / 2, tight = (size_t)g.w * g.h * 3 / 2;
+    jmc_pipeline *p = nullptr;
+    CHECK(jmc_pipeline_create(ctx, &shape, surf_bytes, depth, &p) == JMC_OK, "pipeline_create (%s)", jmc_last_error());
+    const size_t n = (size_t)sub * batches;
+    void *hin = nullptr, *hout = nullptr, *din = nullptr;
+    jmc_alloc_host(ctx, surf_bytes * n, 0, &hin);
+    jmc_alloc_host(ctx, tight * n + 8, 0, &hout);
+    memset(hout, 0xA5, tight * n + 8);
+    std::vector<std::vector<uint8_t>> want;
+    for (size_t f = 0; f < n; f++) {
+        const std::vector<uint8_t> s = surface(g, seed * 31 + (unsigned)f);
+        memcpy((uint8_t *)hin + f * surf_bytes, s.data(), surf_bytes);
+        want.push_back(expected(s, g, fmt));
+    }
+    if (device_input) { jmc_alloc_device(ctx, surf_bytes * n, &din); jmc_memcpy_h2d(ctx, din, hin, surf_bytes * n); memset(hin, 0x11, surf_bytes * n); }
+    for (int b = 0; b < batches; b++) {
+        const int nf = b == batches - 1 && sub > 1 ? sub - 1 : sub;       /* a short last batch */
+        const int slot = jmc_pipeline_submit(p, device_input ? nullptr : (uint8_t *)hin + (size_t)b * sub * surf_bytes,
+                                             device_input ? (uint8_t *)din + (size_t)b * sub * surf_bytes : nullptr,
+                                             (uint8_t *)hout + (size_t)b * sub * tight, nullptr, nf);
+        CHECK(slot >= 0 && slot < depth, "submit returned %d (%s)", slot, jmc_last_error());
+        int dev = -1; cudaGetDevice(&dev);
+        CHECK(dev == 1, "submit left device %d current", dev);
+        if (b % 3 == 1) CHECK(jmc_pipeline_wait(p, slot) == JMC_OK, "wait");
+    }
+    CHECK(jmc_pipeline_drain(p) == JMC_OK, "drain");
+    for (size_t f = 0; f < n; f++) {
+        const bool skipped = sub > 1 && f == n - 1;                         /* the frame the short batch left out */
+        if (skipped) { CHECK(((uint8_t *)hout)[f * tight] == 0xA5, "a frame beyond the short batch was written"); continue; }
+        CHECK(memcmp((uint8_t *)hout + f * tight, want[f].data(), written(fmt, g.w, g.h)) == 0, "pipeline frame %zu differs", f);
+    }
+    CHECK(jmc_pipeline_d2h_bytes(p) > 0 && (device_input || jmc_pipeline_h2d_bytes(p) > 0), "byte counters");
+    jmc_pipeline_destroy(p);
+    if (din) jmc_free_device(ctx, din);
+    jmc_free_host(ctx, hin);
+    jmc_free_host(ctx, hout);
+    jmc_ctx_destroy(ctx);
     sim_clean(base, false);
 }
 
@@ -545,6 +670,52 @@ int main(int argc, char **argv)
         }
     }
 
+    if (want_run("multi")) {
+        for (int lazy = 0; lazy <= 2; lazy++)
+            for (unsigned seed = 1; seed <= (lazy == 1 ? 12u : 2u); seed++) {
+                char name[100];
+                snprintf(name, sizeof(name), "multi-handle lazy=%d seed %u", lazy, seed);
+                g_ctx = name;
+                run_multi(seed, lazy);
+            }
+    }
+
+    if (want_run("pipeline")) {
+        for (int lazy = 0; lazy <= 2; lazy++)
+            for (int depth = 1; depth <= 3; depth++)
+                for (int dev_in = 0; dev_in <= 1; dev_in++) {
+                    char name[100];
+                    snprintf(name, sizeof(name), "pipeline lazy=%d depth=%d device_input=%d", lazy, depth, dev_in);
+                    g_ctx = name;
+                    run_pipeline(geoms[(depth + dev_in) % 2 == 0 ? 1 : 3], (depth + lazy) & 1, 3, depth, 7, dev_in != 0, 40u + (unsigned)depth, lazy);
+                    run_pipeline(geoms[0], 1, 1, depth, 9, dev_in != 0, 50u + (unsigned)depth, lazy);
+                }
+    }
+
+    if (want_run("threads")) {
+        /* one handle per thread, four threads at once on one device (random-progress mode): built with ThreadSanitizer
+         * by the test suite, this is the check of what handles share -- the per-device delivery count, the handle
+         * count, the environment switches, the last-error string */
+        g_ctx = "threads";
+        fake_cuda_reset(11, 1, 2);
+        cudaSetDevice(0);
+        const fake_cuda_counts base = fake_cuda_live();
+        std::vector<std::thread> ts;
+        for (int t = 0; t < 4; t++)
+            ts.emplace_back([t, &geoms] {
+                for (int k = 0; k < 6; k++) {
+                    char name[64];
+                    snprintf(name, sizeof(name), "threads t=%d k=%d", t, k);
+                    g_ctx = name;
+                    raw_cfg c = { geoms[(t + k) % 5], (t + k) & 1, (t * 3 + k) % 4, (t + 2 * k) % 6, (2 * t + k) % 6, (t + k) % 3, 10, 0, false };
+                    raw_session(c, 1000u + (unsigned)(t * 10 + k));
+                }
+            });
+        for (auto &t : ts) t.join();
+        g_ctx = "threads";
+        sim_clean(base, false);
+    }
+
     if (want_run("nvenc")) {
         for (int lazy = 0; lazy <= 2; lazy++)
             for (int fmt : { JM_NVENC_FMT_NV12, JM_NVENC_FMT_YV12, JM_NVENC_FMT_ARGB })
@@ -555,7 +726,7 @@ int main(int argc, char **argv)
                     run_nvenc(fmt, g, 9, lazy);
                 }
     }
-    printf("%d checks, %d failed\n", g_checks, g_fail);
-    printf(g_fail ? "FAILED\n" : "OK\n");
-    return g_fail ? 1 : 0;
+    printf("%d checks, %d failed\n", g_checks.load(), g_fail.load());
+    printf(g_fail.load() ? "FAILED\n" : "OK\n");
+    return g_fail.load() ? 1 : 0;
 }

@@ -5,14 +5,15 @@
  */
 #include <string.h>
 
+#include <atomic>
 #include <vector>
 
 #include "jmc_internal.h"
 #include "../../oracle/jm_oracle.h"
 
-int g_fake_launches = 0;            /* launches seen (the tests check batching) */
-int g_fake_frames = 0;              /* frames converted */
-int g_fake_max_batch = 0;
+std::atomic<int> g_fake_launches{0};        /* launches seen (the tests check batching) */
+std::atomic<int> g_fake_frames{0};          /* frames converted */
+std::atomic<int> g_fake_max_batch{0};
 
 static void *frame_of(const jmc_frames &f, const std::vector<void *> &list, int i)
 {
@@ -41,7 +42,7 @@ int jmc_launch_job(jmc_ctx *ctx, const jmc_job *job, cudaStream_t stream)
     }
     g_fake_launches++;
     g_fake_frames += j.n_frames;
-    if (j.n_frames > g_fake_max_batch) g_fake_max_batch = j.n_frames;
+    for (int seen = g_fake_max_batch.load(); j.n_frames > seen && !g_fake_max_batch.compare_exchange_weak(seen, j.n_frames);) {}
     fake_cuda_enqueue(stream, [j, surf_l, tight_l] {
         for (int f = 0; f < j.n_frames; f++) {
             uint8_t *surf = (uint8_t *)frame_of(j.surf, surf_l, f), *tight = (uint8_t *)frame_of(j.tight, tight_l, f);

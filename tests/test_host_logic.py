@@ -111,17 +111,31 @@ def sim_sanitized(tmp_path_factory):
     return _build_sim(str(tmp_path_factory.mktemp("sim_san")), flags)
 
 
-@pytest.mark.parametrize("scenario", ["raw", "cuvid", "nvenc", "alloc-failure"])
+@pytest.mark.parametrize("scenario", ["raw", "cuvid", "nvenc", "alloc-failure", "multi", "pipeline", "threads"])
 def test_host_layer_on_the_cuda_simulator(sim_sanitized, scenario):
     """jm_nv_dec.cu / jmnv_enc.cu / jmc_runtime.cu, unchanged, through the public C API on a CUDA runtime simulator whose
     streams run work as late as CUDA allows (only when waited for / at random moments / at once): every frame against
     the oracle for every input kind x out_buf kind x display delay, the NVDEC front-end against the fake library
     (batch drain, map limit, format change, overflow), the encoder-input API, an allocation failure at every
-    allocation site; no leak, no free under pending work, caller's device restored -- under ASan + UBSan."""
+    allocation site, five handles interleaved on one device, the jmc_pipeline_* batch pipeline, four threads with a
+    handle each; no leak, no free under pending work, caller's device restored -- under ASan + UBSan."""
     exe, lib = sim_sanitized
     p = subprocess.run([exe, lib, scenario], capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1"))
     assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-3000:] + p.stderr[-3000:]
+
+
+def test_handles_on_several_threads_under_thread_sanitizer(tmp_path):
+    """What handles share across threads (per-device delivery count, handle count, environment switches, last-error
+    string): four threads, one handle each, on the simulator in random-progress mode, built with -fsanitize=thread."""
+    probe = subprocess.run(["g++", "-fsanitize=thread", "-x", "c++", "-", "-o", os.devnull], input="int main(){return 0;}", capture_output=True, text=True)
+    if probe.returncode != 0:
+        pytest.skip("no thread sanitizer runtime in this toolchain")
+    exe, lib = _build_sim(str(tmp_path / "tsan"), ["-g", "-O1", "-fsanitize=thread"])
+    p = subprocess.run([exe, lib, "threads"], capture_output=True, text=True, timeout=900, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1"))
+    if "FATAL: ThreadSanitizer" in p.stderr and "unexpected memory mapping" in p.stderr:
+        pytest.skip("thread sanitizer cannot map its shadow memory in this container")
+    assert p.returncode == 0 and p.stdout.strip().endswith("OK") and "WARNING: ThreadSanitizer" not in p.stderr, p.stdout[-2000:] + p.stderr[-3000:]
 
 
 MUTATIONS = {
