@@ -530,6 +530,98 @@ static void run_pipeline(const geom &g, int fmt, int sub, int depth, int batches
     sim_clean(base, false);
 }
 
+/* ---- malformed input ------------------------------------------------------------------------------------------------ */
+static void run_fuzz(unsigned seed, int laziness)
+{
+    fake_cuda_reset(seed, laziness, 2);
+    cudaSetDevice(0);
+    const fake_cuda_counts base = fake_cuda_live();
+    std::mt19937 rng(seed);
+    handle_nvdec h = jm_nvdec_create_handle();
+    CHECK(jm_nvdec_init(JM_NVDEC_CODEC_RAW_NV12, 1, nullptr, 0, h) == 0, "init");
+    const geom g = { 64, 36, 64 };
+    std::vector<uint8_t> out((size_t)g.w * g.h * 3 / 2 + 8);
+    std::vector<std::vector<uint8_t>> want;
+    size_t next = 0;
+    int good = 0;
+    /* calls before any frame exists */
+    int len = (int)out.size();
+    CHECK(jm_nvdec_output_frame(out.data(), &len, h) == -1, "output_frame without a frame");
+    CHECK(jm_nvdec_output_frame(nullptr, &len, h) == -1 && jm_nvdec_output_frame(out.data(), nullptr, h) == -1, "NULL arguments");
+    int dummy = 0;
+    CHECK(jm_nvdec_decode_frame(out.data(), 16, nullptr, h) == 0, "NULL got_frame is tolerated like the reference does");
+    for (int it = 0; it < 400; it++) {
+        const int kind = (int)(rng() % 8);
+        std::vector<uint8_t> pkt;
+        bool valid = false;
+        jm_nvdec_raw_packet hd;
+        memset(&hd, 0, sizeof(hd));
+        hd.magic = JM_NVDEC_RAW_MAGIC; hd.width = g.w; hd.height = g.h; hd.pitch = g.pitch;
+        const std::vector<uint8_t> s = surface(g, seed * 999 + (unsigned)it);
+        switch (kind) {
+        case 0: valid = true; break;
+        case 1: hd.magic ^= 1u << (rng() % 32); break;                      /* wrong magic */
+        case 2: hd.width = -(int)(rng() % 5000) - 1; break;                 /* negative size */
+        case 3: hd.pitch = g.w - 1 - (int)(rng() % 60); break;              /* pitch below the width */
+        case 4: hd.height = 0x7fffffff / 3; hd.pitch = 0x7fffffff; hd.width = 100; break;     /* byte count overflows an int */
+        case 5: hd.flags = JM_NVDEC_RAW_DEVICE_PTR | JM_NVDEC_RAW_WAIT_EVENT; break;           /* claims an event, too short for one */
+        case 6: hd.height = g.h * 50; break;                                /* payload much shorter than the header says */
+        default: break;                                                     /* truncated below */
+        }
+        pkt.resize(sizeof(hd) + s.size());
+        memcpy(pkt.data(), &hd, sizeof(hd));
+        memcpy(pkt.data() + sizeof(hd), s.data(), s.size());
+        int plen = (int)pkt.size();
+        if (kind == 7) plen = 1 + (int)(rng() % (sizeof(hd) + 40));          /* cut inside the header or just after it (0 would mean end of stream) */
+        if (kind == 5) plen = (int)sizeof(hd);
+        if (valid) want.push_back(expected(s, g, 1));
+        int got = -1;
+        const int r = jm_nvdec_decode_frame(pkt.data(), plen, &got, h);
+        CHECK(r == 0, "decode_frame returned %d for packet kind %d", r, kind);
+        CHECK(valid ? got == 1 : got == 0, "packet kind %d: got_frame %d", kind, got);
+        if (got == 1) {
+            /* a buffer that is too small first: -2, *out_len untouched, the frame stays fetchable (nv_dec.cpp:773-776) */
+            int small = (int)(rng() % ((size_t)g.w * g.h * 3 / 2));
+            const int before = small;
+            CHECK(jm_nvdec_output_frame(out.data(), &small, h) == -2 && small == before, "short out_buf");
+            memset(out.data(), 0xA5, out.size());
+            len = (int)out.size();
+            const int rr = jm_nvdec_output_frame(out.data(), &len, h);
+            CHECK(rr == g.w * g.h * 3 / 2 && next < want.size() && memcmp(out.data(), want[next].data(), out.size()) == 0, "valid frame %zu after %d malformed packets", next, it - good);
+            next++; good++;
+        }
+    }
+    (void)dummy;
+    CHECK(next == want.size(), "%zu of %zu valid frames", next, want.size());
+    jm_nvdec_deinit(h);
+    /* calls on things that are not there */
+    int got = 5;
+    CHECK(jm_nvdec_decode_frame(out.data(), 10, &got, nullptr) == 0 && got == 0, "NULL handle");
+    CHECK(jm_nvdec_is_exit(nullptr) == true && jm_nvdec_dropped_frames(nullptr) == -1 && jm_nvdec_deinit(nullptr) == -1, "NULL handle queries");
+    handle_nvdec fresh = jm_nvdec_create_handle();                          /* never initialised */
+    CHECK(jm_nvdec_decode_frame(out.data(), 10, &got, fresh) == 0 && got == 0, "uninitialised handle");
+    len = 10;
+    CHECK(jm_nvdec_output_frame(out.data(), &len, fresh) == -1, "uninitialised handle output");
+    void *p = nullptr;
+    CHECK(jm_nvdec_memory_alloc_host(&p, 100, fresh) == -1 && jm_nvdec_memory_register_host(out.data(), 100, fresh) == -1, "uninitialised handle memory calls");
+    CHECK(jm_nvdec_set_option("no_such_option", 1, fresh) == -1 && jm_nvdec_set_option("display_delay", 99, fresh) == -1 && jm_nvdec_set_option("map_limit", 0, fresh) == -1, "bad options");
+    CHECK(jm_nvdec_init(JM_NVDEC_CODEC_RAW_NV12, 1, nullptr, 0, fresh) == 0, "init after all that");
+    jm_nvdec_set_device(7, fresh);                                          /* refused on a live handle */
+    jm_nvdec_deinit(fresh);
+    handle_nvdec bad = jm_nvdec_create_handle();
+    jm_nvdec_set_device(7, bad);
+    CHECK(jm_nvdec_init(JM_NVDEC_CODEC_RAW_NV12, 1, nullptr, 0, bad) == -3, "device id beyond the device count (nv_dec.cpp:227-231)");
+    jm_nvdec_deinit(bad);
+    sim_clean(base, false);
+    /* no device at all (nv_dec.cpp:219-222) */
+    fake_cuda_reset(seed, laziness, 0);
+    handle_nvdec none = jm_nvdec_create_handle();
+    CHECK(jm_nvdec_init(JM_NVDEC_CODEC_RAW_NV12, 1, nullptr, 0, none) == -2, "no CUDA device");
+    CHECK(jm_nvdec_is_hw_support() == false, "is_hw_support without a device");
+    jm_nvdec_deinit(none);
+    fake_cuda_reset(seed, laziness, 2);
+}
+
 static const char *in_name[] = { "host-pageable", "host-pinned", "host-registered", "device", "device+sync", "device+event" };
 static const char *out_name[] = { "pageable", "pinned", "registered", "lazy-pin", "device", "ref" };
 
@@ -668,6 +760,16 @@ int main(int argc, char **argv)
             cuvid_cfg c = { { { 200, 120, 0 }, { 64, 48, 0 } }, 20, 1 + (int)(seed % 8), 1 + (int)(seed % 8), (int)(seed % 5), (int)(seed % 3), (int)(seed & 1), OUT_PAGEABLE, false };
             run_cuvid(c, seed, 1, fake_lib);
         }
+    }
+
+    if (want_run("fuzz")) {
+        for (int lazy = 0; lazy <= 2; lazy++)
+            for (unsigned seed = 1; seed <= 4; seed++) {
+                char name[100];
+                snprintf(name, sizeof(name), "fuzz lazy=%d seed %u", lazy, seed);
+                g_ctx = name;
+                run_fuzz(seed, lazy);
+            }
     }
 
     if (want_run("multi")) {

@@ -111,14 +111,14 @@ def sim_sanitized(tmp_path_factory):
     return _build_sim(str(tmp_path_factory.mktemp("sim_san")), flags)
 
 
-@pytest.mark.parametrize("scenario", ["raw", "cuvid", "nvenc", "alloc-failure", "multi", "pipeline", "threads"])
+@pytest.mark.parametrize("scenario", ["raw", "cuvid", "nvenc", "alloc-failure", "multi", "pipeline", "threads", "fuzz"])
 def test_host_layer_on_the_cuda_simulator(sim_sanitized, scenario):
     """jm_nv_dec.cu / jmnv_enc.cu / jmc_runtime.cu, unchanged, through the public C API on a CUDA runtime simulator whose
     streams run work as late as CUDA allows (only when waited for / at random moments / at once): every frame against
     the oracle for every input kind x out_buf kind x display delay, the NVDEC front-end against the fake library
     (batch drain, map limit, format change, overflow), the encoder-input API, an allocation failure at every
     allocation site, five handles interleaved on one device, the jmc_pipeline_* batch pipeline, four threads with a
-    handle each; no leak, no free under pending work, caller's device restored -- under ASan + UBSan."""
+    handle each, malformed packets and calls on missing / uninitialised handles; no leak, no free under pending work, caller's device restored -- under ASan + UBSan."""
     exe, lib = sim_sanitized
     p = subprocess.run([exe, lib, scenario], capture_output=True, text=True, timeout=900,
                        env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1"))
