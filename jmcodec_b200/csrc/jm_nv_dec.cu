@@ -846,6 +846,12 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
         }
         const int slot = c->pool_next;
         c->pool_next = (c->pool_next + 1) % NVDEC_MAX_FRAMES;
+        /* a surface that could not be converted for ten packets (no ring slot to be had: out of memory) is given up before
+         * its upload surface is written again -- never converted from somebody else's bytes */
+        for (auto it = c->pending.begin(); it != c->pending.end();) {
+            if (it->pool_slot == slot) { it = c->pending.erase(it); c->dropped++; c->drop_flag = true; }
+            else ++it;
+        }
         /* uploads and kernels share the convert stream: the next upload into this surface is ordered behind the kernel that read it */
         if (!c->pool[slot]) {
             if (cudaMalloc((void **)&c->pool[slot], c->pool_bytes ? c->pool_bytes : 1) != cudaSuccess) { cudaGetLastError(); return -1; }

@@ -24,7 +24,7 @@
 #include "../../oracle/jm_oracle.h"
 
 extern std::atomic<int> g_fake_launches, g_fake_frames, g_fake_max_batch;
-static int g_arm_kind = -1, g_arm_k = 0;      /* allocation failure to arm right after the simulator reset */
+static int g_arm_kind = -1, g_arm_k = 0, g_arm_count = 1;      /* allocation failure(s) to arm right after the simulator reset */
 
 static std::atomic<int> g_fail{0}, g_checks{0};
 static thread_local std::string g_ctx;
@@ -94,7 +94,7 @@ static int run_raw(const raw_cfg &c, unsigned seed, int laziness)
     fake_cuda_reset(seed, laziness, n_dev);
     cudaSetDevice(0);
     const fake_cuda_counts base = fake_cuda_live();
-    if (g_arm_kind >= 0) fake_cuda_fail_alloc(g_arm_kind, g_arm_k);
+    if (g_arm_kind >= 0) fake_cuda_fail_alloc(g_arm_kind, g_arm_k, g_arm_count);
     const int n = raw_session(c, seed);
     sim_clean(base, false);
     return n;
@@ -728,10 +728,24 @@ int main(int argc, char **argv)
                     snprintf(name, sizeof(name), "alloc-failure kind %d at %d variant %d", kind, k, variant);
                     g_ctx = name;
                     raw_cfg c = { geoms[variant == 2 ? 2 : 0], 1, variant, variant == 1 ? IN_DEVICE : IN_PAGEABLE, variant == 1 ? OUT_PINNED : OUT_PAGEABLE, variant == 2 ? 2 : 0, 6, 0, true };
-                    g_arm_kind = kind; g_arm_k = k;
+                    g_arm_kind = kind; g_arm_k = k; g_arm_count = 1;
                     run_raw(c, 5, 1);
                     g_arm_kind = -1;
                 }
+        /* an allocator that stays empty for a while: many failures in a row, then memory is back */
+        for (int kind = 0; kind < 2; kind++)
+            for (int k : { 3, 9, 14, 22 })
+                for (int count : { 5, 40, 200 })
+                    for (int lazy = 0; lazy <= 2; lazy++) {
+                        char name[100];
+                        snprintf(name, sizeof(name), "alloc-failure kind %d: %d in a row from %d lazy=%d", kind, count, k, lazy);
+                        g_ctx = name;
+                        raw_cfg c = { geoms[0], 1, (k & 1) * 2, IN_PAGEABLE, OUT_PAGEABLE, 0, 40, 0, true };
+                        g_arm_kind = kind; g_arm_k = k; g_arm_count = count;
+                        const int n = run_raw(c, 6, lazy);
+                        g_arm_kind = -1; g_arm_count = 1;
+                        if (count <= 5) CHECK(n >= 20, "only %d of 40 frames were delivered although just %d allocations failed", n, count);
+                    }
     }
 
     if (want_run("cuvid")) {

@@ -102,8 +102,9 @@ struct fake_cuda_counts { size_t device, pinned, registered, streams, events, pe
 fake_cuda_counts fake_cuda_live();
 /* is [p, p+n) inside one live device allocation? (for "kernels" to check their accesses) */
 bool fake_cuda_is_device_range(const void *p, size_t n);
-/* fail the k-th next allocation of the given kind (0 device, 1 pinned, 2 event): error-path tests; k < 0 disables */
-void fake_cuda_fail_alloc(int kind, int k);
+/* fail `count` allocations of the given kind (0 device, 1 pinned, 2 event) starting with the k-th next one: error-path
+ * tests; k < 0 disables */
+void fake_cuda_fail_alloc(int kind, int k, int count = 1);
 /* record a problem from test code that runs as a "kernel" */
 void fake_cuda_complain(const char *msg);
 #endif

@@ -54,7 +54,7 @@ struct sim {
     std::vector<std::unique_ptr<fake_event>> events;
     std::vector<std::string> errors;
     cudaError_t last = cudaSuccess;
-    int fail_kind = -1, fail_in = -1;
+    int fail_kind = -1, fail_in = -1, fail_count = 0;
     int depth = 0;
 };
 
@@ -76,8 +76,10 @@ void complain(const std::string &s)
 bool should_fail(int kind)
 {
     sim &s = S();
-    if (s.fail_kind != kind || s.fail_in < 0) return false;
-    if (s.fail_in-- == 0) { s.fail_kind = -1; return true; }
+    if (s.fail_kind != kind) return false;
+    if (s.fail_in > 0) { s.fail_in--; return false; }
+    if (s.fail_count > 0) { if (--s.fail_count == 0) s.fail_kind = -1; return true; }
+    s.fail_kind = -1;
     return false;
 }
 
@@ -234,6 +236,7 @@ void fake_cuda_reset(unsigned seed, int laziness, int n_devices)
     s.n_devices = n_devices;
     s.last = cudaSuccess;
     s.fail_kind = s.fail_in = -1;
+    s.fail_count = 0;
     /* dead streams / events are only ever forgotten here */
     s.streams.erase(std::remove_if(s.streams.begin(), s.streams.end(), [](const std::unique_ptr<fake_stream> &p) { return !p->alive; }), s.streams.end());
     s.events.erase(std::remove_if(s.events.begin(), s.events.end(), [](const std::unique_ptr<fake_event> &p) { return !p->alive; }), s.events.end());
@@ -280,11 +283,12 @@ void fake_cuda_complain(const char *msg)
     complain(msg);
 }
 
-void fake_cuda_fail_alloc(int kind, int k)
+void fake_cuda_fail_alloc(int kind, int k, int count)
 {
     LOCK;
-    S().fail_kind = kind;
+    S().fail_kind = k < 0 ? -1 : kind;
     S().fail_in = k;
+    S().fail_count = count;
 }
 
 /* ---- runtime ---------------------------------------------------------------------------------------------------- */

@@ -149,6 +149,8 @@ MUTATIONS = {
     "delivery chunks copied out without waiting for them": (
         "auto wait_chunk = [&](int i) { if (cudaEventSynchronize(s.delivered[i]) != cudaSuccess) { cudaGetLastError(); failed = true; } };",
         "auto wait_chunk = [&](int i) { (void)i; (void)failed; };", "raw"),
+    "upload surface written again while an unconverted frame still refers to it": (
+        "if (it->pool_slot == slot) { it = c->pending.erase(it); c->dropped++; c->drop_flag = true; }", "if (false) { }", "alloc-failure"),
     "direct delivery started before the launch finished and never waited for": (
         "if (cudaEventRecord(s.direct, ds) != cudaSuccess || cudaEventSynchronize(s.direct) != cudaSuccess) { cudaGetLastError(); return -1; }", ";", "raw"),
 }
