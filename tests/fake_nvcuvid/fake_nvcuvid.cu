@@ -58,6 +58,15 @@ struct fake_parser {
 };
 
 struct stats_t { int maps, unmaps, cur_mapped, max_mapped, map_refused, decoders; } g_stats;
+/* fault injection (fake_nvcuvid_fail): the next `count` calls of one kind, after `after` good ones, fail */
+struct fault_t { int what, after, count; } g_fault = { 0, 0, 0 };
+bool inject(int what)
+{
+    if (g_fault.what != what || g_fault.count <= 0) return false;
+    if (g_fault.after > 0) { g_fault.after--; return false; }
+    g_fault.count--;
+    return true;
+}
 cudaStream_t g_poison = nullptr;
 
 struct fake_decoder {
@@ -195,21 +204,31 @@ FAKE_API int cuvidParseVideoData(CUvideoparser h, CUVIDSOURCEDATAPACKET *pkt)
 FAKE_API int cuvidCreateDecoder(CUvideodecoder *out, CUVIDDECODECREATEINFO *ci)
 {
     if (!out || !ci || ci->OutputFormat != CUVID_SURFACE_NV12 || ci->ulNumDecodeSurfaces < 1 || ci->ulNumOutputSurfaces < 1) return 1;
+    if (inject(3)) return 2;
     fake_decoder *d = new fake_decoder();
     d->ci = *ci;
     d->pitch = (ci->ulTargetWidth + 511) & ~(size_t)511;                /* decoder-chosen pitch, like the real one */
     d->rows = ci->ulTargetHeight * 3 / 2 + 2;
-    for (unsigned long i = 0; i < ci->ulNumDecodeSurfaces; i++) {
+    bool ok = true;
+    for (unsigned long i = 0; ok && i < ci->ulNumDecodeSurfaces; i++) {
         unsigned char *p = nullptr;
-        if (cudaMalloc(&p, d->pitch * d->rows) != cudaSuccess) return 2;
+        ok = cudaMalloc(&p, d->pitch * d->rows) == cudaSuccess;
+        if (!ok) break;
         cudaMemset(p, 0xCD, d->pitch * d->rows);
         d->decode_surf.push_back(p);
     }
-    for (unsigned long i = 0; i < ci->ulNumOutputSurfaces; i++) {
+    for (unsigned long i = 0; ok && i < ci->ulNumOutputSurfaces; i++) {
         unsigned char *p = nullptr;
-        if (cudaMalloc(&p, d->pitch * d->rows) != cudaSuccess) return 2;
+        ok = cudaMalloc(&p, d->pitch * d->rows) == cudaSuccess;
+        if (!ok) break;
         d->out_surf.push_back(p);
         d->out_busy.push_back(false);
+    }
+    if (!ok) {                                                          /* out of device memory: nothing is kept */
+        for (unsigned char *p : d->decode_surf) cudaFree(p);
+        for (unsigned char *p : d->out_surf) cudaFree(p);
+        delete d;
+        return 2;
     }
     g_stats.decoders++;
     *out = d;
@@ -234,6 +253,7 @@ FAKE_API int cuvidDecodePicture(CUvideodecoder h, void *pic)
     if (!d || !pp || pp->CurrPicIdx < 0 || (size_t)pp->CurrPicIdx >= d->decode_surf.size()) return 1;
     const size_t w = d->ci.ulTargetWidth, hgt = d->ci.ulTargetHeight;
     if (pp->nBitstreamDataLen < w * hgt * 3 / 2) return 1;
+    if (inject(2)) return 2;
     /* "decode": the tight NV12 picture lands in the pitched decode surface (rows h + h/2) */
     if (cudaMemcpy2D(d->decode_surf[pp->CurrPicIdx], d->pitch, pp->pBitstreamData, w, w, hgt + hgt / 2, cudaMemcpyHostToDevice) != cudaSuccess) return 2;
     return 0;
@@ -243,6 +263,7 @@ FAKE_API int cuvidMapVideoFrame64(CUvideodecoder h, int idx, unsigned long long 
 {
     fake_decoder *d = (fake_decoder *)h;
     if (!d || !dptr || !pitch || idx < 0 || (size_t)idx >= d->decode_surf.size()) return 1;
+    if (inject(1)) return 2;
     size_t slot = 0;
     while (slot < d->out_surf.size() && d->out_busy[slot]) slot++;
     if (slot == d->out_surf.size()) { g_stats.map_refused++; return 3; }    /* more frames mapped than ulNumOutputSurfaces */
@@ -275,6 +296,13 @@ FAKE_API int cuvidUnmapVideoFrame64(CUvideodecoder h, unsigned long long dptr)
             return 0;
         }
     return 1;
+}
+
+/* test hook (not part of the NVDEC ABI): make the next `count` calls of one kind fail after `after` good ones.
+ * what: 1 cuvidMapVideoFrame, 2 cuvidDecodePicture, 3 cuvidCreateDecoder; 0 clears */
+FAKE_API void fake_nvcuvid_fail(int what, int after, int count)
+{
+    g_fault.what = what; g_fault.after = after; g_fault.count = count;
 }
 
 /* test hook (not part of the NVDEC ABI): v[0..5] = maps, unmaps, currently mapped, max mapped at once, refused maps,

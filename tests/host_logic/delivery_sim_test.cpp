@@ -270,7 +270,13 @@ struct cuvid_cfg {
     std::vector<geom> formats;      /* one sequence per entry (pitch unused) */
     int pics_per_format, pics_per_packet, map_limit, parser_delay, delay, fmt, out_kind;
     bool expect_drops;
+    int fault_what, fault_after, fault_count;       /* fake_nvcuvid_fail: 1 map, 2 decode, 3 create decoder */
+    bool lossy;                                     /* pictures may vanish without being counted (decode / create failures, out of memory) */
 };
+
+#include <dlfcn.h>
+typedef void (*fake_fail_fn)(int, int, int);
+typedef void (*fake_stats_fn)(int *, int);
 
 static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const char *fake_lib)
 {
@@ -278,6 +284,15 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
     cudaSetDevice(0);
     const fake_cuda_counts base = fake_cuda_live();
     setenv("JMC_NVCUVID_LIB", fake_lib, 1);
+    if (g_arm_kind >= 0) fake_cuda_fail_alloc(g_arm_kind, g_arm_k, g_arm_count);
+    void *fl = dlopen(fake_lib, RTLD_NOW | RTLD_LOCAL);                  /* the same library object the handle loads */
+    fake_fail_fn fake_fail = fl ? (fake_fail_fn)dlsym(fl, "fake_nvcuvid_fail") : nullptr;
+    fake_stats_fn fake_stats = fl ? (fake_stats_fn)dlsym(fl, "fake_nvcuvid_stats") : nullptr;
+    CHECK(fake_fail && fake_stats, "the fake NVDEC library lacks its test hooks");
+    if (!fake_fail || !fake_stats) return;
+    fake_stats(nullptr, 1);
+    fake_fail(c.fault_what, c.fault_after, c.fault_count);
+    const bool lossy = c.lossy || c.fault_what != 0 || g_arm_kind >= 0;
     char num[16];
     snprintf(num, sizeof(num), "%d", c.parser_delay);
     setenv("JMC_NVDEC_PARSER_DELAY", num, 1);
@@ -286,8 +301,8 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
     jm_nvdec_set_option("map_limit", c.map_limit, h);
     jm_nvdec_set_option("display_delay", c.delay, h);
     int r = jm_nvdec_init(JM_NVDEC_CODEC_AVC, c.fmt, nullptr, 0, h);
-    CHECK(r == 0, "init with the fake NVDEC library failed: %d (%s)", r, jmc_last_error());
-    if (r != 0) { jm_nvdec_deinit(h); return; }
+    CHECK(r == 0 || g_arm_kind >= 0, "init with the fake NVDEC library failed: %d (%s)", r, jmc_last_error());
+    if (r != 0) { jm_nvdec_deinit(h); fake_fail(0, 0, 0); dlclose(fl); sim_clean(base, true); return; }
     /* the stream and what must come out of it */
     std::vector<std::vector<uint8_t>> packets, want;
     std::vector<geom> want_geom;
@@ -322,14 +337,14 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
         memset(out, 0xA5, pinned_cap);
         int len = (int)pinned_cap;
         int rr = jm_nvdec_output_frame(out, &len, h);
-        CHECK(rr > 0, "output_frame returned %d (%s)", rr, jmc_last_error());
+        CHECK(rr > 0 || lossy, "output_frame returned %d (%s)", rr, jmc_last_error());
         if (rr <= 0) return;
         bool found = false;
         while (next_want < (int)want.size()) {
             const size_t i = (size_t)next_want++;
             const size_t n = (size_t)want_geom[i].w * want_geom[i].h * 3 / 2;
             if ((int)n == rr && memcmp(out, want[i].data(), n + 8 <= pinned_cap ? n + 8 : n) == 0) { found = true; break; }
-            if (!c.expect_drops) break;
+            if (!c.expect_drops && !lossy) break;
         }
         CHECK(found, "picture %d: bytes differ from the oracle (or out of order)", delivered);
         delivered++;
@@ -340,7 +355,7 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
         std::vector<uint8_t> copy = p;                                      /* handed over, then scribbled on */
         r = jm_nvdec_decode_frame(copy.data(), (int)copy.size(), &got_frame, h);
         if (r != 0) saw_drop_report = true;
-        CHECK(r == 0 || c.expect_drops, "decode_frame returned %d (%s)", r, jmc_last_error());
+        CHECK(r == 0 || c.expect_drops || lossy, "decode_frame returned %d (%s)", r, jmc_last_error());
         memset(copy.data(), 0x77, copy.size());
         int dev = -1; cudaGetDevice(&dev);
         CHECK(dev == 0, "decode_frame left device %d current", dev);
@@ -353,17 +368,26 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
     }
     CHECK(jm_nvdec_is_exit(h), "the handle never reported the end of the stream");
     const int dropped = jm_nvdec_dropped_frames(h);
-    if (!c.expect_drops) {
+    if (lossy) {
+        CHECK(delivered + dropped <= (int)want.size(), "delivered %d + dropped %d > %zu", delivered, dropped, want.size());
+        if (c.fault_what == 1 && g_arm_kind < 0) CHECK(delivered + dropped == (int)want.size() && (dropped >= 1 || c.fault_count < 2), "map failures: delivered %d + dropped %d of %zu", delivered, dropped, want.size());
+        CHECK(dropped == 0 || saw_drop_report, "pictures were dropped but no call reported it");
+    } else if (!c.expect_drops) {
         CHECK(delivered == (int)want.size(), "%d of %zu pictures delivered", delivered, want.size());
         CHECK(dropped == 0, "%d pictures dropped", dropped);
     } else {
         CHECK(delivered + dropped == (int)want.size(), "delivered %d + dropped %d != %zu", delivered, dropped, want.size());
         CHECK(dropped == 0 || saw_drop_report, "pictures were dropped but no call reported it");
     }
-    if (c.pics_per_packet >= 2 && c.map_limit >= 2) CHECK(g_fake_max_batch >= 2, "several pictures per packet were never converted by one launch (max batch %d)", g_fake_max_batch.load());
+    if (c.pics_per_packet >= 2 && c.map_limit >= 2 && !lossy) CHECK(g_fake_max_batch >= 2, "several pictures per packet were never converted by one launch (max batch %d)", g_fake_max_batch.load());
     CHECK(g_fake_max_batch <= c.map_limit, "a launch took %d pictures with a map limit of %d", g_fake_max_batch.load(), c.map_limit);
     if (pinned) jm_nvdec_memory_release_host(pinned, h);
     jm_nvdec_deinit(h);
+    int st[6] = {};
+    fake_stats(st, 0);
+    CHECK(st[2] == 0 && st[0] == st[1], "decoder surfaces left mapped: %d maps, %d unmaps, %d mapped now", st[0], st[1], st[2]);
+    fake_fail(0, 0, 0);
+    dlclose(fl);
     sim_clean(base, true);
 }
 
@@ -767,6 +791,30 @@ int main(int argc, char **argv)
             cuvid_cfg c = { { { 128, 72, 0 } }, 110, 8, 8, 2, 0, 1, OUT_PAGEABLE, true };
             run_cuvid(c, 500, lazy, fake_lib);
         }
+        /* the decoder library itself fails: maps, decodes, decoder creation (first sequence / after a format change) */
+        for (int lazy = 0; lazy <= 2; lazy++)
+            for (int what = 1; what <= 3; what++)
+                for (int after : { 0, 1, 5, 17 })
+                    for (int count : { 1, 3 }) {
+                        if (what == 3 && (after > 1 || count > 1)) continue;
+                        char name[120];
+                        snprintf(name, sizeof(name), "cuvid fault what=%d after=%d count=%d lazy=%d", what, after, count, lazy);
+                        g_ctx = name;
+                        cuvid_cfg c = { { { 320, 180, 0 }, { 198, 102, 0 } }, 20, 1 + (after % 4) * 2, 1 + (after + count) % 8, 2, after & 1, 1, OUT_PAGEABLE, false, what, after, count, true };
+                        run_cuvid(c, 600u + (unsigned)(what * 100 + after * 10 + count), lazy, fake_lib);
+                    }
+        /* device / pinned / event allocations fail under the NVDEC front-end */
+        for (int kind = 0; kind < 3; kind++)
+            for (int k = 0; k < 60; k += (k < 24 ? 1 : 4))
+                for (int count : { 1, 6 }) {
+                    char name[120];
+                    snprintf(name, sizeof(name), "cuvid alloc-failure kind %d at %d x%d", kind, k, count);
+                    g_ctx = name;
+                    cuvid_cfg c = { { { 320, 180, 0 }, { 198, 102, 0 } }, 16, 4, 4, 2, 0, 1, (k & 1) ? OUT_PINNED : OUT_PAGEABLE, false, 0, 0, 0, true };
+                    g_arm_kind = kind; g_arm_k = k; g_arm_count = count;
+                    run_cuvid(c, 700u + (unsigned)k, 1, fake_lib);
+                    g_arm_kind = -1; g_arm_count = 1;
+                }
         for (unsigned seed = 1; seed <= 25; seed++) {
             char name[100];
             snprintf(name, sizeof(name), "cuvid random-progress seed %u", seed);
