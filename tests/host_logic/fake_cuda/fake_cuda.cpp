@@ -61,6 +61,13 @@ struct sim {
 sim &S()
 {
     static sim s;
+    static bool configured = false;
+    if (!configured) {                                      /* programs that never call fake_cuda_reset: from the environment */
+        configured = true;
+        if (const char *e = getenv("FAKE_CUDA_LAZINESS")) s.laziness = atoi(e);
+        if (const char *e = getenv("FAKE_CUDA_SEED")) s.rng.seed((unsigned)atoi(e));
+        if (const char *e = getenv("FAKE_CUDA_DEVICES")) s.n_devices = atoi(e);
+    }
     return s;
 }
 

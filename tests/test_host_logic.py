@@ -181,3 +181,37 @@ def test_the_simulator_catches_injected_ordering_bugs(tmp_path, sim_plain, name)
     _run(["g++", "-g"] + objs + ["-rdynamic", "-ldl", "-lpthread", "-o", exe])
     p = subprocess.run([exe, lib, scenario], capture_output=True, text=True, timeout=900)
     assert p.returncode != 0 and "FAIL" in p.stdout, "mutation survived: " + name
+
+
+REF_PROGRAM = "/root/reference/test_nv_dec/test_nv_dec.cpp"
+
+
+@pytest.mark.skipif(not os.path.exists(REF_PROGRAM), reason="/root/reference is not mounted")
+@pytest.mark.parametrize("laziness", [0, 1, 2])
+def test_reference_test_program_on_the_simulator(sim_plain, tmp_path, laziness):
+    """The reference's own test_nv_dec.cpp, unmodified and compiled in place, linked with the host layer on the CUDA
+    simulator: its NAL splitter and decode / output loop (test_nv_dec.cpp:30-86,163-259) drive jm_nvdec_* to the end of
+    a stream for the fake NVDEC library, whatever the timing of the streams underneath."""
+    import re
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import fake_stream as FS
+    base_dir, lib = sim_plain
+    o = str(tmp_path / "ref_program.o")
+    shim = os.path.join(ROOT, "tests", "ref_driver", "shim")
+    _run(["g++", "-std=gnu++11", "-fpermissive", "-w", "-O1", "-include", os.path.join(shim, "redirect.h"), "-I", shim,
+          "-I", os.path.join(ROOT, "oracle", "ref_shim"), "-I", os.path.join(ROOT, "include"), "-c", REF_PROGRAM, "-o", o])
+    objs = [os.path.join(base_dir, f) for f in os.listdir(base_dir) if f.endswith(".o") and f != "delivery_sim_test.cpp.o"] + [o]
+    exe = str(tmp_path / "test_nv_dec_sim")
+    _run(["g++"] + objs + ["-rdynamic", "-ldl", "-lpthread", "-o", exe])
+    w, h, n = 320, 180, 23
+    rng = np.random.default_rng(5)
+    stream = np.concatenate([FS.sequence_header(w, h)] + [FS.picture(rng.integers(0, 256, w * h * 3 // 2, dtype=np.uint8)) for _ in range(n)])
+    path = tmp_path / "stream.264"
+    stream.tofile(path)
+    env = dict(os.environ, JM_TEST_INPUT=str(path), JMC_NVCUVID_LIB=lib, FAKE_CUDA_LAZINESS=str(laziness), FAKE_CUDA_SEED="3")
+    p = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    assert re.search(rf"Frame Count:\s+{n}\b", p.stdout) and re.search(rf"Display:\s+{w} x {h}", p.stdout), p.stdout
+    assert "Pixel Format:\tYV12" in p.stdout
