@@ -681,6 +681,19 @@ int main(int argc, char **argv)
                 raw_cfg c = { geoms[3], 1, 14, in, OUT_PAGEABLE, 0, 40, 0, false };
                 run_raw(c, 900u + (unsigned)lazy, lazy);
             }
+        /* full-size frames: payloads staged in pieces by the copy threads, deliveries in 512 KB chunks copied out behind
+         * the DMA; both staging layouts */
+        for (int lazy = 0; lazy <= 2; lazy++)
+            for (int linear = 0; linear <= 1; linear++)
+                for (int out : { (int)OUT_PAGEABLE, (int)OUT_REGISTERED }) {
+                    char name[100];
+                    snprintf(name, sizeof(name), "raw 1080p lazy=%d stage_linear=%d out=%s", lazy, linear, out_name[out]);
+                    g_ctx = name;
+                    setenv("JMC_NVDEC_STAGE_LINEAR", linear ? "1" : "0", 1);
+                    raw_cfg c = { { 1920, 1080, 2048 }, 1, 0, linear ? IN_REGISTERED : IN_PAGEABLE, out, 3, 5, 0, false };
+                    run_raw(c, 950u + (unsigned)lazy, lazy);
+                    unsetenv("JMC_NVDEC_STAGE_LINEAR");
+                }
         /* many seeds of the random-progress mode on the calling convention the reference uses */
         for (unsigned seed = 1; seed <= 40; seed++) {
             char name[100];
