@@ -646,6 +646,69 @@ static void run_fuzz(unsigned seed, int laziness)
     fake_cuda_reset(seed, laziness, 2);
 }
 
+/* ---- the jmc_* runtime layer: contexts, memory, events, timed launches, the link probe, error returns ---------------- */
+static void run_runtime(unsigned seed, int laziness)
+{
+    fake_cuda_reset(seed, laziness, 3);
+    cudaSetDevice(2);
+    const fake_cuda_counts base = fake_cuda_live();
+    jmc_ctx *ctx = nullptr;
+    CHECK(jmc_device_count() == 3 && jmc_current_device() == 2, "device count / current device");
+    CHECK(jmc_ctx_create(5, &ctx) == JMC_ERR_NO_DEVICE && ctx == nullptr, "bad device id");
+    CHECK(jmc_ctx_create(0, nullptr) == JMC_ERR_INVALID, "NULL out");
+    CHECK(jmc_ctx_create(1, &ctx) == JMC_OK && ctx, "ctx_create (%s)", jmc_last_error());
+    CHECK(jmc_current_device() == 2, "ctx_create left device %d current", jmc_current_device());
+    CHECK(jmc_ctx_device(ctx) == 1 && jmc_ctx_sm_count(ctx) == 148 && jmc_ctx_stream(ctx, 0) && jmc_ctx_stream(ctx, 2) && !jmc_ctx_stream(ctx, 3), "ctx queries");
+    const geom g = { 322, 180, 384 };
+    const size_t surf_bytes = (size_t)g.pitch * g.h * 3 / 2, tight = (size_t)g.w * g.h * 3 / 2;
+    const int n = 4;
+    void *d_in = nullptr, *d_out = nullptr, *h = nullptr, *dp = nullptr;
+    size_t pitch = 0;
+    CHECK(jmc_alloc_device(ctx, surf_bytes * n, &d_in) == JMC_OK && jmc_alloc_device(ctx, tight * n, &d_out) == JMC_OK, "alloc_device");
+    CHECK(jmc_alloc_pitched(ctx, 100, 7, &dp, &pitch) == JMC_OK && pitch >= 100, "alloc_pitched");
+    CHECK(jmc_alloc_host(ctx, tight * n, 1, &h) == JMC_OK, "alloc_host");
+    CHECK(jmc_alloc_device(ctx, 16, nullptr) == JMC_ERR_INVALID && jmc_alloc_device(nullptr, 16, &dp) == JMC_ERR_INVALID, "NULL arguments");
+    std::vector<std::vector<uint8_t>> want;
+    for (int f = 0; f < n; f++) {
+        const std::vector<uint8_t> s = surface(g, seed * 13 + (unsigned)f);
+        want.push_back(expected(s, g, 1));
+        CHECK(jmc_memcpy_h2d(ctx, (uint8_t *)d_in + (size_t)f * surf_bytes, s.data(), surf_bytes) == JMC_OK, "h2d");
+    }
+    CHECK(jmc_memset_device(ctx, d_out, 0xA5, tight * n) == JMC_OK, "memset");
+    jmc_job j;
+    memset(&j, 0, sizeof(j));
+    CHECK(jmc_job_nvdec(&j, g.w, g.h, g.pitch, 1) == JMC_OK && jmc_job_nvdec(&j, g.w, g.h, g.w - 1, 1) == JMC_ERR_INVALID, "job filler");
+    jmc_job_nvdec(&j, g.w, g.h, g.pitch, 1);
+    j.n_frames = n; j.surf.base = d_in; j.surf.stride = surf_bytes; j.tight.base = d_out; j.tight.stride = tight;
+    CHECK(jmc_job_algorithmic_bytes(&j) == (int64_t)(2 * tight), "algorithmic bytes of NV12->I420 = 3*w*h");
+    jmc_event *e0 = nullptr, *e1 = nullptr;
+    CHECK(jmc_event_create(ctx, &e0) == JMC_OK && jmc_event_create(ctx, &e1) == JMC_OK, "events");
+    CHECK(jmc_event_record(ctx, e0, 0) == JMC_OK && jmc_event_record(ctx, e0, 3) == JMC_ERR_INVALID, "event_record");
+    const uint64_t l0 = jmc_ctx_launch_count(ctx);
+    CHECK(jmc_convert(ctx, &j, nullptr) == JMC_OK, "convert");
+    CHECK(jmc_event_record(ctx, e1, 0) == JMC_OK, "event_record");
+    float ms = -1.f;
+    CHECK(jmc_event_elapsed_ms(ctx, e0, e1, &ms) == JMC_OK && ms >= 0.f, "elapsed");
+    CHECK(jmc_memcpy_d2h(ctx, h, d_out, tight * n) == JMC_OK, "d2h");
+    for (int f = 0; f < n; f++) CHECK(memcmp((uint8_t *)h + (size_t)f * tight, want[(size_t)f].data(), tight) == 0, "converted frame %d", f);
+    CHECK(jmc_convert_timed(ctx, &j, 3, &ms) == JMC_OK && ms > 0.f && jmc_convert_timed(ctx, &j, 0, &ms) == JMC_ERR_INVALID, "convert_timed");
+    CHECK(jmc_ctx_launch_count(ctx) == l0 + 4, "launch count");
+    jmc_link_rates r;
+    for (int mode : { 1, 2, 3, 7 })
+        CHECK(jmc_link_probe(ctx, 1 << 16, 3, mode, &r) == JMC_OK && ((mode & 1) == 0 || r.h2d_gbs > 0) && ((mode & 2) == 0 || r.d2h_gbs > 0), "link probe mode %d", mode);
+    CHECK(jmc_link_probe(ctx, 1 << 16, -3, 3, &r) == JMC_OK && r.h2d_gbs > 0 && r.d2h_gbs > 0, "link probe over a window");
+    CHECK(jmc_link_probe(ctx, 0, 3, 3, &r) == JMC_ERR_INVALID && jmc_link_probe(ctx, 16, 3, 0, &r) == JMC_ERR_INVALID && jmc_link_probe(ctx, 16, 3, 3, nullptr) == JMC_ERR_INVALID, "link probe arguments");
+    CHECK(jmc_current_device() == 2, "a jmc_* call left device %d current", jmc_current_device());
+    jmc_event_destroy(ctx, e0); jmc_event_destroy(ctx, e1);
+    jmc_free_device(ctx, d_in); jmc_free_device(ctx, d_out); jmc_free_device(ctx, dp); jmc_free_host(ctx, h);
+    CHECK(jmc_ctx_destroy(ctx) == JMC_OK, "ctx_destroy");
+    sim_clean(base, false);
+    /* stream creation fails half way: the context leaves nothing behind */
+    fake_cuda_reset(seed, laziness, 0);
+    CHECK(jmc_device_count() == 0 && jmc_ctx_create(0, &ctx) == JMC_ERR_NO_DEVICE, "no device");
+    fake_cuda_reset(seed, laziness, 2);
+}
+
 static const char *in_name[] = { "host-pageable", "host-pinned", "host-registered", "device", "device+sync", "device+event" };
 static const char *out_name[] = { "pageable", "pinned", "registered", "lazy-pin", "device", "ref" };
 
@@ -834,6 +897,15 @@ int main(int argc, char **argv)
             g_ctx = name;
             cuvid_cfg c = { { { 200, 120, 0 }, { 64, 48, 0 } }, 20, 1 + (int)(seed % 8), 1 + (int)(seed % 8), (int)(seed % 5), (int)(seed % 3), (int)(seed & 1), OUT_PAGEABLE, false };
             run_cuvid(c, seed, 1, fake_lib);
+        }
+    }
+
+    if (want_run("runtime")) {
+        for (int lazy = 0; lazy <= 2; lazy++) {
+            char name[100];
+            snprintf(name, sizeof(name), "runtime lazy=%d", lazy);
+            g_ctx = name;
+            run_runtime(21, lazy);
         }
     }
 

@@ -111,7 +111,7 @@ def sim_sanitized(tmp_path_factory):
     return _build_sim(str(tmp_path_factory.mktemp("sim_san")), flags)
 
 
-@pytest.mark.parametrize("scenario", ["raw", "cuvid", "nvenc", "alloc-failure", "multi", "pipeline", "threads", "fuzz"])
+@pytest.mark.parametrize("scenario", ["raw", "cuvid", "nvenc", "alloc-failure", "multi", "pipeline", "threads", "fuzz", "runtime"])
 def test_host_layer_on_the_cuda_simulator(sim_sanitized, scenario):
     """jm_nv_dec.cu / jmnv_enc.cu / jmc_runtime.cu, unchanged, through the public C API on a CUDA runtime simulator whose
     streams run work as late as CUDA allows (only when waited for / at random moments / at once): every frame against
