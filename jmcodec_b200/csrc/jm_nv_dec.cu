@@ -881,7 +881,7 @@ int raw_packet(nvdec_b200 *c, const unsigned char *buf, int len)
                 if (er == cudaSuccess) er = cudaMemcpyAsync(c->pool[slot] + head, blo, body, cudaMemcpyHostToDevice, st);
                 if (er == cudaSuccess && tail) { memcpy(e + 4096, bhi, tail); er = cudaMemcpyAsync(c->pool[slot] + head + body, e + 4096, tail, cudaMemcpyHostToDevice, st); }
                 if (er == cudaSuccess) er = cudaStreamSynchronize(st);
-                if (er != cudaSuccess) { cudaGetLastError(); return -1; }
+                if (er != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(st); return -1; }    /* nothing of ours may still be reading in_buf */
             } else if (pinned) {
                 /* pinned / registered payload: DMA straight out of the caller's buffer, complete before returning */
                 if (cudaMemcpy2DAsync(c->pool[slot], (size_t)h.pitch, src, (size_t)h.pitch, wbytes, rows, cudaMemcpyHostToDevice, st) != cudaSuccess) { cudaGetLastError(); return -1; }
@@ -1296,7 +1296,7 @@ static int output_frame_impl(unsigned char *out_buf, int *out_len, handle_nvdec 
             if (er == cudaSuccess && tail) er = cudaMemcpyAsync(c->h_edge + 4096, s.d_tight + head + body, tail, cudaMemcpyDeviceToHost, ds);
             if (er == cudaSuccess) er = cudaEventRecord(s.direct, ds);
             if (er == cudaSuccess) er = cudaEventSynchronize(s.direct);
-            if (er != cudaSuccess) { cudaGetLastError(); return -1; }
+            if (er != cudaSuccess) { cudaGetLastError(); cudaStreamSynchronize(ds); return -1; }       /* no copy into out_buf outlives the call */
             if (head) memcpy(out_buf, c->h_edge, head);
             if (tail) memcpy(bhi, c->h_edge + 4096, tail);
         } else if (kind != MEM_PAGEABLE) {
@@ -1307,7 +1307,11 @@ static int output_frame_impl(unsigned char *out_buf, int *out_len, handle_nvdec 
             cudaStream_t ds = delivery_stream(c);
             if (cudaEventSynchronize(c->ring[s.conv_slot >= 0 ? s.conv_slot : c->cur].converted) != cudaSuccess) { cudaGetLastError(); return -1; }   /* launch done: the copy never waits on the device */
             if (cudaMemcpyAsync(out_buf, s.d_tight, s.total, kind == MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ds) != cudaSuccess) { cudaGetLastError(); return -1; }
-            if (cudaEventRecord(s.direct, ds) != cudaSuccess || cudaEventSynchronize(s.direct) != cudaSuccess) { cudaGetLastError(); return -1; }
+            if (cudaEventRecord(s.direct, ds) != cudaSuccess || cudaEventSynchronize(s.direct) != cudaSuccess) {
+                cudaGetLastError();
+                cudaStreamSynchronize(ds);                                    /* no copy into out_buf outlives the call */
+                return -1;
+            }
         } else {
             /* pageable out_buf (what the reference's callers pass): the frame is (being) prefetched into the pinned
              * ring; copy chunk i out while chunk i+1 is still in flight */

@@ -25,6 +25,7 @@
 
 extern std::atomic<int> g_fake_launches, g_fake_frames, g_fake_max_batch;
 static int g_arm_kind = -1, g_arm_k = 0, g_arm_count = 1;      /* allocation failure(s) to arm right after the simulator reset */
+static int g_arm_call = -1, g_arm_call_count = 1;             /* enqueue-call failure(s), same */
 
 static std::atomic<int> g_fail{0}, g_checks{0};
 static thread_local std::string g_ctx;
@@ -95,6 +96,7 @@ static int run_raw(const raw_cfg &c, unsigned seed, int laziness)
     cudaSetDevice(0);
     const fake_cuda_counts base = fake_cuda_live();
     if (g_arm_kind >= 0) fake_cuda_fail_alloc(g_arm_kind, g_arm_k, g_arm_count);
+    if (g_arm_call >= 0) fake_cuda_fail_call(g_arm_call, g_arm_call_count);
     const int n = raw_session(c, seed);
     sim_clean(base, false);
     return n;
@@ -135,7 +137,8 @@ static int raw_session(const raw_cfg &c, unsigned seed)
     if (c.out_kind == OUT_REGISTERED && !c.tolerate_errors) CHECK(out_registered == (out_cap >= (64u << 10) + 8192), "registration of a %zu-byte out_buf: %d", out_cap, (int)out_registered);
     CHECK((pkt && out) || c.tolerate_errors, "caller buffers");
     /* device-pointer inputs: a ring of surfaces, as a decoder has; a slot is rewritten only after the frame made from it was fetched */
-    const int n_dsurf = c.delay + 4;
+    /* when frames may be lost the display pipeline can stall, and with it the moment a surface is free again: one surface per frame */
+    const int n_dsurf = c.tolerate_errors ? c.frames : c.delay + 4;
     std::vector<uint8_t *> dsurf;
     cudaStream_t up = nullptr;
     cudaEvent_t up_ev = nullptr;
@@ -171,6 +174,7 @@ static int raw_session(const raw_cfg &c, unsigned seed)
         }
         int dev = -1; cudaGetDevice(&dev);
         CHECK(dev == 0, "output_frame left device %d current", dev);
+        if (getenv("SIM_VERBOSE")) printf("  [%s] output_frame -> %d\n", g_ctx.c_str(), rr);
         if (rr < 0) { CHECK(c.tolerate_errors, "output_frame returned %d (%s)", rr, jmc_last_error()); return; }
         CHECK(rr == (int)tight && len == (int)tight, "output_frame returned %d, len %d, expected %zu", rr, len, tight);
         /* which frame is it?  In order, but frames may be missing when errors are tolerated */
@@ -222,6 +226,7 @@ static int raw_session(const raw_cfg &c, unsigned seed)
         int dev = -1; cudaGetDevice(&dev);
         CHECK(dev == 0, "decode_frame left device %d current", dev);
         CHECK(r == 0 || c.tolerate_errors, "decode_frame returned %d (%s)", r, jmc_last_error());
+        if (getenv("SIM_VERBOSE")) printf("  [%s] frame %d: decode_frame -> %d, got_frame %d%s%s\n", g_ctx.c_str(), f, r, got_frame, r ? "  " : "", r ? jmc_last_error() : "");
         memset(pkt, 0x77, (size_t)len);                                    /* in_buf is the caller's again */
         if (c.in_kind == IN_DEVICE_SYNC && surf_bytes) cudaMemset(dsurf[(size_t)f % dsurf.size()], 0x33, surf_bytes);   /* ... and so is the surface */
         if (got_frame == 1) fetch();
@@ -285,6 +290,7 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
     const fake_cuda_counts base = fake_cuda_live();
     setenv("JMC_NVCUVID_LIB", fake_lib, 1);
     if (g_arm_kind >= 0) fake_cuda_fail_alloc(g_arm_kind, g_arm_k, g_arm_count);
+    if (g_arm_call >= 0) fake_cuda_fail_call(g_arm_call, g_arm_call_count);
     void *fl = dlopen(fake_lib, RTLD_NOW | RTLD_LOCAL);                  /* the same library object the handle loads */
     fake_fail_fn fake_fail = fl ? (fake_fail_fn)dlsym(fl, "fake_nvcuvid_fail") : nullptr;
     fake_stats_fn fake_stats = fl ? (fake_stats_fn)dlsym(fl, "fake_nvcuvid_stats") : nullptr;
@@ -292,7 +298,7 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
     if (!fake_fail || !fake_stats) return;
     fake_stats(nullptr, 1);
     fake_fail(c.fault_what, c.fault_after, c.fault_count);
-    const bool lossy = c.lossy || c.fault_what != 0 || g_arm_kind >= 0;
+    const bool lossy = c.lossy || c.fault_what != 0 || g_arm_kind >= 0 || g_arm_call >= 0;
     char num[16];
     snprintf(num, sizeof(num), "%d", c.parser_delay);
     setenv("JMC_NVDEC_PARSER_DELAY", num, 1);
@@ -301,7 +307,7 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
     jm_nvdec_set_option("map_limit", c.map_limit, h);
     jm_nvdec_set_option("display_delay", c.delay, h);
     int r = jm_nvdec_init(JM_NVDEC_CODEC_AVC, c.fmt, nullptr, 0, h);
-    CHECK(r == 0 || g_arm_kind >= 0, "init with the fake NVDEC library failed: %d (%s)", r, jmc_last_error());
+    CHECK(r == 0 || g_arm_kind >= 0 || g_arm_call >= 0, "init with the fake NVDEC library failed: %d (%s)", r, jmc_last_error());
     if (r != 0) { jm_nvdec_deinit(h); fake_fail(0, 0, 0); dlclose(fl); sim_clean(base, true); return; }
     /* the stream and what must come out of it */
     std::vector<std::vector<uint8_t>> packets, want;
@@ -363,7 +369,7 @@ static void run_cuvid(const cuvid_cfg &c, unsigned seed, int laziness, const cha
     }
     for (int guard = 0; guard < (int)want.size() + 50 && !jm_nvdec_is_exit(h); guard++) {
         int got_frame = 0;
-        jm_nvdec_decode_frame(nullptr, 0, &got_frame, h);
+        if (jm_nvdec_decode_frame(nullptr, 0, &got_frame, h) != 0) saw_drop_report = true;
         if (got_frame == 1) fetch();
     }
     CHECK(jm_nvdec_is_exit(h), "the handle never reported the end of the stream");
@@ -846,6 +852,45 @@ int main(int argc, char **argv)
                         g_arm_kind = -1; g_arm_count = 1;
                         if (count <= 5) CHECK(n >= 20, "only %d of 40 frames were delivered although just %d allocations failed", n, count);
                     }
+    }
+
+    if (want_run("debug-one")) {                                           /* SIM_VERBOSE=1 ./delivery_sim_test lib debug-one <k> <count> <variant> */
+        const int k = argc > 3 ? atoi(argv[3]) : 0, count = argc > 4 ? atoi(argv[4]) : 1, variant = argc > 5 ? atoi(argv[5]) : 0;
+        g_ctx = "debug-one";
+        const int in = variant == 1 ? IN_DEVICE : (variant == 3 ? IN_PINNED : IN_PAGEABLE);
+        const int out = variant == 1 ? OUT_PINNED : (variant == 2 ? OUT_REF : OUT_PAGEABLE);
+        raw_cfg c = { geoms[variant == 2 ? 2 : 0], 1, variant == 0 ? 0 : 2, in, out, 0, 14, 0, true };
+        g_arm_call = k; g_arm_call_count = count;
+        run_raw(c, 8, (k + variant) % 3);
+        g_arm_call = -1;
+    }
+
+    if (want_run("call-failure")) {
+        /* an enqueue-type CUDA call (async copy, event record, stream wait, launch) fails once, or a few times in a row:
+         * frames may be lost and calls may report it -- nothing crashes, leaks, stays mapped or comes out wrong */
+        for (int k = 0; k < 120; k += (k < 40 ? 1 : 3))
+            for (int count : { 1, 4 })
+                for (int variant = 0; variant < 4; variant++) {
+                    char name[100];
+                    snprintf(name, sizeof(name), "call-failure at %d x%d variant %d", k, count, variant);
+                    g_ctx = name;
+                    const int in = variant == 1 ? IN_DEVICE : (variant == 3 ? IN_PINNED : IN_PAGEABLE);
+                    const int out = variant == 1 ? OUT_PINNED : (variant == 2 ? OUT_REF : OUT_PAGEABLE);
+                    raw_cfg c = { geoms[variant == 2 ? 2 : 0], 1, variant == 0 ? 0 : 2, in, out, 0, 14, 0, true };
+                    g_arm_call = k; g_arm_call_count = count;
+                    run_raw(c, 8, (k + variant) % 3);
+                    g_arm_call = -1;
+                }
+        for (int k = 0; k < 200; k += (k < 40 ? 1 : 5))
+            for (int count : { 1, 3 }) {
+                char name[100];
+                snprintf(name, sizeof(name), "cuvid call-failure at %d x%d", k, count);
+                g_ctx = name;
+                cuvid_cfg c = { { { 320, 180, 0 }, { 198, 102, 0 } }, 16, 4, 4, 2, 0, 1, (k & 1) ? OUT_PINNED : OUT_PAGEABLE, false, 0, 0, 0, true };
+                g_arm_call = k; g_arm_call_count = count;
+                run_cuvid(c, 800u + (unsigned)k, k % 3, fake_lib);
+                g_arm_call = -1;
+            }
     }
 
     if (want_run("cuvid")) {

@@ -105,6 +105,11 @@ bool fake_cuda_is_device_range(const void *p, size_t n);
 /* fail `count` allocations of the given kind (0 device, 1 pinned, 2 event) starting with the k-th next one: error-path
  * tests; k < 0 disables */
 void fake_cuda_fail_alloc(int kind, int k, int count = 1);
+/* make `count` ENQUEUE-type calls (async copies / memsets, event records, stream waits, launches) fail with
+ * cudaErrorInvalidValue, starting with the k-th next one; nothing is enqueued by a failing call.  k < 0 disables */
+void fake_cuda_fail_call(int k, int count = 1);
+/* for stand-in launch code: does the armed call failure hit this launch? */
+bool fake_cuda_launch_should_fail();
 /* record a problem from test code that runs as a "kernel" */
 void fake_cuda_complain(const char *msg);
 #endif

@@ -55,6 +55,7 @@ struct sim {
     std::vector<std::string> errors;
     cudaError_t last = cudaSuccess;
     int fail_kind = -1, fail_in = -1, fail_count = 0;
+    int call_fail_in = -1, call_fail_count = 0;
     int depth = 0;
 };
 
@@ -78,6 +79,15 @@ cudaError_t fail(cudaError_t e) { S().last = e; return e; }
 void complain(const std::string &s)
 {
     S().errors.push_back(s);
+}
+
+bool call_should_fail()
+{
+    sim &s = S();
+    if (s.call_fail_in < 0) return false;
+    if (s.call_fail_in > 0) { s.call_fail_in--; return false; }
+    if (s.call_fail_count > 0 && --s.call_fail_count == 0) s.call_fail_in = -1;
+    return true;
 }
 
 bool should_fail(int kind)
@@ -244,6 +254,8 @@ void fake_cuda_reset(unsigned seed, int laziness, int n_devices)
     s.last = cudaSuccess;
     s.fail_kind = s.fail_in = -1;
     s.fail_count = 0;
+    s.call_fail_in = -1;
+    s.call_fail_count = 0;
     /* dead streams / events are only ever forgotten here */
     s.streams.erase(std::remove_if(s.streams.begin(), s.streams.end(), [](const std::unique_ptr<fake_stream> &p) { return !p->alive; }), s.streams.end());
     s.events.erase(std::remove_if(s.events.begin(), s.events.end(), [](const std::unique_ptr<fake_event> &p) { return !p->alive; }), s.events.end());
@@ -282,6 +294,19 @@ bool fake_cuda_is_device_range(const void *p, size_t n)
 {
     LOCK;
     return classify(p, n) == 2;
+}
+
+void fake_cuda_fail_call(int k, int count)
+{
+    LOCK;
+    S().call_fail_in = k;
+    S().call_fail_count = count;
+}
+
+bool fake_cuda_launch_should_fail()
+{
+    LOCK;
+    return call_should_fail();
 }
 
 void fake_cuda_complain(const char *msg)
@@ -459,6 +484,7 @@ cudaError_t cudaStreamWaitEvent(cudaStream_t st, cudaEvent_t e, unsigned)
     LOCK;
     tick();
     if (!valid_stream(st) || !valid_event(e)) { complain("cudaStreamWaitEvent with a dead stream or event"); return fail(cudaErrorInvalidResourceHandle); }
+    if (call_should_fail()) return fail(cudaErrorInvalidValue);
     if (e->recorded == 0 || e->completed >= e->recorded) return cudaSuccess;      /* nothing to wait for */
     op o{ OP_WAIT, nullptr, e, e->recorded, {}, "wait" };
     enqueue(st, std::move(o));
@@ -488,6 +514,7 @@ cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t st)
     LOCK;
     tick();
     if (!valid_stream(st) || !valid_event(e)) { complain("cudaEventRecord with a dead stream or event"); return fail(cudaErrorInvalidResourceHandle); }
+    if (call_should_fail()) return fail(cudaErrorInvalidValue);
     e->recorded++;
     op o{ OP_RECORD, nullptr, e, e->recorded, {}, "record" };
     enqueue(st, std::move(o));
@@ -528,6 +555,7 @@ static cudaError_t copy2d(void *dst, size_t dpitch, const void *src, size_t spit
     tick();
     if (!valid_stream(st)) { complain(std::string(what) + " on a dead stream"); return fail(cudaErrorInvalidResourceHandle); }
     if (width == 0 || height == 0) return cudaSuccess;
+    if (call_should_fail()) return fail(cudaErrorInvalidValue);
     if (dpitch < width || spitch < width) return fail(cudaErrorInvalidValue);
     const size_t dspan = (height - 1) * dpitch + width, sspan = (height - 1) * spitch + width;
     const bool h2d = kind == cudaMemcpyHostToDevice, d2h = kind == cudaMemcpyDeviceToHost;
@@ -572,6 +600,7 @@ cudaError_t cudaMemsetAsync(void *p, int byte, size_t bytes, cudaStream_t st)
     LOCK;
     tick();
     if (!valid_stream(st)) return fail(cudaErrorInvalidResourceHandle);
+    if (call_should_fail()) return fail(cudaErrorInvalidValue);
     check_device_side(p, bytes, "cudaMemsetAsync");
     op o{ OP_WORK, [=] { memset(p, byte, bytes); }, nullptr, 0, { { (uintptr_t)p, (uintptr_t)p + bytes } }, "cudaMemsetAsync" };
     enqueue(st, std::move(o));

@@ -40,6 +40,7 @@ int jmc_launch_job(jmc_ctx *ctx, const jmc_job *job, cudaStream_t stream)
         jmc_set_error("fake launch: op %d is not simulated", j.op);
         return JMC_ERR_INVALID;
     }
+    if (fake_cuda_launch_should_fail()) { jmc_set_error("fake launch: injected launch failure"); return JMC_ERR_CUDA; }
     g_fake_launches++;
     g_fake_frames += j.n_frames;
     for (int seen = g_fake_max_batch.load(); j.n_frames > seen && !g_fake_max_batch.compare_exchange_weak(seen, j.n_frames);) {}
