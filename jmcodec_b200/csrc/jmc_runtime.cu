@@ -556,7 +556,21 @@ int jmc_pipeline_destroy(jmc_pipeline *p)
     return JMC_OK;
 }
 
+static int pipeline_submit_impl(jmc_pipeline *p, const void *host_in, const void *dev_in, void *host_out, void *host_out2, int n_frames);
+
 int jmc_pipeline_submit(jmc_pipeline *p, const void *host_in, const void *dev_in, void *host_out, void *host_out2, int n_frames)
+{
+    const int r = pipeline_submit_impl(p, host_in, dev_in, host_out, host_out2, n_frames);
+    if (r < 0 && p) {
+        /* a submit that failed half way may have queued copies from / to the caller's buffers and will never be waited
+         * for through its slot: nothing of it is left in flight when the error is returned (the message stays) */
+        jmc_device_guard g(p->ctx);
+        if (!g.err) for (int i = 0; i < 3; i++) if (cudaStreamSynchronize(p->ctx->stream[i]) != cudaSuccess) cudaGetLastError();
+    }
+    return r;
+}
+
+static int pipeline_submit_impl(jmc_pipeline *p, const void *host_in, const void *dev_in, void *host_out, void *host_out2, int n_frames)
 {
     if (!p) return JMC_ERR_INVALID;
     JMC_BIND(p->ctx);

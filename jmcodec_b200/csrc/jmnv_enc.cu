@@ -192,13 +192,23 @@ int jm_nvenc_enc_frame(const unsigned char *in_yuv_buf, const int yuv_len, int *
             /* the pool's surfaces are ours: zeroed at init and only ever written here, so zeroing the padding behind a row
              * end again changes nothing -- and saves the kernel the read-merge of every row's last sector */
             j.flags = JMC_JOB_PAD_ZERO;
-            if (jmc_convert(c->ctx, &j, nullptr) != JMC_OK) { s.lock_count = 0; return JM_NVENC_ERR_GENERIC; }
+            if (jmc_convert(c->ctx, &j, nullptr) != JMC_OK) {
+                cudaStreamSynchronize(st);                            /* the upload may still be reading in_yuv_buf */
+                s.lock_count = 0;
+                return JM_NVENC_ERR_GENERIC;
+            }
         }
     } else {                                                          /* ARGB/ABGR, :1083-1097 (pitch honoured) */
         e = cudaMemcpy2DAsync(s.dptr, s.pitch, in_yuv_buf, (size_t)w * 4, (size_t)w * 4, (size_t)h, cudaMemcpyHostToDevice, st);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);              /* in_yuv_buf is consumed before return */
-    if (e != cudaSuccess) { s.lock_count = 0; jmc_cuda_fail(e, "jm_nvenc_enc_frame upload"); return JM_NVENC_ERR_GENERIC; }
+    if (e != cudaSuccess) {
+        jmc_cuda_fail(e, "jm_nvenc_enc_frame upload");
+        cudaStreamSynchronize(st);                                    /* nothing of ours reads in_yuv_buf after we return */
+        cudaGetLastError();
+        s.lock_count = 0;
+        return JM_NVENC_ERR_GENERIC;
+    }
     c->last = idx;
     /* no NVENC: nothing is encoded, so no packet ever becomes ready */
     return 0;

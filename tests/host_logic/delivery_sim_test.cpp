@@ -893,6 +893,92 @@ int main(int argc, char **argv)
             }
     }
 
+    if (want_run("call-failure")) {
+        /* the same under the encoder-input API and the batch pipeline; the caller gives its buffers back right after an error */
+        for (int k = 0; k < 40; k++)
+            for (int fmt : { JM_NVENC_FMT_NV12, JM_NVENC_FMT_YV12, JM_NVENC_FMT_ARGB }) {
+                char name[100];
+                snprintf(name, sizeof(name), "nvenc call-failure at %d fmt 0x%x", k, fmt);
+                g_ctx = name;
+                fake_cuda_reset(3, k % 3, 2);
+                cudaSetDevice(0);
+                const fake_cuda_counts base = fake_cuda_live();
+                handle_nvenc h = jm_nvenc_create_handle();
+                nv_enc_param p;
+                memset(&p, 0, sizeof(p));
+                const geom g = { 322, 180, 0 };
+                p.codec_id = JM_NVENC_CODEC_SURFACE_ONLY; p.src_width = g.w; p.src_height = g.h; p.in_fmt = fmt;
+                if (jm_nvenc_init(&p, h) == JM_NVENC_SUCCESS) {
+                    const bool rgb = fmt == JM_NVENC_FMT_ARGB;
+                    const size_t in_bytes = rgb ? (size_t)g.w * g.h * 4 : (size_t)g.w * g.h * 3 / 2;
+                    void *in = nullptr;
+                    CHECK(jm_nvenc_memory_alloc_host(&in, (int)in_bytes, h) == 0, "pinned input buffer");
+                    fake_cuda_fail_call(k, 2);
+                    for (int f = 0; f < 5 && in; f++) {
+                        std::vector<uint8_t> bytes(in_bytes);
+                        random_bytes(bytes.data(), in_bytes, (uint32_t)(k * 10 + f));
+                        memcpy(in, bytes.data(), in_bytes);
+                        int got = 0;
+                        const int r = jm_nvenc_enc_frame((const unsigned char *)in, (int)in_bytes, &got, h);
+                        memset(in, 0x77, in_bytes);                          /* ours again, success or not */
+                        if (r != 0) continue;
+                        void *d = nullptr; int pitch = 0, rows = 0;
+                        jm_nvenc_peek_surface(&d, &pitch, &rows, h);
+                        std::vector<uint8_t> want((size_t)pitch * rows, 0);
+                        if (rgb) { for (int y = 0; y < g.h; y++) memcpy(&want[(size_t)y * pitch], &bytes[(size_t)y * g.w * 4], (size_t)g.w * 4); }
+                        else jmo_nvenc_upload(bytes.data(), fmt, g.w, g.h, want.data(), pitch);
+                        CHECK(memcmp(d, want.data(), want.size()) == 0, "surface of frame %d differs although enc_frame succeeded", f);
+                        jm_nvenc_release_surface(h);
+                    }
+                    if (in) jm_nvenc_memory_release_host(in, h);
+                }
+                jm_nvenc_deinit(h);
+                sim_clean(base, false);
+            }
+        for (int k = 0; k < 60; k++) {
+            char name[100];
+            snprintf(name, sizeof(name), "pipeline call-failure at %d", k);
+            g_ctx = name;
+            fake_cuda_reset(4, k % 3, 2);
+            cudaSetDevice(0);
+            const fake_cuda_counts base = fake_cuda_live();
+            jmc_ctx *ctx = nullptr;
+            if (jmc_ctx_create(0, &ctx) != JMC_OK) continue;
+            const geom g = { 322, 180, 384 };
+            jmc_job shape;
+            memset(&shape, 0, sizeof(shape));
+            jmc_job_nvdec(&shape, g.w, g.h, g.pitch, 1);
+            shape.n_frames = 2;
+            const size_t surf_bytes = (size_t)g.pitch * g.h * 3 / 2, tight = (size_t)g.w * g.h * 3 / 2;
+            jmc_pipeline *pl = nullptr;
+            if (jmc_pipeline_create(ctx, &shape, surf_bytes, 2, &pl) == JMC_OK) {
+                fake_cuda_fail_call(k, 1);
+                for (int b = 0; b < 6; b++) {
+                    void *hin = nullptr, *hout = nullptr;
+                    jmc_alloc_host(ctx, surf_bytes * 2, 0, &hin);
+                    jmc_alloc_host(ctx, tight * 2 + 8, 0, &hout);
+                    if (!hin || !hout) { if (hin) jmc_free_host(ctx, hin); if (hout) jmc_free_host(ctx, hout); continue; }
+                    std::vector<std::vector<uint8_t>> want;
+                    for (int f = 0; f < 2; f++) {
+                        const std::vector<uint8_t> s = surface(g, (uint32_t)(k * 100 + b * 2 + f));
+                        memcpy((uint8_t *)hin + (size_t)f * surf_bytes, s.data(), surf_bytes);
+                        want.push_back(expected(s, g, 1));
+                    }
+                    const int slot = jmc_pipeline_submit(pl, hin, nullptr, hout, nullptr, 2);
+                    if (slot >= 0) {
+                        CHECK(jmc_pipeline_wait(pl, slot) == JMC_OK, "wait");
+                        for (int f = 0; f < 2; f++) CHECK(memcmp((uint8_t *)hout + (size_t)f * tight, want[(size_t)f].data(), tight) == 0, "batch %d frame %d differs although submit succeeded", b, f);
+                    }
+                    jmc_free_host(ctx, hin);                                /* given back at once, also after a failed submit */
+                    jmc_free_host(ctx, hout);
+                }
+                jmc_pipeline_destroy(pl);
+            }
+            jmc_ctx_destroy(ctx);
+            sim_clean(base, false);
+        }
+    }
+
     if (want_run("cuvid")) {
         struct { int ppp, map_limit, pdelay, delay; } v[] = { { 8, 8, 2, 0 }, { 8, 3, 2, 0 }, { 4, 8, 0, 2 }, { 1, 8, 2, 0 }, { 8, 1, 1, 1 }, { 3, 2, 4, 0 } };
         for (int lazy = 0; lazy <= 2; lazy++)
