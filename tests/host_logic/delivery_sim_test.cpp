@@ -838,6 +838,41 @@ int main(int argc, char **argv)
                     run_raw(c, 5, 1);
                     g_arm_kind = -1;
                 }
+        /* the same for the set-up calls of the pipeline and of the encoder-input API: all or nothing */
+        for (int kind : { 0, 2 })
+            for (int k = 0; k < 16; k++) {
+                char name[100];
+                snprintf(name, sizeof(name), "alloc-failure in set-up calls, kind %d at %d", kind, k);
+                g_ctx = name;
+                fake_cuda_reset(9, 1, 2);
+                cudaSetDevice(0);
+                const fake_cuda_counts base = fake_cuda_live();
+                fake_cuda_fail_alloc(kind, k, 1);
+                jmc_ctx *ctx = nullptr;
+                if (jmc_ctx_create(0, &ctx) == JMC_OK) {
+                    jmc_job shape;
+                    memset(&shape, 0, sizeof(shape));
+                    jmc_job_nvdec(&shape, 64, 36, 64, 1);
+                    shape.n_frames = 2;
+                    jmc_pipeline *pl = nullptr;
+                    const int r = jmc_pipeline_create(ctx, &shape, 64 * 36 * 3 / 2, 3, &pl);
+                    CHECK((r == JMC_OK) == (pl != nullptr), "pipeline_create returned %d with pipeline %p", r, (void *)pl);
+                    if (pl) jmc_pipeline_destroy(pl);
+                    jmc_ctx_destroy(ctx);
+                }
+                handle_nvenc e = jm_nvenc_create_handle();
+                nv_enc_param p;
+                memset(&p, 0, sizeof(p));
+                p.codec_id = JM_NVENC_CODEC_SURFACE_ONLY; p.src_width = 64; p.src_height = 36; p.in_fmt = JM_NVENC_FMT_YV12;
+                const int r = jm_nvenc_init(&p, e);
+                if (r != JM_NVENC_SUCCESS) {                                /* a failed init holds nothing; the handle can be initialised again */
+                    const fake_cuda_counts mid = fake_cuda_live();
+                    CHECK(mid.device == base.device && mid.streams == base.streams, "a failed jm_nvenc_init kept %zu device allocations / %zu streams", mid.device - base.device, mid.streams - base.streams);
+                    CHECK(jm_nvenc_init(&p, e) == JM_NVENC_SUCCESS, "init after a failed init");
+                }
+                jm_nvenc_deinit(e);
+                sim_clean(base, false);
+            }
         /* an allocator that stays empty for a while: many failures in a row, then memory is back */
         for (int kind = 0; kind < 2; kind++)
             for (int k : { 3, 9, 14, 22 })
