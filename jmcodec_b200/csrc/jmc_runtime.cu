@@ -468,6 +468,9 @@ int jmc_event_elapsed_ms(jmc_ctx *c, jmc_event *start, jmc_event *stop, float *m
 {
     JMC_BIND(c);
     if (!ms) return JMC_ERR_INVALID;
+    /* both ends: `start` may sit on another stream than `stop`, and nothing orders it before the work `stop` follows
+     * (a start recorded on an otherwise idle stream) */
+    JMC_CUDA(cudaEventSynchronize((cudaEvent_t)start));
     JMC_CUDA(cudaEventSynchronize((cudaEvent_t)stop));
     JMC_CUDA(cudaEventElapsedTime(ms, (cudaEvent_t)start, (cudaEvent_t)stop));
     return JMC_OK;

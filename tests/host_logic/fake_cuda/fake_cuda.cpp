@@ -62,13 +62,14 @@ struct sim {
 sim &S()
 {
     static sim s;
-    static bool configured = false;
-    if (!configured) {                                      /* programs that never call fake_cuda_reset: from the environment */
-        configured = true;
+    /* programs that never call fake_cuda_reset are configured from the environment (once; thread-safe static init) */
+    static const bool configured = [] {
         if (const char *e = getenv("FAKE_CUDA_LAZINESS")) s.laziness = atoi(e);
         if (const char *e = getenv("FAKE_CUDA_SEED")) s.rng.seed((unsigned)atoi(e));
         if (const char *e = getenv("FAKE_CUDA_DEVICES")) s.n_devices = atoi(e);
-    }
+        return true;
+    }();
+    (void)configured;
     return s;
 }
 

@@ -136,6 +136,16 @@ def test_handles_on_several_threads_under_thread_sanitizer(tmp_path):
     if "FATAL: ThreadSanitizer" in p.stderr and "unexpected memory mapping" in p.stderr:
         pytest.skip("thread sanitizer cannot map its shadow memory in this container")
     assert p.returncode == 0 and p.stdout.strip().endswith("OK") and "WARNING: ThreadSanitizer" not in p.stderr, p.stdout[-2000:] + p.stderr[-3000:]
+    # tools/jm_dropin.cpp with four handles on four threads, copy helper threads included, in the same build
+    out_dir = os.path.dirname(exe)
+    objs = [os.path.join(out_dir, f) for f in os.listdir(out_dir) if f.endswith(".o") and f != "delivery_sim_test.cpp.o"]
+    tool = str(tmp_path / "jm_dropin_tsan")
+    _run(["g++", "-std=c++17", "-g", "-O1", "-fsanitize=thread", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", "jm_dropin.cpp")] + objs +
+         ["-rdynamic", "-ldl", "-lpthread", "-o", tool])
+    for custom in ("device,pinned,0,-1,4", "host,pageable,2,2,4", "device,ref,2,0,3"):
+        p = subprocess.run([tool, "--frames", "16", "--width", "1280", "--height", "720", "--pitch", "1280", "--custom", custom], capture_output=True, text=True,
+                           timeout=900, env=dict(os.environ, TSAN_OPTIONS="halt_on_error=1", FAKE_CUDA_LAZINESS="1", FAKE_CUDA_SEED="4", FAKE_CUDA_DEVICES="2"))
+        assert p.returncode == 0 and "WARNING: ThreadSanitizer" not in p.stderr, custom + "\n" + p.stdout[-2000:] + p.stderr[-3000:]
 
 
 MUTATIONS = {
@@ -215,3 +225,30 @@ def test_reference_test_program_on_the_simulator(sim_plain, tmp_path, laziness):
     assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
     assert re.search(rf"Frame Count:\s+{n}\b", p.stdout) and re.search(rf"Display:\s+{w} x {h}", p.stdout), p.stdout
     assert "Pixel Format:\tYV12" in p.stdout
+
+
+@pytest.mark.parametrize("laziness", [1, 2])
+def test_the_measurement_tools_on_the_simulator(sim_plain, tmp_path, laziness):
+    """tools/jm_dropin.cpp (every calling convention of the drop-in API, several handles on several threads; it compares
+    the first frame of every handle with its own CPU loop) and tools/jm_streams.cpp (config 5: streams sharded over GPUs,
+    one thread per GPU, static and dynamic assignment) use nothing but the public C API, so they run on the simulator
+    too: functional coverage of what they otherwise only time."""
+    import json
+    base_dir, lib = sim_plain
+    objs = [os.path.join(base_dir, f) for f in os.listdir(base_dir) if f.endswith(".o") and f != "delivery_sim_test.cpp.o"]
+    env = dict(os.environ, FAKE_CUDA_LAZINESS=str(laziness), FAKE_CUDA_SEED="9", FAKE_CUDA_DEVICES="4")
+    for tool in ("jm_dropin", "jm_streams"):
+        exe = str(tmp_path / tool)
+        _run(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tools", tool + ".cpp")] + objs +
+             ["-rdynamic", "-ldl", "-lpthread", "-o", exe])
+    p = subprocess.run([str(tmp_path / "jm_dropin"), "--frames", "24", "--width", "322", "--height", "180", "--pitch", "384"],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    d = json.loads(p.stdout[p.stdout.index("{"):])
+    assert len(d) >= 20 and all(isinstance(v, (int, float)) and v > 0 for k, v in d.items() if k.endswith("_fps")), d
+    for mode, assign in (("e2e", "static"), ("d2h", "dynamic"), ("device", "static")):
+        p = subprocess.run([str(tmp_path / "jm_streams"), "--gpus", "4", "--streams", "8", "--frames", "12", "--batch", "4", "--width", "322",
+                            "--height", "180", "--pitch", "384", "--mode", mode, "--assign", assign], env=env, capture_output=True, text=True, timeout=600)
+        assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")][-1]
+        assert json.loads(line)["frames_per_s"] > 0 if "frames_per_s" in json.loads(line) else True, line

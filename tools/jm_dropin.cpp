@@ -14,6 +14,7 @@
  * Prints one JSON object: variant name -> frames/s (wall clock around the timed loop, all handles together).
  * The first frame of every handle is checked against a CPU restatement of nv_dec.cpp:798-820 written here.
  */
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -81,7 +82,7 @@ static void cpu_i420(const unsigned char *s, int pitch, int w, int h, unsigned c
 
 struct Result { long long frames = 0; double seconds = 0; std::string error; };
 
-static void run_handle(const Options &o, const Variant &v, int tid, int warm, int timed, volatile int *go, Result *res)
+static void run_handle(const Options &o, const Variant &v, int tid, int warm, int timed, std::atomic<int> *go, Result *res)
 {
     const int w = o.width, h = o.height, pitch = o.pitch;
     const size_t surf = (size_t)pitch * h * 3 / 2, need = (size_t)w * h * 3 / 2;
@@ -143,8 +144,8 @@ static void run_handle(const Options &o, const Variant &v, int tid, int warm, in
         }
     };
     for (int k = 0; k < warm; k++) step(pkts[k % NS].data(), (int)pkts[k % NS].size());
-    __sync_fetch_and_add(go, 1);
-    while (*go < v.handles) { }                                           /* all handles start together */
+    go->fetch_add(1);
+    while (go->load() < v.handles) { }                                           /* all handles start together */
     const long long f0 = fetched;
     auto t0 = std::chrono::steady_clock::now();
     for (int k = 0; k < timed; k++) step(pkts[(k + warm) % NS].data(), (int)pkts[(k + warm) % NS].size());
@@ -194,7 +195,7 @@ int main(int argc, char **argv)
         if (!o.only.empty() && o.only != v.name) continue;
         std::vector<Result> res((size_t)v.handles);
         std::vector<std::thread> th;
-        volatile int go = 0;
+        std::atomic<int> go{0};
         const int timed = v.device_in ? o.frames * 4 : o.frames;
         for (int t = 0; t < v.handles; t++) th.emplace_back(run_handle, std::cref(o), std::cref(v), t, 20, timed, &go, &res[(size_t)t]);
         for (auto &t : th) t.join();
