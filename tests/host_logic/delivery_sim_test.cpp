@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <random>
@@ -32,7 +33,8 @@ static thread_local std::string g_ctx;
 #define CHECK(cond, ...)                                                                                         \
     do {                                                                                                         \
         g_checks++;                                                                                              \
-        if (!(cond)) { if (g_fail.load() < 40) { printf("FAIL [%s] line %d: ", g_ctx.c_str(), __LINE__); printf(__VA_ARGS__); printf("\n"); } g_fail++; } \
+        if (!(cond)) { if (g_fail.load() < 40) { printf("FAIL [%s] line %d: ", g_ctx.c_str(), __LINE__); printf(__VA_ARGS__); printf("\n"); } g_fail++; \
+                       if (getenv("SIM_FAIL_FAST")) { printf("FAILED (first failure)\n"); fflush(stdout); _exit(1); } }                     \
     } while (0)
 
 struct geom { int w, h, pitch; };

@@ -79,26 +79,24 @@ def _run(cmd, **kw):
 
 
 def _build_sim(out_dir, flags, nvdec_source=None):
-    """Objects + link of the simulation harness in out_dir; nvdec_source replaces jm_nv_dec.cu (mutation tests)."""
+    """Objects + link of the simulation harness in out_dir; nvdec_source replaces jm_nv_dec.cu (mutation tests).
+    The translation units are compiled side by side."""
+    from concurrent.futures import ThreadPoolExecutor
     os.makedirs(out_dir, exist_ok=True)
-    objs = []
-    _run(["gcc"] + flags + ["-c", os.path.join(ROOT, "oracle", "jm_oracle.c"), "-o", os.path.join(out_dir, "jm_oracle.o")])
-    objs.append(os.path.join(out_dir, "jm_oracle.o"))
+    jobs = [(["gcc"] + flags + ["-c", os.path.join(ROOT, "oracle", "jm_oracle.c")], os.path.join(out_dir, "jm_oracle.o"))]
     for f in PRODUCT:
         src = nvdec_source if (nvdec_source and f == "jm_nv_dec.cu") else os.path.join(CSRC, f)
-        o = os.path.join(out_dir, f + ".o")
-        _run(["g++", "-std=c++17"] + flags + INCLUDES + ["-x", "c++", "-c", src, "-o", o])
-        objs.append(o)
+        jobs.append((["g++", "-std=c++17"] + flags + INCLUDES + ["-x", "c++", "-c", src], os.path.join(out_dir, f + ".o")))
     for f in HARNESS:
-        o = os.path.join(out_dir, os.path.basename(f) + ".o")
-        _run(["g++", "-std=c++17"] + flags + INCLUDES + ["-c", f, "-o", o])
-        objs.append(o)
-    exe = os.path.join(out_dir, "delivery_sim_test")
-    _run(["g++"] + flags + objs + ["-rdynamic", "-ldl", "-lpthread", "-o", exe])
+        jobs.append((["g++", "-std=c++17"] + flags + INCLUDES + ["-c", f], os.path.join(out_dir, os.path.basename(f) + ".o")))
     # the fake NVDEC library of the GPU tests, built against the simulator; its cuda* calls bind to the executable's
     lib = os.path.join(out_dir, "libfake_nvcuvid_sim.so")
-    _run(["g++", "-std=c++17"] + flags + ["-shared", "-fPIC", "-I", os.path.join(HL, "fake_cuda"), "-I", CSRC, "-x", "c++",
-          os.path.join(ROOT, "tests", "fake_nvcuvid", "fake_nvcuvid.cu"), "-o", lib])
+    jobs.append((["g++", "-std=c++17"] + flags + ["-shared", "-fPIC", "-I", os.path.join(HL, "fake_cuda"), "-I", CSRC, "-x", "c++",
+                  os.path.join(ROOT, "tests", "fake_nvcuvid", "fake_nvcuvid.cu")], lib))
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        list(ex.map(lambda j: _run(j[0] + ["-o", j[1]]), jobs))
+    exe = os.path.join(out_dir, "delivery_sim_test")
+    _run(["g++"] + flags + [o for _, o in jobs if o.endswith(".o")] + ["-rdynamic", "-ldl", "-lpthread", "-o", exe])
     return exe, lib
 
 
@@ -111,18 +109,32 @@ def sim_sanitized(tmp_path_factory):
     return _build_sim(str(tmp_path_factory.mktemp("sim_san")), flags)
 
 
-@pytest.mark.parametrize("scenario", ["raw", "cuvid", "nvenc", "alloc-failure", "multi", "pipeline", "threads", "fuzz", "runtime", "call-failure"])
-def test_host_layer_on_the_cuda_simulator(sim_sanitized, scenario):
+SCENARIOS = ["raw", "cuvid", "nvenc", "alloc-failure", "multi", "pipeline", "threads", "fuzz", "runtime", "call-failure"]
+
+
+@pytest.fixture(scope="module")
+def sim_runs(sim_sanitized):
+    """All scenarios are started at once, one process each (they are independent); every test collects its own."""
+    exe, lib = sim_sanitized
+    env = dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1")
+    procs = {sc: subprocess.Popen([exe, lib, sc], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env) for sc in SCENARIOS}
+    yield procs
+    for p in procs.values():
+        if p.poll() is None:
+            p.kill()
+
+
+@pytest.mark.parametrize("scenario", SCENARIOS)
+def test_host_layer_on_the_cuda_simulator(sim_runs, scenario):
     """jm_nv_dec.cu / jmnv_enc.cu / jmc_runtime.cu, unchanged, through the public C API on a CUDA runtime simulator whose
     streams run work as late as CUDA allows (only when waited for / at random moments / at once): every frame against
     the oracle for every input kind x out_buf kind x display delay, the NVDEC front-end against the fake library
     (batch drain, map limit, format change, overflow), the encoder-input API, an allocation failure at every
     allocation site, failing enqueue-type CUDA calls (copies, event records, stream waits, launches), five handles interleaved on one device, the jmc_pipeline_* batch pipeline, four threads with a
     handle each, malformed packets and calls on missing / uninitialised handles; no leak, no free under pending work, caller's device restored -- under ASan + UBSan."""
-    exe, lib = sim_sanitized
-    p = subprocess.run([exe, lib, scenario], capture_output=True, text=True, timeout=900,
-                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1"))
-    assert p.returncode == 0 and p.stdout.strip().endswith("OK"), p.stdout[-3000:] + p.stderr[-3000:]
+    p = sim_runs[scenario]
+    out, err = p.communicate(timeout=900)
+    assert p.returncode == 0 and out.strip().endswith("OK"), out[-3000:] + err[-3000:]
 
 
 def test_handles_on_several_threads_under_thread_sanitizer(tmp_path):
@@ -189,7 +201,7 @@ def test_the_simulator_catches_injected_ordering_bugs(tmp_path, sim_plain, name)
     objs = [os.path.join(base_dir, f) for f in os.listdir(base_dir) if f.endswith(".o") and f != "jm_nv_dec.cu.o"] + [o]
     exe = str(tmp_path / "mutant")
     _run(["g++", "-g"] + objs + ["-rdynamic", "-ldl", "-lpthread", "-o", exe])
-    p = subprocess.run([exe, lib, scenario], capture_output=True, text=True, timeout=900)
+    p = subprocess.run([exe, lib, scenario], capture_output=True, text=True, timeout=900, env=dict(os.environ, SIM_FAIL_FAST="1"))
     assert p.returncode != 0 and "FAIL" in p.stdout, "mutation survived: " + name
 
 
