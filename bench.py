@@ -223,6 +223,20 @@ def make_inputs(op, w, h, pitch, rank):
     return [synth.nv12_surface(w, h, pitch, rank, f) for f in range(N_DISTINCT)]
 
 
+def cpu_description():
+    """What SURVEY.md 8d wants next to every CPU figure: the CPU model and how the reference code was compiled."""
+    model = "unknown"
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.lower().startswith("model name"):
+                model = ln.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return {"cpu_model": model,
+            "compiler_flags": "g++ -std=gnu++11 -fpermissive -O2 (the reference's MSVC Release /O2 'MaxSpeed'); oracle/Makefile"}
+
+
 def cpu_reference_fps(w, h, pitch, frames, threads, surfs=None):
     """Time the reference's own CPU function (oracle/_ref, else the C port) on `frames` calls."""
     import oracle
@@ -261,9 +275,9 @@ def run_reference_arm(args, name):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3 / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": run_config(name, args.gpus),
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": chk.kind,
-                         "sample": f"{args.steps} steps x {n} frames, jm_nvdec_output_frame out_fmt=1, one handle per thread, "
-                                   f"{N_DISTINCT} distinct surfaces"},
+        "cpu_baseline": dict({"value": fps, "unit": "frames/s", "cores": threads, "kind": chk.kind,
+                              "sample": f"{args.steps} steps x {n} frames, jm_nvdec_output_frame out_fmt=1, one handle per thread, "
+                                        f"{N_DISTINCT} distinct surfaces"}, **cpu_description()),
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -560,6 +574,7 @@ def main():
             cpu = {"value": fN, "unit": "frames/s", "cores": threads, "kind": kind, "value_1thread": f1,
                    "sample": f"jm_nvdec_output_frame out_fmt=1 on {w}x{h} pitch {pitch}: 1500 frames on 1 thread, "
                              f"{nfr} frames on {threads} threads (one handle per thread), {N_DISTINCT} distinct surfaces"}
+            cpu.update(cpu_description())
             try:
                 import oracle
                 S = np.stack(distinct)

@@ -29,6 +29,7 @@ def test_reference_arm_line():
     assert d["config"]["workload"] == "nv12_to_i420_1080p_x300_pitch2048" and "model" not in d["config"]
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("reference", "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert cb["cpu_model"] and "-O2" in cb["compiler_flags"]                # CPU model and compiler flags beside the CPU figure
     assert d["e2e"] == {"value": d["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["value"] > 100
 
